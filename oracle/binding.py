@@ -1,0 +1,156 @@
+"""oracle/binding.py — TEST INFRASTRUCTURE: ctypes binding of the CPU oracle (oracle/liblfba_oracle.so) and of
+the reference functors compiled in place (oracle/_ref/libref_functor.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+The product package (lifcal_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from lifcal_b200 import capi  # noqa: E402  (struct mirrors only)
+
+c_double_p = C.POINTER(C.c_double)
+BLOCK_FN = C.CFUNCTYPE(C.c_int, C.c_uint32, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double,
+                       c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p)
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liblfba_oracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built (make -C oracle)")
+        L = C.CDLL(path)
+        L.oracle_eval.argtypes = [C.POINTER(capi.Problem), c_double_p, c_double_p, c_double_p, c_double_p,
+                                  c_double_p, c_double_p, c_double_p, c_double_p, C.POINTER(capi.ReprojStats),
+                                  C.c_double, C.c_int, C.c_void_p]
+        L.oracle_solve.argtypes = [C.POINTER(capi.Problem), C.POINTER(capi.Options), c_double_p, c_double_p,
+                                   c_double_p, C.POINTER(capi.Summary), C.c_int, C.c_double, C.c_void_p]
+        L.oracle_time_eval.argtypes = [C.POINTER(capi.Problem), c_double_p, c_double_p, c_double_p, C.c_int,
+                                       C.c_int, c_double_p]
+        L.oracle_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own functors (None if oracle/_ref was not built)."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libref_functor.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_block_eval.argtypes = [C.c_uint32, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double,
+                                     c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                     c_double_p]
+        R.ref_block_eval.restype = C.c_int
+        R.ref_distance_eval.argtypes = [C.c_double, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p]
+        R.ref_distance_eval.restype = C.c_int
+        R.ref_project_point.argtypes = [c_double_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        c_double_p, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int,
+                                        c_double_p]
+        R.ref_pose_matrix.argtypes = [c_double_p, c_double_p]
+        _ref = R
+    return _ref
+
+
+def ref_block_fn_ptr():
+    R = ref_lib()
+    if R is None:
+        return None
+    return C.cast(R.ref_block_eval, C.c_void_p)
+
+
+def default_options(**kw) -> capi.Options:
+    """The reference's solver options (src/CameraCalibration.cpp:955-962) over Ceres 2.1.0 defaults."""
+    o = capi.Options()
+    o.max_num_iterations = 200
+    o.function_tolerance = 1e-6
+    o.parameter_tolerance = 1e-8
+    o.gradient_tolerance = 1e-10
+    o.initial_trust_region_radius = 1e4
+    o.max_trust_region_radius = 1e16
+    o.min_trust_region_radius = 1e-32
+    o.min_relative_decrease = 1e-3
+    o.min_lm_diagonal = 1e-6
+    o.max_lm_diagonal = 1e32
+    o.max_num_consecutive_invalid_steps = 5
+    o.loss_scale = 0.5
+    o.minimizer_progress_to_stdout = 0
+    o.device = -1
+    o.num_gpus = 1
+    o.profile = 0
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def evaluate(pa: capi.ProblemArrays, camera, views, points, jacobians=True, threads=0, use_ref=False,
+             inlier_threshold=1.0):
+    L = lib()
+    n = pa.n_obs
+    cam = np.ascontiguousarray(camera, np.float64)
+    vw = np.ascontiguousarray(views, np.float64)
+    pt = np.ascontiguousarray(points, np.float64)
+    res = np.zeros(2 * n)
+    jc = np.zeros((n, 2, 17)) if jacobians else None
+    jv = np.zeros((n, 2, 6)) if jacobians else None
+    jp = np.zeros((n, 2, 3)) if jacobians else None
+    cost = C.c_double(0)
+    st = capi.ReprojStats()
+    p = pa.as_struct()
+    fn = ref_block_fn_ptr() if use_ref else None
+    rc = L.oracle_eval(C.byref(p), capi._dp(cam), capi._dp(vw), capi._dp(pt), capi._dp(res), capi._dp(jc),
+                       capi._dp(jv), capi._dp(jp), C.byref(cost), C.byref(st), inlier_threshold, threads, fn)
+    if rc != 0:
+        raise RuntimeError(f"oracle_eval rc={rc}")
+    return {"residuals": res.reshape(n, 2), "jac_camera": jc, "jac_view": jv, "jac_point": jp,
+            "cost": cost.value,
+            "stats": {"std_x": st.std_x, "std_y": st.std_y, "mae_x": st.mae_x, "mae_y": st.mae_y,
+                      "num_points": st.num_points, "num_inliers": st.num_inliers}}
+
+
+def solve(pa: capi.ProblemArrays, camera, views, points, options=None, threads=0, max_seconds=0.0,
+          use_ref=False):
+    """Returns (camera, views, points, summary_dict); inputs are not modified."""
+    L = lib()
+    cam = np.array(camera, np.float64, copy=True)
+    vw = np.array(views, np.float64, copy=True)
+    pt = np.array(points, np.float64, copy=True)
+    o = options if options is not None else default_options()
+    s, rows = capi.new_summary(max(8, o.max_num_iterations + 8))
+    p = pa.as_struct()
+    fn = ref_block_fn_ptr() if use_ref else None
+    rc = L.oracle_solve(C.byref(p), C.byref(o), capi._dp(cam), capi._dp(vw), capi._dp(pt), C.byref(s), threads,
+                        max_seconds, fn)
+    d = capi.summary_to_dict(s, rows)
+    d["status"] = rc
+    return cam, vw, pt, d
+
+
+def time_eval(pa: capi.ProblemArrays, camera, views, points, reps=1, threads=0) -> float:
+    L = lib()
+    sec = C.c_double(0)
+    p = pa.as_struct()
+    cam = np.ascontiguousarray(camera, np.float64)
+    vw = np.ascontiguousarray(views, np.float64)
+    pt = np.ascontiguousarray(points, np.float64)
+    rc = L.oracle_time_eval(C.byref(p), capi._dp(cam), capi._dp(vw), capi._dp(pt), reps, threads, C.byref(sec))
+    if rc != 0:
+        raise RuntimeError(f"oracle_time_eval rc={rc}")
+    return sec.value
+
+
+def max_threads() -> int:
+    return int(lib().oracle_max_threads())

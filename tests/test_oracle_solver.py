@@ -1,0 +1,101 @@
+"""CPU tests (no GPU): the oracle's Ceres-2.1.0-equivalent LM loop.
+ - reproduces the committed iteration tables (tests/golden/solver_small.json, generated with the REFERENCE
+   functor plugged into the loop) with its own restated functor
+ - Ceres trust-region invariants on the logged rows
+The LM loop itself is "parity unpinned" (Ceres is not available here); these tests pin it against regressions
+and against the documented semantics."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from lifcal_b200 import capi
+from oracle import binding as ob
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "solver_small.json")
+
+
+def _cases():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", list(_cases().keys()))
+def test_solver_reproduces_golden_tables(built, name):
+    case = _cases()[name]
+    sc = capi.make_scene(None, **case["scene"])
+    assert sc.problem.n_obs == case["n_obs"]
+    cam, vw, pt, s = ob.solve(sc.problem, sc.camera_init, sc.views_init, sc.points_init, threads=2)
+    assert s["num_iterations"] == case["num_iterations"]
+    assert s["stop_reason"] == case["stop_reason"]
+    for r, gr in zip(s["iterations"], case["rows"]):
+        assert r["iteration"] == gr["iteration"]
+        assert r["step_is_successful"] == gr["step_is_successful"]
+        assert abs(r["cost"] - gr["cost"]) <= 1e-9 * abs(gr["cost"])
+        assert abs(r["trust_region_radius"] - gr["trust_region_radius"]) <= 1e-6 * gr["trust_region_radius"]
+    assert abs(s["final_cost"] - case["final_cost"]) <= 1e-9 * case["final_cost"]
+    assert np.allclose(cam, case["camera"], rtol=1e-7, atol=1e-12)
+    assert np.allclose(vw, case["views"], rtol=1e-6, atol=1e-9)
+    assert np.allclose(pt[:30], case["points_head"], rtol=1e-7, atol=1e-7)
+
+
+def test_trust_region_invariants(built):
+    sc = capi.make_scene(None, n_points=80, n_frames=5, n_constraints=2, seed=99, init_intrinsics_rel=2e-3)
+    cam, vw, pt, s = ob.solve(sc.problem, sc.camera_init, sc.views_init, sc.points_init, threads=2)
+    rows = s["iterations"]
+    assert rows[0]["iteration"] == 0 and rows[0]["trust_region_radius"] == 1e4
+    assert s["initial_cost"] == rows[0]["cost"]
+    cost = rows[0]["cost"]
+    radius = 1e4
+    dec = 2.0
+    for r in rows[1:]:
+        if r["step_is_successful"]:
+            assert r["cost"] < cost
+            assert r["relative_decrease"] > 1e-3
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * r["relative_decrease"] - 1.0) ** 3))
+            dec = 2.0
+            cost = r["cost"]
+        else:
+            radius /= dec
+            dec *= 2.0
+        assert abs(r["trust_region_radius"] - radius) <= 1e-12 * radius
+    assert abs(s["final_cost"] - cost) <= 1e-15 * cost
+    # unmodified inputs, outputs differ
+    assert not np.array_equal(cam, sc.camera_init)
+
+
+def test_invalid_flag_combination_is_rejected(built):
+    # refinePoses = 0 with refine3Dpoints = 1 null-derefs in the reference
+    sc = capi.make_scene(None, n_points=10, n_frames=2, seed=1)
+    pa = sc.problem.with_config(2 | capi.CFG_REFINE_POINTS)
+    cam, vw, pt, s = ob.solve(pa, sc.camera_init, sc.views_init, sc.points_init)
+    assert s["status"] == capi.INVALID_ARGUMENT
+
+
+def test_recalib_holds_f_and_B_and_respects_bounds(built):
+    sc = capi.make_scene(None, n_points=60, n_frames=5, seed=13, calib_type=capi.RECALIBRATION)
+    cam, vw, pt, s = ob.solve(sc.problem, sc.camera_init, sc.views_init, sc.points_init, threads=2)
+    assert cam[0] == sc.camera_init[0] and cam[2] == sc.camera_init[2]  # SubsetManifold(17,{0,2})
+    for j in (1, 3, 4):
+        assert 0.7 * sc.camera_init[j] <= cam[j] <= 1.3 * sc.camera_init[j]
+    assert s["final_cost"] < s["initial_cost"]
+
+
+def test_scene_generator_is_deterministic_and_shardable(built):
+    a = capi.make_scene(None, n_points=200, n_frames=8, window=3, seed=5, order=1)
+    b = capi.make_scene(None, n_points=200, n_frames=8, window=3, seed=5, order=1, num_threads=1)
+    assert np.array_equal(a.problem.obs_x, b.problem.obs_x) and np.array_equal(a.problem.point_idx, b.problem.point_idx)
+    lo = capi.make_scene(None, n_points=200, n_frames=8, window=3, seed=5, order=1, point_begin=0, point_end=120)
+    hi = capi.make_scene(None, n_points=200, n_frames=8, window=3, seed=5, order=1, point_begin=120, point_end=200)
+    assert lo.problem.n_obs + hi.problem.n_obs == a.problem.n_obs
+    assert np.array_equal(np.concatenate([lo.problem.obs_y, hi.problem.obs_y]), a.problem.obs_y)
+    # frame-major order holds the same multiset of observations
+    c = capi.make_scene(None, n_points=200, n_frames=8, window=3, seed=5, order=0)
+    assert np.all(np.diff(c.problem.frame_idx) >= 0)
+    ka = np.lexsort((a.problem.ml_y, a.problem.ml_x, a.problem.frame_idx, a.problem.point_idx))
+    kc = np.lexsort((c.problem.ml_y, c.problem.ml_x, c.problem.frame_idx, c.problem.point_idx))
+    assert np.array_equal(a.problem.obs_x[ka], c.problem.obs_x[kc])
+    # float32 round trip of observations and lens centres (src/CameraCalibration.cpp:748-762)
+    assert np.array_equal(a.problem.obs_x, a.problem.obs_x.astype(np.float32).astype(np.float64))
+    assert np.array_equal(a.problem.ml_x, a.problem.ml_x.astype(np.float32).astype(np.float64))
