@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "--expt-relaxed-constexpr", "-Xptxas", "-v", "--fmad=true",
 ]
 
@@ -56,18 +56,37 @@ def build_scene(force=False) -> str:
 
 
 def build_cuda(force=False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo: one object per .cu (compiled in parallel), then a
+    shared library. -Xptxas -v output is kept in build_cuda.log (registers / spills per kernel)."""
+    from concurrent.futures import ThreadPoolExecutor
     out = os.path.join(HERE, "liblfba.so")
     csrc = os.path.join(HERE, "csrc")
+    objdir = os.path.join(HERE, "build")
     cu = sorted(glob.glob(os.path.join(csrc, "*.cu")))
-    deps = cu + glob.glob(os.path.join(csrc, "*.cuh")) + glob.glob(os.path.join(csrc, "*.h")) + \
+    hdr = glob.glob(os.path.join(csrc, "*.cuh")) + glob.glob(os.path.join(csrc, "*.h")) + \
         [os.path.join(ROOT, "include", "lfba.h")]
     if not cu:
         raise RuntimeError("no CUDA sources under lifcal_b200/csrc")
-    if force or _stale(out, deps):
-        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", _host_cxx(), "-I", os.path.join(ROOT, "include"), "-o", out] + cu + \
-            ["-ldl", "-lpthread"]
-        _run(cmd, log=os.path.join(HERE, "build_cuda.log"))
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    common = [nvcc] + NVCC_FLAGS + ["-ccbin", _host_cxx(), "-I", os.path.join(ROOT, "include")]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if force or _stale(obj, [src] + hdr):
+            log = _run(common + ["-c", "-o", obj, src])
+            with open(obj + ".log", "w") as f:
+                f.write(log)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(cu))) as ex:
+        objs = list(ex.map(compile_one, cu))
+    if force or _stale(out, objs):
+        _run([nvcc, "-shared", "-o", out, "-ccbin", _host_cxx()] + objs + ["-ldl", "-lpthread"])
+        with open(os.path.join(HERE, "build_cuda.log"), "w") as f:
+            for o in objs:
+                if os.path.exists(o + ".log"):
+                    f.write(open(o + ".log").read())
     return out
 
 

@@ -1,0 +1,153 @@
+// lfba_device.cuh — device-side data layout of one rank's share of an LF-BA problem, and the LM state that
+// lives in HBM for the whole solve (the host only polls `done`).
+//
+// Layout in HBM (per rank; N observations, T tracks = (point, frame) pairs, P points, F frames, NL lenses):
+//   obs      double2[N]   observed micro-image point, sorted by (point, frame)          16 B/obs  \  the streamed
+//   lens_id  int32[N]     index into the lens table                                      4 B/obs  /  20 B/obs
+//   lens     double[NL*16] per-lens undistortion table (rebuilt per evaluation, L2-resident)
+//   frames   double[2][F*40] per-frame rotation table for the accepted / candidate poses
+//   trk_*    int32[T]     point, frame, first observation of each track (+ begin[T])
+//   rec      double[2][T*REC] per-track normal-equation blocks in the camera frame (A 6, b 3, C 3xNC),
+//                          double-buffered: accepted state / candidate
+//   pdata    double[P*40] per-point Schur data (inverse of the damped 3x3, gradient, damping, camera coupling)
+//   vw       double[T*36] per-track pose-point coupling V (6x3) and V*Hpp^-1 (6x3)
+//   S        skyline lower-triangular reduced system [poses 6F | coupled points 3Pc | camera | rhs row]
+// Parameters are double-buffered (accepted x / candidate x+) so that accept/reject is an index flip on device.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lfba.h"
+#include "lfba_math.cuh"
+
+namespace lfba {
+
+constexpr int kPointStride = 40;  // pdata: Hinv(6) gp(3) dmp(3) Hcp(3*NC<=27) pad
+constexpr int kVWStride = 36;     // vw: V(18: 6x3 row-major) W(18)
+constexpr int kMaxLog = 1024;
+constexpr int kTile = 64;         // Cholesky tile
+
+__host__ __device__ inline int rec_stride(int nc) { return 9 + 3 * nc; }
+
+// scalars exchanged between kernels / ranks through small device arrays
+enum EvalScalar {  // tiny buffer reduced (sum) across ranks after the candidate evaluation
+  ES_COST = 0,     // candidate cost (observations of this rank + constraints on rank 0)
+  ES_MCC,          // model cost change partial (points of this rank; reduced part added on rank 0)
+  ES_STEP2,        // |x - x+|^2 partial
+  ES_NORM2,        // |x+|^2 partial
+  ES_GDELTA,       // gradient . delta partial
+  ES_BAD,          // non-finite step flag (count)
+  ES_COUNT = 8
+};
+enum SysScalar {   // trailer of the big buffer reduced (sum) across ranks with S and g
+  SS_GNORM2 = 0,   // sum of squared gradient over the points of this rank
+  SS_PTFAIL,       // number of points whose damped 3x3 block was not positive definite
+  SS_COUNT = 4     // followed by nranks slots for max |g| over points (one slot per rank)
+};
+
+struct LmState {
+  int iter;         // index of the iteration row being produced (0 = IterationZero)
+  int cur;          // buffer index of the accepted state
+  int done;
+  int eval_skip;    // candidate evaluation skipped: the step was known to be invalid
+  int solve_ok;     // Cholesky succeeded and the step is finite
+  int num_invalid;  // consecutive invalid steps
+  int termination, stop_reason, status;
+  int n_success, n_fail, n_rows;
+  int first;        // Jacobi scaling still to be computed (iteration 0)
+  int pending_row;  // a row is waiting for its gradient norms (k_finalize)
+  int n_jac_evals;
+  int ls_needed;    // projected line search would have to contract the step (recalib only)
+  double radius, decrease_factor;
+  double x_cost, x_norm2, min_cost;
+  double gmax, gnorm;
+  double mcc_red, step2_red, norm2_red, gdelta_red;  // reduced-part contributions to the candidate scalars
+  lfba_iteration row;
+  unsigned long long t_start, t_iter;
+};
+
+struct Options {
+  int max_iter;
+  double ftol, ptol, gtol, r0, rmax, rmin, min_rel_dec, min_diag, max_diag;
+  int max_invalid;
+  double loss_a;
+};
+
+// Everything a kernel needs, passed by value.
+struct Dev {
+  // sizes
+  int64_t N;
+  int T, P, F, NL, K;       // tracks, points, frames, lenses, constraints
+  int NC;                   // live camera parameters
+  int n;                    // reduced system size (without the rhs row)
+  int np6;                  // 6F if poses are refined else 0
+  int Pc;                   // coupled points
+  int n_cam_red;            // free camera parameters in the reduced system
+  int rank, nranks;
+  uint32_t config;
+  int recalib, refine_poses, refine_points;
+  double spx, spy, scale;
+  Options opt;
+  // observations (sorted by point, frame)
+  const double2* obs;
+  const int32_t* lens_id;
+  const int32_t* trk_point;
+  const int32_t* trk_frame;
+  const int32_t* trk_begin;   // [T+1]
+  const int32_t* pt_trk_begin;  // [P+1]
+  const int32_t* frm_begin;   // [F+1] into frm_trk
+  const int32_t* frm_trk;     // track ids grouped by frame
+  const int32_t* pair_begin;  // [npairs+1] into pair_t1/pair_t2
+  const int32_t* pair_f1;     // [npairs]
+  const int32_t* pair_f2;
+  const int32_t* pair_t1;
+  const int32_t* pair_t2;
+  int npairs;
+  const int32_t* eval_order;  // track processing order of the evaluation kernel (length-sorted)
+  // point / frame flags
+  const int32_t* pt_coupled;  // [P] index among coupled points or -1
+  const int32_t* coupled_pts; // [Pc]
+  const int32_t* pt_active;   // [P] 1 if the point is in the problem on this rank
+  const int32_t* frm_active;  // [F] 1 if the frame has observations on any rank
+  const int32_t* c_p1;
+  const int32_t* c_p2;
+  const double* c_dist;
+  const double* c_sigma;
+  int cam_red[kMaxNC];        // camera column -> reduced index (absolute) or -1 when held constant
+  double cam_lo[17], cam_hi[17];  // box bounds on the camera block (recalib), +-DBL_MAX otherwise
+  // parameters, double-buffered
+  double* camera[2];   // [17]
+  double* views[2];    // [6F]
+  double* points[2];   // [3P]
+  // tables
+  double* lens;        // [NL*16]
+  const double* lens_xy;  // [NL*2] lens centres
+  double* frames[2];   // [F*40]
+  // per-track / per-point work arrays
+  double* rec[2];
+  double* camsum[2];   // [64]: Hcc (lower, NC*(NC+1)/2), gc (NC), cost
+  double* pdata;
+  double* pscale;      // [3P] Jacobi scale of the point columns
+  double* vw;
+  // reduced system
+  double* S;           // skyline storage
+  const int64_t* row_off;  // [n+2]
+  const int32_t* row_c0;   // [n+1] first stored column of each row
+  double* g;           // [n]   reduced rhs  (lives right after S in the reduce buffer)
+  double* gfull;       // [n]   gradient J^T r of the reduced parameters (before the Schur correction)
+  double* hdiag;       // [n]   diagonal of F^T F (undamped, before Schur)
+  double* sys_scalars; // [SS_COUNT + nranks]
+  double* rscale;      // [n] Jacobi scale of the reduced columns
+  double* rdamp;       // [n] LM damping added to the reduced diagonal
+  double* y;           // [n] reduced solution
+  double* eval_scalars;  // [ES_COUNT]
+  // partial sums of the block reductions
+  double* part_eval;   // [grid_eval * 64]
+  double* part_pts;    // [grid_pts * 64]
+  double* part_step;   // [grid_pts * 8]
+  int grid_eval, grid_pts;
+  LmState* st;
+  lfba_iteration* log;
+};
+
+}  // namespace lfba

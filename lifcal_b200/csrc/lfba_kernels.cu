@@ -1,0 +1,1145 @@
+// lfba_kernels.cu — hand-written sm_100a FP64 kernels of the LF-BA Levenberg-Marquardt iteration.
+//
+// Reference being replaced: one ceres::Solve iteration over the problem built at
+// src/CameraCalibration.cpp:858-953 (Ceres 2.1.0: ProgramEvaluator + AutoDiff of OurCostFunctionBundle,
+// CauchyLoss/Corrector, SchurEliminator<2,3,Dynamic>, TrustRegionMinimizer).
+//
+// Round structure (all on one stream, no host decisions; the host only polls LmState::done):
+//   E  k_tables            per-lens undistortion table + per-frame rotation table at the CANDIDATE parameters
+//      k_eval_tracks       fused residual + analytic Jacobian + robust weighting + per-track normal-equation
+//                          blocks in the camera frame (A = G^T G, b = G^T r, C = G^T Jc) + camera block
+//                          (Hcc, gc) + cost.  The Jacobian never leaves registers.
+//      k_reduce_eval       deterministic reduction of the per-CTA partials; candidate scalars
+//   C1 k_control_accept    step tests, rho, accept/reject (buffer flip), radius update   [device-resident LM]
+//   B  k_points            per point: Hpp, g_p, Hcp; damping; 3x3 inverse; camera-camera Schur term
+//      k_frame_pose        per frame: pose diagonal block, pose gradient (Schur-corrected), V and W=V Hpp^-1
+//      k_frame_cam         per frame: camera-pose block (Schur-corrected)
+//      k_pairs             per co-visible frame pair: -sum_p W_{p,f1} V_{p,f2}^T
+//      k_coupled, k_constraints, k_add_camera
+//   C2 k_finalize          Jacobi scaling (iteration 0), gradient norms, iteration row, termination tests,
+//                          LM damping of the reduced system
+//   S  (lfba_chol.cu)      Cholesky + solves of the reduced system
+//   P  k_point_step        per-point back substitution, candidate point, model-cost/step-norm partials
+//      k_reduced_step      candidate camera/poses/coupled points (manifold + bounds), reduced-part scalars
+// Scatter into the reduced system is gather-by-destination (per frame, per frame pair): no atomics on the hot
+// blocks and a fixed summation order.
+#include <float.h>
+
+#include "lfba_device.cuh"
+#include "lfba_kernels.h"
+
+namespace lfba {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ double* S_at(const Dev& d, int r, int c) {
+  return d.S + d.row_off[r] + (c - d.row_c0[r]);
+}
+
+// Sum NV per-thread values over the CTA (fixed order: lanes by butterfly, warps ascending), result to out[0..NV).
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double* vals, double* out, double* smem /*[nwarps*NV]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const double s = warp_sum(vals[v]);
+    if (lane == 0) smem[warp * NV + v] = s;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += smem[w * NV + v];
+    out[v] = s;
+  }
+  __syncthreads();
+}
+
+// ================================================================================================
+// E. candidate evaluation
+// ================================================================================================
+__global__ void k_tables(Dev d) {
+  const LmState* st = d.st;
+  if (st->done || st->eval_skip) return;
+  const int cand = 1 - st->cur;
+  __shared__ CamModel cm;
+  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d.NL) {
+    double e[kLensStride];
+    lens_entry(cm, d.lens_xy[2 * i], d.lens_xy[2 * i + 1], e);
+    double2* dst = reinterpret_cast<double2*>(d.lens + (size_t)i * kLensStride);
+#pragma unroll
+    for (int k = 0; k < kLensStride / 2; ++k) dst[k] = make_double2(e[2 * k], e[2 * k + 1]);
+  }
+  if (i < d.F) {
+    double f[kFrameStride];
+    frame_entry(d.views[cand] + 6 * i, f);
+    double* dst = d.frames[cand] + (size_t)i * kFrameStride;
+#pragma unroll
+    for (int k = 0; k < kFrameStride; ++k) dst[k] = f[k];
+  }
+}
+
+// Fused residual + analytic Jacobian + per-track normal-equation blocks.
+// L lanes cooperate on one track (point, frame): lane j takes observations j, j+L, ... of the track; the
+// track sums (A 6, b 3, C 3xNC) are combined with xor-shuffles inside the L-lane group; the camera block
+// (Hcc, gc) and the cost stay in per-thread accumulators for the whole kernel and are reduced once per CTA.
+// Algorithmic HBM traffic: 20 B per observation (double2 + int32) + REC*8 B per track written.
+template <int NC, int L>
+__global__ void __launch_bounds__(128) k_eval_tracks(Dev d) {
+  const LmState* st = d.st;
+  if (st->done || st->eval_skip) return;
+  const int cand = 1 - st->cur;
+  constexpr int NH = NC * (NC + 1) / 2;
+  constexpr int NV = NH + NC + 1;
+  constexpr int RS = 9 + 3 * NC;
+  __shared__ CamModel cm;
+  __shared__ double red[4 * NV];
+  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+  __syncthreads();
+
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+
+  const int lig = threadIdx.x % L;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int ngroups = (gridDim.x * blockDim.x) / L;
+  const int iters = (d.T + ngroups - 1) / ngroups;
+  const double* __restrict__ frames = d.frames[cand];
+  const double* __restrict__ points = d.points[cand];
+  double* __restrict__ recs = d.rec[cand];
+  const bool robust = cm.robust != 0;
+
+  for (int it = 0; it < iters; ++it) {
+    const int slot = group + it * ngroups;
+    const bool valid = slot < d.T;
+    const int t = valid ? (d.eval_order ? d.eval_order[slot] : slot) : 0;
+    double tr[RS];
+#pragma unroll
+    for (int v = 0; v < RS; ++v) tr[v] = 0.0;
+    if (valid) {
+      const int p = d.trk_point[t], f = d.trk_frame[t];
+      const int ob = d.trk_begin[t], oe = d.trk_begin[t + 1];
+      double Pc[3];
+      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
+      TrackCtx tc;
+      track_setup(cm, Pc, tc);
+      for (int i = ob + lig; i < oe; i += L) {
+        const double2 o = d.obs[i];
+        const double2* lp = reinterpret_cast<const double2*>(d.lens + (size_t)d.lens_id[i] * kLensStride);
+        double e[kLensStride];
+#pragma unroll
+        for (int k = 0; k < kLensStride / 2; ++k) {
+          const double2 v2 = __ldg(lp + k);
+          e[2 * k] = v2.x;
+          e[2 * k + 1] = v2.y;
+        }
+        double r[2], G[6], J[2 * NC];
+        obs_eval<NC>(cm, tc, e, o.x, o.y, r, G, J);
+        const double s = r[0] * r[0] + r[1] * r[1];
+        if (robust) {
+          double rho;
+          const double sw = robust_scale(cm, s, rho);
+          acc[NH + NC] += 0.5 * rho;
+          r[0] *= sw;
+          r[1] *= sw;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) G[k] *= sw;
+#pragma unroll
+          for (int k = 0; k < 2 * NC; ++k) J[k] *= sw;
+        } else {
+          acc[NH + NC] += 0.5 * s;
+        }
+        // track blocks
+        tr[0] += G[0] * G[0] + G[3] * G[3];
+        tr[1] += G[0] * G[1] + G[3] * G[4];
+        tr[2] += G[0] * G[2] + G[3] * G[5];
+        tr[3] += G[1] * G[1] + G[4] * G[4];
+        tr[4] += G[1] * G[2] + G[4] * G[5];
+        tr[5] += G[2] * G[2] + G[5] * G[5];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tr[6 + k] += G[k] * r[0] + G[3 + k] * r[1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) tr[9 + k * NC + c] += G[k] * J[c] + G[3 + k] * J[NC + c];
+        // camera block
+        int h = 0;
+#pragma unroll
+        for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+          for (int c2 = 0; c2 <= c1; ++c2) {
+            acc[h] += J[c1] * J[c2] + J[NC + c1] * J[NC + c2];
+            ++h;
+          }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[NH + c] += J[c] * r[0] + J[NC + c] * r[1];
+      }
+    }
+    if (L > 1) {
+#pragma unroll
+      for (int v = 0; v < RS; ++v)
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) tr[v] += __shfl_xor_sync(0xffffffffu, tr[v], o);
+    }
+    if (valid) {
+      double* dst = recs + (size_t)t * RS;
+#pragma unroll
+      for (int v = 0; v < RS; ++v)
+        if ((v % L) == lig) dst[v] = tr[v];
+    }
+  }
+  block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
+}
+
+// Sum the CTA partials of k_eval_tracks (fixed order) -> camsum[cand]; sum the step partials of
+// k_point_step (previous round); candidate cost of the distance constraints; assemble eval_scalars.
+__global__ void k_reduce_eval(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int cand = 1 - st->cur;
+  const int NH = d.NC * (d.NC + 1) / 2, NV = NH + d.NC + 1;
+  __shared__ double sh[64];
+  __shared__ double shs[8];
+  const int v = threadIdx.x;
+  if (v < 64) {
+    double s = 0.0;
+    if (v < NV && !st->eval_skip)
+      for (int b = 0; b < d.grid_eval; ++b) s += d.part_eval[(size_t)b * 64 + v];
+    sh[v] = s;
+    if (v < NV) d.camsum[cand][v] = s;
+  }
+  if (v >= 64 && v < 72) {
+    const int k = v - 64;
+    double s = 0.0;
+    if (d.refine_points && (st->iter == 0 || st->solve_ok))
+      for (int b = 0; b < d.grid_pts; ++b) s += d.part_step[(size_t)b * 8 + k];
+    shs[k] = s;
+  }
+  __syncthreads();
+  if (v == 0) {
+    double cost = sh[NV - 1];
+    if (d.rank == 0 && !st->eval_skip) {
+      const double* pts = d.points[cand];
+      for (int k = 0; k < d.K; ++k) {
+        double r, j[3];
+        distance_eval(pts + 3 * d.c_p1[k], pts + 3 * d.c_p2[k], d.c_dist[k], d.c_sigma[k], r, j);
+        cost += 0.5 * r * r;
+      }
+    }
+    double* es = d.eval_scalars;
+    es[ES_COST] = cost;
+    const double own = d.rank == 0 ? 1.0 : 0.0;
+    es[ES_MCC] = shs[0] + own * st->mcc_red;
+    es[ES_STEP2] = shs[1] + own * st->step2_red;
+    es[ES_NORM2] = shs[2] + own * st->norm2_red;
+    es[ES_GDELTA] = shs[3] + own * st->gdelta_red;
+    es[ES_BAD] = shs[4];
+    es[5] = es[6] = es[7] = 0.0;
+  }
+}
+
+// ================================================================================================
+// C1. accept / reject — ceres::internal::TrustRegionMinimizer::Minimize loop body after the candidate
+// evaluation (ParameterToleranceReached, FunctionToleranceReached, IsStepSuccessful, HandleSuccessfulStep /
+// StepRejected / HandleInvalidStep) and LevenbergMarquardtStrategy::StepAccepted/StepRejected.
+// ================================================================================================
+__global__ void k_control_accept(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const double* es = d.eval_scalars;
+  const Options& o = d.opt;
+  lfba_iteration& row = st->row;
+  if (st->iter == 0) {  // IterationZero
+    st->t_start = st->t_iter = gtimer();
+    st->cur ^= 1;
+    st->x_cost = es[ES_COST];
+    st->x_norm2 = es[ES_NORM2];
+    st->min_cost = DBL_MAX;
+    st->first = 1;
+    st->n_jac_evals = 1;
+    row.iteration = 0;
+    row.step_is_valid = 1;
+    row.step_is_successful = 1;
+    row.line_search_iterations = 0;
+    row.cost = st->x_cost;
+    row.cost_change = 0.0;
+    row.step_norm = 0.0;
+    row.relative_decrease = 0.0;
+    st->pending_row = 1;
+    return;
+  }
+  row.iteration = st->iter;
+  row.line_search_iterations = 0;
+  const double mcc = es[ES_MCC];
+  const bool valid = !st->eval_skip && st->solve_ok && es[ES_BAD] == 0.0 && mcc > 0.0;
+  if (!valid) {  // HandleInvalidStep
+    if (++st->num_invalid >= o.max_invalid) {
+      st->done = 1;
+      st->termination = LFBA_TERM_FAILURE;
+      st->stop_reason = LFBA_STOP_INVALID_STEPS;
+      st->status = LFBA_FAILURE;
+      return;
+    }
+    st->radius = st->radius / st->decrease_factor;
+    st->decrease_factor *= 2.0;
+    row.step_is_valid = 0;
+    row.step_is_successful = 0;
+    row.cost = st->x_cost;
+    row.cost_change = 0.0;
+    row.step_norm = 0.0;
+    row.relative_decrease = 0.0;
+    st->pending_row = 1;
+    return;
+  }
+  st->num_invalid = 0;
+  if (!st->eval_skip) st->n_jac_evals += 1;
+  double cand_cost = es[ES_COST];
+  if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
+  row.step_is_valid = 1;
+  if (d.recalib) {
+    // Projected Armijo test at step size 1 (Ceres DoLineSearch for bounds-constrained problems): if it
+    // holds, the line search returns 1.0 and delta is unchanged. Otherwise the host contracts the step.
+    if (!(cand_cost <= st->x_cost + 1e-4 * es[ES_GDELTA])) {
+      st->ls_needed = 1;
+      st->done = 1;
+      return;
+    }
+  }
+  row.step_norm = sqrt(es[ES_STEP2]);
+  if (row.step_norm <= o.ptol * (sqrt(st->x_norm2) + o.ptol)) {
+    st->done = 1;
+    st->termination = LFBA_CONVERGENCE;
+    st->stop_reason = LFBA_STOP_PARAMETER_TOLERANCE;
+    return;
+  }
+  row.cost_change = st->x_cost - cand_cost;
+  if (fabs(row.cost_change) <= o.ftol * st->x_cost) {
+    st->done = 1;
+    st->termination = LFBA_CONVERGENCE;
+    st->stop_reason = LFBA_STOP_FUNCTION_TOLERANCE;
+    return;
+  }
+  row.relative_decrease = cand_cost >= DBL_MAX ? -DBL_MAX : (st->x_cost - cand_cost) / mcc;
+  if (row.relative_decrease > o.min_rel_dec) {
+    st->cur ^= 1;
+    st->x_cost = cand_cost;
+    st->x_norm2 = es[ES_NORM2];
+    row.cost = cand_cost;
+    row.step_is_successful = 1;
+    const double q = 2.0 * row.relative_decrease - 1.0;
+    st->radius = st->radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+    st->radius = fmin(o.rmax, st->radius);
+    st->decrease_factor = 2.0;
+  } else {
+    row.step_is_successful = 0;
+    row.cost = cand_cost;
+    st->radius = st->radius / st->decrease_factor;
+    st->decrease_factor *= 2.0;
+  }
+  st->pending_row = 1;
+}
+
+// ================================================================================================
+// B. system assembly at the accepted state
+// ================================================================================================
+// Per point: Hpp = sum_t R^T A_t R, g_p = sum_t R^T b_t, Hcp = sum_t C_t^T R  (E-block of SchurEliminator),
+// Jacobi scale (iteration 0), LM damping, inverse of the damped block, camera-camera Schur term.
+template <int NC>
+__global__ void __launch_bounds__(128) k_points(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int cur = st->cur;
+  constexpr int NH = NC * (NC + 1) / 2;
+  constexpr int NV = NH + NC + 3;  // Schur cam-cam (NH), Schur cam gradient (NC), |g|^2, fail count, (max separately)
+  constexpr int RS = 9 + 3 * NC;
+  __shared__ double red[4 * NV];
+  __shared__ double redmax[4];
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  double gmax = 0.0;
+  const double mu = st->radius;
+  const bool first = st->first != 0;
+  const double* __restrict__ frames = d.frames[cur];
+  const double* __restrict__ recs = d.rec[cur];
+
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.P; p += gridDim.x * blockDim.x) {
+    if (!d.pt_active[p]) continue;
+    double* pd = d.pdata + (size_t)p * kPointStride;
+    if (d.pt_coupled[p] >= 0) {  // stays in the reduced system (k_coupled); no elimination
+      for (int k = 0; k < kPointStride; ++k) pd[k] = 0.0;
+      continue;
+    }
+    double H[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0}, Hcp[3 * NC];
+#pragma unroll
+    for (int k = 0; k < 3 * NC; ++k) Hcp[k] = 0.0;
+    for (int t = d.pt_trk_begin[p]; t < d.pt_trk_begin[p + 1]; ++t) {
+      const double* rc = recs + (size_t)t * RS;
+      const double* R = frames + (size_t)d.trk_frame[t] * kFrameStride;
+      const double A[6] = {rc[0], rc[1], rc[2], rc[3], rc[4], rc[5]};
+      double AR[9];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        AR[0 + j] = A[0] * R[j] + A[1] * R[3 + j] + A[2] * R[6 + j];
+        AR[3 + j] = A[1] * R[j] + A[3] * R[3 + j] + A[4] * R[6 + j];
+        AR[6 + j] = A[2] * R[j] + A[4] * R[3 + j] + A[5] * R[6 + j];
+      }
+      H[0] += R[0] * AR[0] + R[3] * AR[3] + R[6] * AR[6];
+      H[1] += R[0] * AR[1] + R[3] * AR[4] + R[6] * AR[7];
+      H[2] += R[0] * AR[2] + R[3] * AR[5] + R[6] * AR[8];
+      H[3] += R[1] * AR[1] + R[4] * AR[4] + R[7] * AR[7];
+      H[4] += R[1] * AR[2] + R[4] * AR[5] + R[7] * AR[8];
+      H[5] += R[2] * AR[2] + R[5] * AR[5] + R[8] * AR[8];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gp[j] += R[j] * rc[6] + R[3 + j] * rc[7] + R[6 + j] * rc[8];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double c0 = rc[9 + c], c1 = rc[9 + NC + c], c2 = rc[9 + 2 * NC + c];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Hcp[3 * c + j] += c0 * R[j] + c1 * R[3 + j] + c2 * R[6 + j];
+      }
+    }
+    const double hd[3] = {H[0], H[3], H[5]};
+    double* ps = d.pscale + 3 * (size_t)p;
+    if (first)
+      for (int j = 0; j < 3; ++j) ps[j] = 1.0 / (1.0 + sqrt(hd[j]));
+    double dmp[3];
+    for (int j = 0; j < 3; ++j) {
+      const double s2 = ps[j] * ps[j];
+      dmp[j] = fmin(fmax(s2 * hd[j], d.opt.min_diag), d.opt.max_diag) / (mu * s2);
+    }
+    const double Hd[6] = {H[0] + dmp[0], H[1], H[2], H[3] + dmp[1], H[4], H[5] + dmp[2]};
+    double Hi[6];
+    if (!spd3_inverse(Hd, Hi)) {
+      acc[NH + NC + 1] += 1.0;
+      for (int k = 0; k < 6; ++k) Hi[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pd[k] = Hi[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      pd[6 + k] = gp[k];
+      pd[9 + k] = dmp[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * NC; ++k) pd[12 + k] = Hcp[k];
+    // camera-camera Schur term: -(Hcp Hi) Hcp^T, -(Hcp Hi) g_p
+    double Tm[3 * NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sym3_vec(Hi, Hcp + 3 * c, Tm + 3 * c);
+    int h = 0;
+#pragma unroll
+    for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+      for (int c2 = 0; c2 <= c1; ++c2) {
+        acc[h] -= Tm[3 * c1] * Hcp[3 * c2] + Tm[3 * c1 + 1] * Hcp[3 * c2 + 1] + Tm[3 * c1 + 2] * Hcp[3 * c2 + 2];
+        ++h;
+      }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[NH + c] -= Tm[3 * c] * gp[0] + Tm[3 * c + 1] * gp[1] + Tm[3 * c + 2] * gp[2];
+    acc[NH + NC] += gp[0] * gp[0] + gp[1] * gp[1] + gp[2] * gp[2];
+    gmax = fmax(gmax, fmax(fabs(gp[0]), fmax(fabs(gp[1]), fabs(gp[2]))));
+  }
+  block_reduce_store<NV>(acc, d.part_pts + (size_t)blockIdx.x * 64, red);
+  gmax = warp_max(gmax);
+  if ((threadIdx.x & 31) == 0) redmax[threadIdx.x >> 5] = gmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m = fmax(m, redmax[w]);
+    d.part_pts[(size_t)blockIdx.x * 64 + 63] = m;
+  }
+}
+
+// M = [dR0 X, dR1 X, dR2 X, I3] (3x6, d P_c / d pose) of a track
+__device__ __forceinline__ void track_M(const double* fe, const double* X, double m[9]) {
+  mat3_vec(fe + 9, X, m + 0);
+  mat3_vec(fe + 18, X, m + 3);
+  mat3_vec(fe + 27, X, m + 6);
+}
+
+// Per frame (one CTA per (frame, split)): pose diagonal block, pose gradient, both Schur-corrected with the
+// track's own point; writes V = Hvp (6x3) and W = V Hpp^-1 for k_pairs / k_frame_cam / k_point_step.
+__global__ void __launch_bounds__(128) k_frame_pose(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int cur = st->cur;
+  const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  const int RS = rec_stride(d.NC);
+  constexpr int NV = 21 + 6 + 6 + 6;  // S_ff (lower 21), reduced gradient, full gradient, diag(F^T F)
+  __shared__ double fe[kFrameStride];
+  __shared__ double red[4 * NV];
+  __shared__ double out[NV];
+  if (threadIdx.x < kFrameStride) fe[threadIdx.x] = d.frames[cur][(size_t)f * kFrameStride + threadIdx.x];
+  __syncthreads();
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  const double* __restrict__ recs = d.rec[cur];
+  const double* __restrict__ points = d.points[cur];
+  for (int idx = d.frm_begin[f] + split * blockDim.x + threadIdx.x; idx < d.frm_begin[f + 1];
+       idx += nsplit * blockDim.x) {
+    const int t = d.frm_trk[idx];
+    const int p = d.trk_point[t];
+    const double* rc = recs + (size_t)t * RS;
+    const double* pd = d.pdata + (size_t)p * kPointStride;
+    const double A[6] = {rc[0], rc[1], rc[2], rc[3], rc[4], rc[5]};
+    const double b[3] = {rc[6], rc[7], rc[8]};
+    double m[9];
+    track_M(fe, points + 3 * (size_t)p, m);
+    // AM (3x6): columns 0..2 = A m_k, columns 3..5 = A
+    double AM[18];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double y[3];
+      sym3_vec(A, m + 3 * k, y);
+      AM[0 * 6 + k] = y[0];
+      AM[1 * 6 + k] = y[1];
+      AM[2 * 6 + k] = y[2];
+    }
+    AM[0 * 6 + 3] = A[0]; AM[0 * 6 + 4] = A[1]; AM[0 * 6 + 5] = A[2];
+    AM[1 * 6 + 3] = A[1]; AM[1 * 6 + 4] = A[3]; AM[1 * 6 + 5] = A[4];
+    AM[2 * 6 + 3] = A[2]; AM[2 * 6 + 4] = A[4]; AM[2 * 6 + 5] = A[5];
+    // M^T as rows: Mt[a][i], a<3: m[3a+i]; a>=3: delta(a-3,i)
+    auto Mt = [&](int a, int i) -> double { return a < 3 ? m[3 * a + i] : (a - 3 == i ? 1.0 : 0.0); };
+    double Hvv[21], gv[6];
+    {
+      int h = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = 0; c <= a; ++c) {
+          Hvv[h++] = Mt(a, 0) * AM[0 * 6 + c] + Mt(a, 1) * AM[1 * 6 + c] + Mt(a, 2) * AM[2 * 6 + c];
+        }
+        gv[a] = Mt(a, 0) * b[0] + Mt(a, 1) * b[1] + Mt(a, 2) * b[2];
+      }
+    }
+    // V = M^T (A R) (6x3), W = V Hi
+    const double* R = fe;
+    double AR[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      AR[0 + j] = A[0] * R[j] + A[1] * R[3 + j] + A[2] * R[6 + j];
+      AR[3 + j] = A[1] * R[j] + A[3] * R[3 + j] + A[4] * R[6 + j];
+      AR[6 + j] = A[2] * R[j] + A[4] * R[3 + j] + A[5] * R[6 + j];
+    }
+    double V[18], W[18];
+    const double Hi[6] = {pd[0], pd[1], pd[2], pd[3], pd[4], pd[5]};
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) V[3 * a + j] = Mt(a, 0) * AR[j] + Mt(a, 1) * AR[3 + j] + Mt(a, 2) * AR[6 + j];
+      sym3_vec(Hi, V + 3 * a, W + 3 * a);
+    }
+    double* vw = d.vw + (size_t)t * kVWStride;
+#pragma unroll
+    for (int k = 0; k < 18; ++k) {
+      vw[k] = V[k];
+      vw[18 + k] = W[k];
+    }
+    const double gp[3] = {pd[6], pd[7], pd[8]};
+    {
+      int h = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = 0; c <= a; ++c) {
+          acc[h] += Hvv[h] - (W[3 * a] * V[3 * c] + W[3 * a + 1] * V[3 * c + 1] + W[3 * a + 2] * V[3 * c + 2]);
+          ++h;
+        }
+        acc[21 + a] += gv[a] - (W[3 * a] * gp[0] + W[3 * a + 1] * gp[1] + W[3 * a + 2] * gp[2]);
+        acc[27 + a] += gv[a];
+      }
+      acc[33] += Hvv[0];
+      acc[34] += Hvv[2];
+      acc[35] += Hvv[5];
+      acc[36] += Hvv[9];
+      acc[37] += Hvv[14];
+      acc[38] += Hvv[20];
+    }
+  }
+  block_reduce_store<NV>(acc, out, red);
+  if (threadIdx.x < NV) {
+    const int v = threadIdx.x;
+    const double s = out[v];
+    double* dst;
+    if (v < 21) {
+      int a = 0, h = v;
+      while (h > a) { h -= a + 1; ++a; }
+      dst = S_at(d, 6 * f + a, 6 * f + h);
+    } else if (v < 27) {
+      dst = d.g + 6 * f + (v - 21);
+    } else if (v < 33) {
+      dst = d.gfull + 6 * f + (v - 27);
+    } else {
+      dst = d.hdiag + 6 * f + (v - 33);
+    }
+    if (nsplit == 1) *dst += s; else atomicAdd(dst, s);
+  }
+}
+
+// Per frame: camera-pose block S[cam, f] = sum_t (C_t^T M_t - Hcp W_t^T).
+template <int NC>
+__global__ void __launch_bounds__(128) k_frame_cam(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int cur = st->cur;
+  const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  constexpr int RS = 9 + 3 * NC;
+  constexpr int NV = 6 * NC;
+  __shared__ double fe[kFrameStride];
+  __shared__ double red[4 * NV];
+  __shared__ double out[NV];
+  if (threadIdx.x < kFrameStride) fe[threadIdx.x] = d.frames[cur][(size_t)f * kFrameStride + threadIdx.x];
+  __syncthreads();
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  const double* __restrict__ recs = d.rec[cur];
+  const double* __restrict__ points = d.points[cur];
+  for (int idx = d.frm_begin[f] + split * blockDim.x + threadIdx.x; idx < d.frm_begin[f + 1];
+       idx += nsplit * blockDim.x) {
+    const int t = d.frm_trk[idx];
+    const int p = d.trk_point[t];
+    const double* rc = recs + (size_t)t * RS;
+    const double* pd = d.pdata + (size_t)p * kPointStride;
+    const double* W = d.vw + (size_t)t * kVWStride + 18;
+    double m[9];
+    track_M(fe, points + 3 * (size_t)p, m);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double c0 = rc[9 + c], c1 = rc[9 + NC + c], c2 = rc[9 + 2 * NC + c];
+      const double h0 = pd[12 + 3 * c], h1 = pd[13 + 3 * c], h2 = pd[14 + 3 * c];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double cm = a < 3 ? (c0 * m[3 * a] + c1 * m[3 * a + 1] + c2 * m[3 * a + 2])
+                                : (a == 3 ? c0 : (a == 4 ? c1 : c2));
+        acc[6 * c + a] += cm - (h0 * W[3 * a] + h1 * W[3 * a + 1] + h2 * W[3 * a + 2]);
+      }
+    }
+  }
+  block_reduce_store<NV>(acc, out, red);
+  if (threadIdx.x < NV) {
+    const int c = threadIdx.x / 6, a = threadIdx.x % 6;
+    const int r = d.cam_red[c];
+    if (r >= 0) {
+      double* dst = S_at(d, r, 6 * f + a);
+      if (nsplit == 1) *dst += out[threadIdx.x]; else atomicAdd(dst, out[threadIdx.x]);
+    }
+  }
+}
+
+// Per co-visible frame pair (f1 > f2), one warp: S[f1, f2] = -sum_p W_{p,f1} V_{p,f2}^T.
+__global__ void __launch_bounds__(128) k_pairs(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= d.npairs) return;
+  double acc[36];
+#pragma unroll
+  for (int v = 0; v < 36; ++v) acc[v] = 0.0;
+  for (int i = d.pair_begin[warp] + lane; i < d.pair_begin[warp + 1]; i += 32) {
+    const double* W = d.vw + (size_t)d.pair_t1[i] * kVWStride + 18;
+    const double* V = d.vw + (size_t)d.pair_t2[i] * kVWStride;
+    double w[18], v[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) {
+      w[k] = W[k];
+      v[k] = V[k];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b)
+        acc[6 * a + b] += w[3 * a] * v[3 * b] + w[3 * a + 1] * v[3 * b + 1] + w[3 * a + 2] * v[3 * b + 2];
+  }
+  const int f1 = d.pair_f1[warp], f2 = d.pair_f2[warp];
+#pragma unroll
+  for (int v = 0; v < 36; ++v) {
+    const double s = warp_sum(acc[v]);
+    if (lane == (v & 31)) *S_at(d, 6 * f1 + v / 6, 6 * f2 + v % 6) -= s;
+  }
+}
+
+// Points touched by a distance constraint stay in the reduced system: their blocks are added
+// to S directly. A handful of points: one thread each.
+template <int NC>
+__global__ void k_coupled(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int cur = st->cur;
+  constexpr int RS = 9 + 3 * NC;
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= d.Pc) return;
+  const int p = d.coupled_pts[ci];
+  const int ro = d.np6 + 3 * ci;
+  const double* X = d.points[cur] + 3 * (size_t)p;
+  double H[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0}, Hcp[3 * NC];
+  for (int k = 0; k < 3 * NC; ++k) Hcp[k] = 0.0;
+  for (int t = d.pt_trk_begin[p]; t < d.pt_trk_begin[p + 1]; ++t) {
+    const double* rc = d.rec[cur] + (size_t)t * RS;
+    const int f = d.trk_frame[t];
+    const double* fe = d.frames[cur] + (size_t)f * kFrameStride;
+    const double* R = fe;
+    const double A[6] = {rc[0], rc[1], rc[2], rc[3], rc[4], rc[5]};
+    double AR[9];
+    for (int j = 0; j < 3; ++j) {
+      AR[0 + j] = A[0] * R[j] + A[1] * R[3 + j] + A[2] * R[6 + j];
+      AR[3 + j] = A[1] * R[j] + A[3] * R[3 + j] + A[4] * R[6 + j];
+      AR[6 + j] = A[2] * R[j] + A[4] * R[3 + j] + A[5] * R[6 + j];
+    }
+    H[0] += R[0] * AR[0] + R[3] * AR[3] + R[6] * AR[6];
+    H[1] += R[0] * AR[1] + R[3] * AR[4] + R[6] * AR[7];
+    H[2] += R[0] * AR[2] + R[3] * AR[5] + R[6] * AR[8];
+    H[3] += R[1] * AR[1] + R[4] * AR[4] + R[7] * AR[7];
+    H[4] += R[1] * AR[2] + R[4] * AR[5] + R[7] * AR[8];
+    H[5] += R[2] * AR[2] + R[5] * AR[5] + R[8] * AR[8];
+    for (int j = 0; j < 3; ++j) gp[j] += R[j] * rc[6] + R[3 + j] * rc[7] + R[6 + j] * rc[8];
+    for (int c = 0; c < NC; ++c)
+      for (int j = 0; j < 3; ++j)
+        Hcp[3 * c + j] += rc[9 + c] * R[j] + rc[9 + NC + c] * R[3 + j] + rc[9 + 2 * NC + c] * R[6 + j];
+    if (d.refine_poses) {  // S[point, pose f] += V^T
+      double m[9];
+      track_M(fe, X, m);
+      for (int a = 0; a < 6; ++a)
+        for (int j = 0; j < 3; ++j) {
+          double v;
+          if (a < 3) v = m[3 * a] * AR[j] + m[3 * a + 1] * AR[3 + j] + m[3 * a + 2] * AR[6 + j];
+          else v = AR[3 * (a - 3) + j];
+          *S_at(d, ro + j, 6 * f + a) += v;
+        }
+    }
+  }
+  *S_at(d, ro + 0, ro + 0) += H[0];
+  *S_at(d, ro + 1, ro + 0) += H[1];
+  *S_at(d, ro + 2, ro + 0) += H[2];
+  *S_at(d, ro + 1, ro + 1) += H[3];
+  *S_at(d, ro + 2, ro + 1) += H[4];
+  *S_at(d, ro + 2, ro + 2) += H[5];
+  d.hdiag[ro + 0] += H[0];
+  d.hdiag[ro + 1] += H[3];
+  d.hdiag[ro + 2] += H[5];
+  for (int j = 0; j < 3; ++j) {
+    d.g[ro + j] += gp[j];
+    d.gfull[ro + j] += gp[j];
+  }
+  for (int c = 0; c < NC; ++c) {
+    const int r = d.cam_red[c];
+    if (r < 0) continue;
+    for (int j = 0; j < 3; ++j) *S_at(d, r, ro + j) += Hcp[3 * c + j];
+  }
+}
+
+// Distance constraints (OurConstraintFunctionBundle, no loss) between coupled points; rank 0 only, one thread.
+__global__ void k_constraints(Dev d) {
+  LmState* st = d.st;
+  if (st->done || d.rank != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double* pts = d.points[st->cur];
+  for (int k = 0; k < d.K; ++k) {
+    const int p1 = d.c_p1[k], p2 = d.c_p2[k];
+    double r, j[3];
+    distance_eval(pts + 3 * p1, pts + 3 * p2, d.c_dist[k], d.c_sigma[k], r, j);
+    const int o1 = d.np6 + 3 * d.pt_coupled[p1], o2 = d.np6 + 3 * d.pt_coupled[p2];
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b <= a; ++b) {
+        *S_at(d, o1 + a, o1 + b) += j[a] * j[b];
+        *S_at(d, o2 + a, o2 + b) += j[a] * j[b];
+      }
+      for (int b = 0; b < 3; ++b) {
+        if (o1 > o2) *S_at(d, o1 + a, o2 + b) -= j[a] * j[b];
+        else if (o2 > o1) *S_at(d, o2 + a, o1 + b) -= j[a] * j[b];
+      }
+      d.g[o1 + a] += j[a] * r;
+      d.g[o2 + a] -= j[a] * r;
+      d.gfull[o1 + a] += j[a] * r;
+      d.gfull[o2 + a] -= j[a] * r;
+      d.hdiag[o1 + a] += j[a] * j[a];
+      d.hdiag[o2 + a] += j[a] * j[a];
+    }
+  }
+}
+
+// Camera block: Hcc, gc of the accepted state (from k_eval_tracks) + the Schur terms of k_points; point
+// gradient statistics into the system scalars.
+__global__ void k_add_camera(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int NC = d.NC, NH = NC * (NC + 1) / 2;
+  const double* cs = d.camsum[st->cur];
+  __shared__ double sp[64];
+  const int v = threadIdx.x;
+  if (v < 64) {
+    double s = 0.0;
+    if (d.refine_points) {
+      if (v == 63) {
+        for (int b = 0; b < d.grid_pts; ++b) s = fmax(s, d.part_pts[(size_t)b * 64 + 63]);
+      } else {
+        for (int b = 0; b < d.grid_pts; ++b) s += d.part_pts[(size_t)b * 64 + v];
+      }
+    }
+    sp[v] = s;
+  }
+  __syncthreads();
+  if (v < NH) {
+    int c1 = 0, h = v;
+    while (h > c1) { h -= c1 + 1; ++c1; }
+    const int r1 = d.cam_red[c1], r2 = d.cam_red[h];
+    if (r1 >= 0 && r2 >= 0) *S_at(d, r1, r2) += cs[v] + sp[v];
+    if (c1 == h && r1 >= 0) d.hdiag[r1] += cs[v];
+  } else if (v < NH + NC) {
+    const int r = d.cam_red[v - NH];
+    if (r >= 0) {
+      d.g[r] += cs[v] + sp[v];
+      d.gfull[r] += cs[v];
+    }
+  } else if (v == NH + NC) {
+    d.sys_scalars[SS_GNORM2] = sp[NH + NC];
+    d.sys_scalars[SS_PTFAIL] = sp[NH + NC + 1];
+    for (int r = 0; r < d.nranks; ++r) d.sys_scalars[SS_COUNT + r] = (r == d.rank) ? sp[63] : 0.0;
+  }
+}
+
+// ================================================================================================
+// C2. finalize the iteration row, termination tests, Jacobi scaling and LM damping of the reduced system
+// (EvaluateGradientAndJacobian's scaling + gradient norms, FinalizeIterationAndCheckIfMinimizerCanContinue,
+//  LevenbergMarquardtStrategy::ComputeStep's diagonal). One CTA.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_finalize(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const Options& o = d.opt;
+  __shared__ double sg2[8], sgm[8];
+  const bool first = st->first != 0;
+  const bool refresh = st->pending_row && st->row.step_is_successful;
+  double g2 = 0.0, gm = 0.0;
+  for (int j = threadIdx.x; j < d.n; j += blockDim.x) {
+    if (first) d.rscale[j] = 1.0 / (1.0 + sqrt(d.hdiag[j]));
+    if (refresh) {
+      // |x - Plus(x, -g)|: identical to |g| except where a box bound of the camera block clips it
+      double gj = d.gfull[j];
+      if (d.recalib) {
+        for (int c = 0; c < d.NC; ++c)
+          if (d.cam_red[c] == j) {
+            const double x = d.camera[st->cur][c];
+            const double xn = fmin(fmax(x - gj, d.cam_lo[c]), d.cam_hi[c]);
+            gj = x - xn;
+          }
+      }
+      g2 += gj * gj;
+      gm = fmax(gm, fabs(gj));
+    }
+  }
+  g2 = warp_sum(g2);
+  gm = warp_max(gm);
+  if ((threadIdx.x & 31) == 0) {
+    sg2[threadIdx.x >> 5] = g2;
+    sgm[threadIdx.x >> 5] = gm;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (st->pending_row) {
+      lfba_iteration& row = st->row;
+      if (refresh) {
+        double t2 = d.sys_scalars[SS_GNORM2], tm = 0.0;
+        for (int w = 0; w < 8; ++w) {
+          t2 += sg2[w];
+          tm = fmax(tm, sgm[w]);
+        }
+        for (int r = 0; r < d.nranks; ++r) tm = fmax(tm, d.sys_scalars[SS_COUNT + r]);
+        st->gnorm = sqrt(t2);
+        st->gmax = tm;
+      }
+      row.gradient_norm = st->gnorm;
+      row.gradient_max_norm = st->gmax;
+      if (row.step_is_successful) {
+        st->n_success++;
+        if (st->x_cost < st->min_cost) st->min_cost = st->x_cost;
+      } else {
+        st->n_fail++;
+      }
+      row.trust_region_radius = st->radius;
+      const unsigned long long now = gtimer();
+      row.iteration_time_s = 1e-9 * (double)(now - st->t_iter);
+      row.cumulative_time_s = 1e-9 * (double)(now - st->t_start);
+      st->t_iter = now;
+      if (st->n_rows < kMaxLog) d.log[st->n_rows] = row;
+      st->n_rows++;
+      st->pending_row = 0;
+      if (row.iteration >= o.max_iter) {
+        st->done = 1;
+        st->termination = LFBA_NO_CONVERGENCE;
+        st->stop_reason = LFBA_STOP_MAX_ITERATIONS;
+      } else if (row.step_is_successful && row.gradient_max_norm <= o.gtol) {
+        st->done = 1;
+        st->termination = LFBA_CONVERGENCE;
+        st->stop_reason = LFBA_STOP_GRADIENT_TOLERANCE;
+      } else if (row.trust_region_radius <= o.rmin) {
+        st->done = 1;
+        st->termination = LFBA_CONVERGENCE;
+        st->stop_reason = LFBA_STOP_MIN_RADIUS;
+      }
+      st->iter = row.iteration + 1;
+    }
+    st->first = 0;
+    st->eval_skip = 0;
+    // a point block that is not positive definite makes the linear solve fail (LINEAR_SOLVER_FAILURE)
+    st->solve_ok = d.sys_scalars[SS_PTFAIL] > 0.0 ? 0 : 1;
+  }
+  __syncthreads();
+  if (st->done) return;
+  const double mu = st->radius;
+  for (int j = threadIdx.x; j < d.n; j += blockDim.x) {
+    const double s2 = d.rscale[j] * d.rscale[j];
+    const double dm = fmin(fmax(s2 * d.hdiag[j], o.min_diag), o.max_diag) / (mu * s2);
+    d.rdamp[j] = dm;
+    *S_at(d, j, j) += dm;
+    // augmented row: the reduced right-hand side, forward-substituted for free by the factorisation
+    *S_at(d, d.n, j) = d.g[j];
+  }
+}
+
+// ================================================================================================
+// P. steps and candidate
+// ================================================================================================
+// Per point back substitution y_p = Hpp^-1 (g_p - Hpc y_c - sum_t V_t^T y_f), candidate X+ = X - y_p, and the
+// point's share of: model cost change 1/2 y.(g + D y), |step|^2, |x+|^2, g.delta.
+template <int NC>
+__global__ void __launch_bounds__(128) k_point_step(Dev d) {
+  LmState* st = d.st;
+  if (st->done || !st->solve_ok) return;
+  const int cur = st->cur, cand = 1 - cur;
+  __shared__ double red[4 * 8];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const double* __restrict__ y = d.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.P; p += gridDim.x * blockDim.x) {
+    if (!d.pt_active[p] || d.pt_coupled[p] >= 0) continue;
+    const double* pd = d.pdata + (size_t)p * kPointStride;
+    double h[3] = {0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int r = d.cam_red[c];
+      const double yc = r >= 0 ? y[r] : 0.0;
+      h[0] += pd[12 + 3 * c] * yc;
+      h[1] += pd[13 + 3 * c] * yc;
+      h[2] += pd[14 + 3 * c] * yc;
+    }
+    if (d.refine_poses) {
+      for (int t = d.pt_trk_begin[p]; t < d.pt_trk_begin[p + 1]; ++t) {
+        const double* V = d.vw + (size_t)t * kVWStride;
+        const double* yf = y + 6 * d.trk_frame[t];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          h[0] += V[3 * a] * yf[a];
+          h[1] += V[3 * a + 1] * yf[a];
+          h[2] += V[3 * a + 2] * yf[a];
+        }
+      }
+    }
+    const double gp[3] = {pd[6], pd[7], pd[8]};
+    const double rhs[3] = {gp[0] - h[0], gp[1] - h[1], gp[2] - h[2]};
+    double yp[3];
+    sym3_vec(pd, rhs, yp);
+    const double* X = d.points[cur] + 3 * (size_t)p;
+    double* Xc = d.points[cand] + 3 * (size_t)p;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double xn = X[j] - yp[j];
+      Xc[j] = xn;
+      const double dl = xn - X[j];
+      acc[0] += 0.5 * yp[j] * (gp[j] + pd[9 + j] * yp[j]);
+      acc[1] += dl * dl;
+      acc[2] += xn * xn;
+      acc[3] += gp[j] * dl;
+      if (!isfinite(yp[j])) acc[4] += 1.0;
+    }
+  }
+  block_reduce_store<8>(acc, d.part_step + (size_t)blockIdx.x * 8, red);
+}
+
+// Back substitution output y (reduced) -> candidate camera (SubsetManifold + box bounds), poses, coupled points;
+// reduced-part scalars. One CTA.
+__global__ void __launch_bounds__(256) k_reduced_step(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int cur = st->cur, cand = 1 - cur;
+  __shared__ double red[8 * 8];
+  __shared__ double out[8];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (st->solve_ok) {
+    const double* y = d.y;
+    // poses
+    for (int j = threadIdx.x; j < d.np6; j += blockDim.x) {
+      const double x = d.views[cur][j];
+      const double xn = x - y[j];
+      d.views[cand][j] = xn;
+      if (d.frm_active[j / 6]) {
+        const double dl = xn - x;
+        acc[0] += 0.5 * y[j] * (d.gfull[j] + d.rdamp[j] * y[j]);
+        acc[1] += dl * dl;
+        acc[2] += xn * xn;
+        acc[3] += d.gfull[j] * (-y[j]);
+      }
+      if (!isfinite(y[j])) acc[4] += 1.0;
+    }
+    if (!d.refine_poses)
+      for (int j = threadIdx.x; j < 6 * d.F; j += blockDim.x) d.views[cand][j] = d.views[cur][j];
+    // coupled points
+    for (int j = threadIdx.x; j < 3 * d.Pc; j += blockDim.x) {
+      const int r = d.np6 + j;
+      const int p = d.coupled_pts[j / 3];
+      const double x = d.points[cur][3 * (size_t)p + j % 3];
+      const double xn = x - y[r];
+      d.points[cand][3 * (size_t)p + j % 3] = xn;
+      const double dl = xn - x;
+      acc[0] += 0.5 * y[r] * (d.gfull[r] + d.rdamp[r] * y[r]);
+      acc[1] += dl * dl;
+      acc[2] += xn * xn;
+      acc[3] += d.gfull[r] * (-y[r]);
+      if (!isfinite(y[r])) acc[4] += 1.0;
+    }
+    // camera block: all 17 entries count in |x|; held-constant and inactive entries do not move
+    for (int c = threadIdx.x; c < 17; c += blockDim.x) {
+      const double x = d.camera[cur][c];
+      double xn = x;
+      const int r = c < d.NC ? d.cam_red[c] : -1;
+      if (r >= 0) {
+        xn = x - y[r];
+        acc[0] += 0.5 * y[r] * (d.gfull[r] + d.rdamp[r] * y[r]);
+        acc[3] += d.gfull[r] * (-y[r]);
+        if (!isfinite(y[r])) acc[4] += 1.0;
+      }
+      xn = fmin(fmax(xn, d.cam_lo[c]), d.cam_hi[c]);
+      d.camera[cand][c] = xn;
+      const double dl = xn - x;
+      acc[1] += dl * dl;
+      acc[2] += xn * xn;
+    }
+  }
+  block_reduce_store<8>(acc, out, red);
+  if (threadIdx.x == 0) {
+    st->mcc_red = out[0];
+    st->step2_red = out[1];
+    st->norm2_red = out[2];
+    st->gdelta_red = out[3];
+    if (out[4] > 0.0) st->solve_ok = 0;
+    st->eval_skip = st->solve_ok ? 0 : 1;
+  }
+}
+
+// Start of a solve: candidate := initial parameters, |x0|^2 partials (k_reduce_eval reads them in round 0).
+__global__ void __launch_bounds__(128) k_init_norms(Dev d) {
+  __shared__ double red[4 * 8];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int cand = 1 - d.st->cur;
+  if (d.refine_points)
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.P; p += gridDim.x * blockDim.x) {
+      if (!d.pt_active[p] || d.pt_coupled[p] >= 0) continue;
+      const double* X = d.points[cand] + 3 * (size_t)p;
+      acc[2] += X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
+    }
+  block_reduce_store<8>(acc, d.part_step + (size_t)blockIdx.x * 8, red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int c = 0; c < 17; ++c) s += d.camera[cand][c] * d.camera[cand][c];
+    if (d.refine_poses)
+      for (int f = 0; f < d.F; ++f)
+        if (d.frm_active[f])
+          for (int j = 0; j < 6; ++j) s += d.views[cand][6 * f + j] * d.views[cand][6 * f + j];
+    for (int c = 0; c < d.Pc; ++c) {
+      const double* X = d.points[cand] + 3 * (size_t)d.coupled_pts[c];
+      s += X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
+    }
+    d.st->norm2_red = s;
+    d.st->mcc_red = d.st->step2_red = d.st->gdelta_red = 0.0;
+  }
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+template <int NC>
+static void launch_eval_nc(const Dev& d, int L, int grid, cudaStream_t s) {
+  switch (L) {
+    case 1: k_eval_tracks<NC, 1><<<grid, 128, 0, s>>>(d); break;
+    case 2: k_eval_tracks<NC, 2><<<grid, 128, 0, s>>>(d); break;
+    case 4: k_eval_tracks<NC, 4><<<grid, 128, 0, s>>>(d); break;
+    case 8: k_eval_tracks<NC, 8><<<grid, 128, 0, s>>>(d); break;
+    default: k_eval_tracks<NC, 16><<<grid, 128, 0, s>>>(d); break;
+  }
+}
+
+#define LFBA_DISPATCH_NC(NCV, CALL)   \
+  switch (NCV) {                      \
+    case 5: { constexpr int NC = 5; CALL; } break; \
+    case 6: { constexpr int NC = 6; CALL; } break; \
+    case 7: { constexpr int NC = 7; CALL; } break; \
+    case 8: { constexpr int NC = 8; CALL; } break; \
+    default: { constexpr int NC = 9; CALL; } break; \
+  }
+
+void launch_tables(const Dev& d, cudaStream_t s) {
+  const int n = d.NL > d.F ? d.NL : d.F;
+  k_tables<<<(n + 127) / 128, 128, 0, s>>>(d);
+}
+void launch_eval(const Dev& d, int L, cudaStream_t s) {
+  LFBA_DISPATCH_NC(d.NC, launch_eval_nc<NC>(d, L, d.grid_eval, s));
+}
+void launch_reduce_eval(const Dev& d, cudaStream_t s) { k_reduce_eval<<<1, 128, 0, s>>>(d); }
+void launch_control_accept(const Dev& d, cudaStream_t s) { k_control_accept<<<1, 1, 0, s>>>(d); }
+int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
+  int launches = 0;
+  if (d.refine_points) {
+    LFBA_DISPATCH_NC(d.NC, (k_points<NC><<<d.grid_pts, 128, 0, s>>>(d)));
+    ++launches;
+  }
+  if (d.refine_poses) {
+    dim3 grid(d.F, frame_splits);
+    k_frame_pose<<<grid, 128, 0, s>>>(d);
+    LFBA_DISPATCH_NC(d.NC, (k_frame_cam<NC><<<grid, 128, 0, s>>>(d)));
+    launches += 2;
+    if (d.refine_points && d.npairs > 0) {
+      k_pairs<<<(d.npairs + 3) / 4, 128, 0, s>>>(d);
+      ++launches;
+    }
+  }
+  if (d.Pc > 0) {
+    LFBA_DISPATCH_NC(d.NC, (k_coupled<NC><<<(d.Pc + 31) / 32, 32, 0, s>>>(d)));
+    ++launches;
+  }
+  if (d.K > 0) {
+    k_constraints<<<1, 32, 0, s>>>(d);
+    ++launches;
+  }
+  k_add_camera<<<1, 64, 0, s>>>(d);
+  return launches + 1;
+}
+void launch_finalize(const Dev& d, cudaStream_t s) { k_finalize<<<1, 256, 0, s>>>(d); }
+int launch_steps(const Dev& d, cudaStream_t s) {
+  int launches = 1;
+  if (d.refine_points) {
+    LFBA_DISPATCH_NC(d.NC, (k_point_step<NC><<<d.grid_pts, 128, 0, s>>>(d)));
+    ++launches;
+  }
+  k_reduced_step<<<1, 256, 0, s>>>(d);
+  return launches;
+}
+void launch_init_norms(const Dev& d, cudaStream_t s) { k_init_norms<<<d.grid_pts, 128, 0, s>>>(d); }
+
+}  // namespace lfba

@@ -1,0 +1,450 @@
+// lfba_math.cuh — per-item arithmetic of the LF-BA hot path, written as __host__ __device__ functions so
+// that the CUDA kernels (lfba_kernels.cu) and the CPU test harness (tests/cpu_harness) run the SAME code.
+//
+// What is computed (reference file:line it replaces):
+//   cam_model_init   camera-block decode of OurCostFunctionBundle::operator_function
+//                    (src/BundleAdjustment/BundleAdjustment.h:123-146) + per-evaluation scalars
+//   lens_entry       the 10-step fixed-point undistortion of a micro-lens centre (src/CameraModel.h:93-125)
+//                    AND its exact forward-mode derivative recurrence (what Ceres' Jets carry through the
+//                    loop), once per distinct lens instead of once per observation
+//   frame_entry      R = Rx Ry Rz and dR/da_k of RigidBody::getTransformationMatrix (src/CameraModel.h:246-264),
+//                    once per frame instead of once per observation
+//   track_setup      everything that depends only on (camera, pose, point): P_c = R X + t and the
+//                    per-track scalars of the analytic Jacobian
+//   obs_eval         residual (2) + analytic Jacobian of CameraModel::projectPoint (src/CameraModel.h:127-195)
+//                    w.r.t. the camera-frame point (G, 2x3) and the live camera parameters (Jc, 2xNC)
+//   robust_scale     ceres::CauchyLoss(a) + Corrector (rho'' < 0 branch): sqrt(rho') and rho
+// The reference differentiates with ceres::Jet<double,26>; here the derivative is analytic. The chain rule
+// through pose and point is applied per TRACK (point, frame), not per observation:
+//   J_i = [ Jc_i | G_i M | G_i R ],  M = [dR/da0 X, dR/da1 X, dR/da2 X, I3]  
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LFBA_HD __host__ __device__ __forceinline__
+#else
+#define LFBA_HD inline
+#endif
+
+namespace lfba {
+
+constexpr int kMaxNC = 9;         // live camera parameters: 5 + nRadial(<=2) + 2*tangential
+constexpr int kLensStride = 16;   // doubles per lens-table entry (one 128-byte line)
+constexpr int kFrameStride = 40;  // doubles per frame-table entry: R(9) dR0(9) dR1(9) dR2(9) t(3) pad(1)
+
+// lens-table entry layout
+//  [0] mx [1] my                      lens centre (raw px)
+//  [2] ux [3] uy                      u10: undistorted centre on the MLA plane (mm), before the mlAdj scaling
+//  [4] dux/dc3 [5] duy/dc3            derivative w.r.t. camera[3] (cx)
+//  [6] dux/dc4 [7] duy/dc4            derivative w.r.t. camera[4] (cy)
+//  [8..9] d/dk0  [10..11] d/dk1  [12..13] d/dt0  [14..15] d/dt1
+
+struct CamModel {
+  int n_radial, tangential, ml_adjust, robust, any_dist, nc;
+  double fL, bL0, B;    // |camera[0..2]|
+  double sg[3];         // sign of camera[0..2]: d|x|/dx with Jet semantics (x < 0 ? -1 : +1)
+  double crx, cry;      // c_raw = |(c + 0.5) * scale - 0.5|
+  double dcrx, dcry;    // d c_raw / d camera[3], camera[4]
+  double sx, sy, isx, isy;  // raw pixel size (mm) and reciprocal
+  double k0, k1, t0, t1;
+  double invD, alpha, zC0, gB, inv_fL, gamma;
+  double dalpha_dfL, dalpha_dbL0, dz_dfL, dz_dbL0, dgB_dfL, dgB_dbL0, dgB_dB, dgamma_dbL0, dgamma_dB;
+  double loss_b, loss_c;  // Cauchy: b = a^2, c = 1/b
+};
+
+LFBA_HD void cam_model_init(CamModel& m, const double* c, uint32_t config, double spx, double spy, double scale,
+                            double loss_a) {
+  m.n_radial = (int)(config & 3u);
+  m.tangential = (config & 0x4u) ? 1 : 0;
+  m.ml_adjust = (config & 0x800u) ? 1 : 0;
+  m.robust = (config & 0x200u) ? 1 : 0;
+  m.any_dist = (m.n_radial > 0 || m.tangential) ? 1 : 0;
+  m.nc = 5 + m.n_radial + 2 * m.tangential;
+  m.fL = fabs(c[0]);
+  m.bL0 = fabs(c[1]);
+  m.B = fabs(c[2]);
+  for (int i = 0; i < 3; ++i) m.sg[i] = c[i] < 0.0 ? -1.0 : 1.0;
+  const double cx_in = (c[3] + 0.5) * scale - 0.5, cy_in = (c[4] + 0.5) * scale - 0.5;
+  m.crx = fabs(cx_in);
+  m.cry = fabs(cy_in);
+  m.dcrx = (cx_in < 0.0 ? -1.0 : 1.0) * scale;
+  m.dcry = (cy_in < 0.0 ? -1.0 : 1.0) * scale;
+  m.sx = spx / scale;
+  m.sy = spy / scale;
+  m.isx = 1.0 / m.sx;
+  m.isy = 1.0 / m.sy;
+  m.k0 = m.n_radial > 0 ? c[5] : 0.0;
+  m.k1 = m.n_radial > 1 ? c[6] : 0.0;
+  m.t0 = m.tangential ? c[5 + m.n_radial] : 0.0;
+  m.t1 = m.tangential ? c[6 + m.n_radial] : 0.0;
+  const double D = m.fL - m.bL0;
+  m.invD = 1.0 / D;
+  m.alpha = m.fL * m.invD;
+  m.zC0 = m.fL * m.bL0 * m.invD;
+  m.gB = m.fL * m.B * m.invD;
+  m.inv_fL = 1.0 / m.fL;
+  const double id2 = m.invD * m.invD;
+  m.dalpha_dfL = -m.bL0 * id2;
+  m.dalpha_dbL0 = m.fL * id2;
+  m.dz_dfL = -m.bL0 * m.bL0 * id2;
+  m.dz_dbL0 = m.fL * m.fL * id2;
+  m.dgB_dfL = m.B * m.dalpha_dfL;
+  m.dgB_dbL0 = m.B * m.dalpha_dbL0;
+  m.dgB_dB = m.alpha;
+  if (m.ml_adjust) {
+    const double s = m.bL0 + m.B, is2 = 1.0 / (s * s);
+    m.gamma = m.bL0 / s;
+    m.dgamma_dbL0 = m.B * is2;
+    m.dgamma_dB = -m.bL0 * is2;
+  } else {
+    m.gamma = 1.0;
+    m.dgamma_dbL0 = 0.0;
+    m.dgamma_dB = 0.0;
+  }
+  m.loss_b = loss_a * loss_a;
+  m.loss_c = 1.0 / m.loss_b;
+}
+
+// radial + tangential shift (src/CameraModel.h:205-241), value only
+LFBA_HD void dist_shift(const CamModel& m, double x, double y, double& dx, double& dy) {
+  // same expression tree as dist_shift_jac so both paths round identically
+  const double xx = x * x, yy = y * y, xy = x * y;
+  const double r2 = xx + yy, r4 = r2 * r2;
+  const double dr = m.k0 * r2 + m.k1 * r4;
+  dx = x * dr + m.t0 * (r2 + 2.0 * xx) + 2.0 * m.t1 * xy;
+  dy = y * dr + m.t1 * (r2 + 2.0 * yy) + 2.0 * m.t0 * xy;
+}
+
+// shift, its 2x2 Jacobian A = d(shift)/d(x,y) (row-major) and d(shift)/d(k0,k1,t0,t1) (each a 2-vector)
+LFBA_HD void dist_shift_jac(const CamModel& m, double x, double y, double& dx, double& dy, double A[4],
+                            double dk0[2], double dk1[2], double dt0[2], double dt1[2]) {
+  const double xx = x * x, yy = y * y, xy = x * y;
+  const double r2 = xx + yy, r4 = r2 * r2;
+  const double dr = m.k0 * r2 + m.k1 * r4;
+  const double ddr = m.k0 + 2.0 * m.k1 * r2;  // d(dr)/d(r2)
+  dx = x * dr + m.t0 * (r2 + 2.0 * xx) + 2.0 * m.t1 * xy;
+  dy = y * dr + m.t1 * (r2 + 2.0 * yy) + 2.0 * m.t0 * xy;
+  A[0] = dr + 2.0 * xx * ddr + 6.0 * m.t0 * x + 2.0 * m.t1 * y;
+  A[1] = 2.0 * xy * ddr + 2.0 * m.t0 * y + 2.0 * m.t1 * x;
+  A[2] = 2.0 * xy * ddr + 2.0 * m.t1 * x + 2.0 * m.t0 * y;
+  A[3] = dr + 2.0 * yy * ddr + 6.0 * m.t1 * y + 2.0 * m.t0 * x;
+  dk0[0] = x * r2;
+  dk0[1] = y * r2;
+  dk1[0] = x * r4;
+  dk1[1] = y * r4;
+  dt0[0] = r2 + 2.0 * xx;
+  dt0[1] = 2.0 * xy;
+  dt1[0] = 2.0 * xy;
+  dt1[1] = r2 + 2.0 * yy;
+}
+
+// One lens-table entry: u_0 = cd, u_i = cd - shift(u_{i-1}), i = 1..10 (exactly ten steps, src/CameraModel.h:109),
+// carrying U_i = du_i/dcd (2x2) and E_i = du_i/d(k0,k1,t0,t1) (2x4) through the same ten steps:
+//   U_i = I - A(u_{i-1}) U_{i-1},   E_i = -A(u_{i-1}) E_{i-1} - dshift/dtheta(u_{i-1}).
+LFBA_HD void lens_entry(const CamModel& m, double mx, double my, double* e) {
+  const double cdx = (mx - m.crx) * m.sx, cdy = (my - m.cry) * m.sy;
+  double ux = cdx, uy = cdy;
+  double U[4] = {1.0, 0.0, 0.0, 1.0};
+  double E[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // E[2*k + row], k = k0,k1,t0,t1
+  if (m.any_dist) {
+    for (int it = 0; it < 10; ++it) {
+      double dx, dy, A[4], d[8];
+      dist_shift_jac(m, ux, uy, dx, dy, A, d + 0, d + 2, d + 4, d + 6);
+      const double n0 = 1.0 - (A[0] * U[0] + A[1] * U[2]), n1 = -(A[0] * U[1] + A[1] * U[3]);
+      const double n2 = -(A[2] * U[0] + A[3] * U[2]), n3 = 1.0 - (A[2] * U[1] + A[3] * U[3]);
+      U[0] = n0;
+      U[1] = n1;
+      U[2] = n2;
+      U[3] = n3;
+      for (int k = 0; k < 4; ++k) {
+        const double ex = E[2 * k], ey = E[2 * k + 1];
+        E[2 * k] = -(A[0] * ex + A[1] * ey) - d[2 * k];
+        E[2 * k + 1] = -(A[2] * ex + A[3] * ey) - d[2 * k + 1];
+      }
+      ux = (cdx - dx);
+      uy = (cdy - dy);
+    }
+  }
+  e[0] = mx;
+  e[1] = my;
+  e[2] = ux;
+  e[3] = uy;
+  // d cd / d camera[3] = (-dcrx * sx, 0);  d cd / d camera[4] = (0, -dcry * sy)
+  const double fx = -m.dcrx * m.sx, fy = -m.dcry * m.sy;
+  e[4] = U[0] * fx;
+  e[5] = U[2] * fx;
+  e[6] = U[1] * fy;
+  e[7] = U[3] * fy;
+  for (int k = 0; k < 8; ++k) e[8 + k] = E[k];
+}
+
+// R = Rx(a0) Ry(a1) Rz(a2) (row-major) and dR/da_k; f[36..38] = translation.
+LFBA_HD void frame_entry(const double* v, double* f) {
+  const double c0 = cos(v[0]), s0 = sin(v[0]);
+  const double c1 = cos(v[1]), s1 = sin(v[1]);
+  const double c2 = cos(v[2]), s2 = sin(v[2]);
+  double* R = f;
+  R[0] = c1 * c2;
+  R[1] = -c1 * s2;
+  R[2] = s1;
+  R[3] = s0 * s1 * c2 + c0 * s2;
+  R[4] = -s0 * s1 * s2 + c0 * c2;
+  R[5] = -s0 * c1;
+  R[6] = -c0 * s1 * c2 + s0 * s2;
+  R[7] = c0 * s1 * s2 + s0 * c2;
+  R[8] = c0 * c1;
+  double* d0 = f + 9;  // d/da0: derivative of (s0, c0) -> (c0, -s0)
+  d0[0] = 0.0;
+  d0[1] = 0.0;
+  d0[2] = 0.0;
+  d0[3] = c0 * s1 * c2 - s0 * s2;
+  d0[4] = -c0 * s1 * s2 - s0 * c2;
+  d0[5] = -c0 * c1;
+  d0[6] = s0 * s1 * c2 + c0 * s2;
+  d0[7] = -s0 * s1 * s2 + c0 * c2;
+  d0[8] = -s0 * c1;
+  double* d1 = f + 18;  // d/da1
+  d1[0] = -s1 * c2;
+  d1[1] = s1 * s2;
+  d1[2] = c1;
+  d1[3] = s0 * c1 * c2;
+  d1[4] = -s0 * c1 * s2;
+  d1[5] = s0 * s1;
+  d1[6] = -c0 * c1 * c2;
+  d1[7] = c0 * c1 * s2;
+  d1[8] = -c0 * s1;
+  double* d2 = f + 27;  // d/da2
+  d2[0] = -c1 * s2;
+  d2[1] = -c1 * c2;
+  d2[2] = 0.0;
+  d2[3] = -s0 * s1 * s2 + c0 * c2;
+  d2[4] = -s0 * s1 * c2 - c0 * s2;
+  d2[5] = 0.0;
+  d2[6] = c0 * s1 * s2 + s0 * c2;
+  d2[7] = c0 * s1 * c2 - s0 * s2;
+  d2[8] = 0.0;
+  f[36] = v[3];
+  f[37] = v[4];
+  f[38] = v[5];
+  f[39] = 0.0;
+}
+
+LFBA_HD void mat3_vec(const double* R, const double* x, double* y) {
+  y[0] = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
+  y[1] = R[3] * x[0] + R[4] * x[1] + R[5] * x[2];
+  y[2] = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
+}
+
+// camera-frame point of a track
+LFBA_HD void track_point(const double* fe, const double* X, double Pc[3]) {
+  mat3_vec(fe, X, Pc);
+  Pc[0] += fe[36];
+  Pc[1] += fe[37];
+  Pc[2] += fe[38];
+}
+
+struct TrackCtx {
+  double Px, Py;   // P_c.xy / q_z
+  double a1;       // alpha / q_z
+  double g1;       // gB / q_z
+  double kl;       // d w0 / d u   (scalar): mlAdj ? (kappa + 1) * gamma : kappa
+  double af, bf, ab, bb, aB, bB;  // d w0 / d(fL,bL0,B) = u * a + q * b  (signs of the |.| folded in)
+};
+
+LFBA_HD void track_setup(const CamModel& m, const double Pc[3], TrackCtx& t) {
+  const double iq = 1.0 / (Pc[2] + m.zC0);
+  t.Px = Pc[0] * iq;
+  t.Py = Pc[1] * iq;
+  t.a1 = m.alpha * iq;
+  t.g1 = m.gB * iq;
+  const double kappa = m.gB * (t.a1 - m.inv_fL);  // d pm / d cu
+  const double k1 = m.ml_adjust ? kappa + 1.0 : kappa;
+  t.kl = k1 * m.gamma;
+  // d pm / d theta at fixed cu = cu * a' + q * b'
+  const double af = m.gB * (m.dalpha_dfL * iq + m.inv_fL * m.inv_fL) - m.inv_fL * m.dgB_dfL;
+  const double bf = m.dgB_dfL - t.g1 * m.dz_dfL;
+  const double ab = m.gB * m.dalpha_dbL0 * iq - m.inv_fL * m.dgB_dbL0;
+  const double bb = m.dgB_dbL0 - t.g1 * m.dz_dbL0;
+  const double aB = -m.alpha * m.inv_fL;
+  const double bB = m.alpha;
+  // in terms of u (cu = gamma * u), plus the path through gamma(bL0, B) when mlAdj
+  t.af = m.sg[0] * (m.gamma * af);
+  t.bf = m.sg[0] * bf;
+  t.ab = m.sg[1] * (m.gamma * ab + k1 * m.dgamma_dbL0);
+  t.bb = m.sg[1] * bb;
+  t.aB = m.sg[2] * (m.gamma * aB + k1 * m.dgamma_dB);
+  t.bB = m.sg[2] * bB;
+}
+
+// residual only (candidate-cost evaluation, reprojection statistics)
+LFBA_HD void obs_residual(const CamModel& m, const TrackCtx& t, const double* e, double ox, double oy,
+                          double r[2]) {
+  const double cux = e[2] * m.gamma, cuy = e[3] * m.gamma;
+  const double qx = t.Px + t.a1 * cux, qy = t.Py + t.a1 * cuy;
+  const double pmx = (qx - cux * m.inv_fL) * m.gB, pmy = (qy - cuy * m.inv_fL) * m.gB;
+  double wx, wy;
+  if (m.ml_adjust) {
+    wx = pmx + cux;
+    wy = pmy + cuy;
+    if (m.any_dist) {
+      double dx, dy;
+      dist_shift(m, wx, wy, dx, dy);
+      wx += dx;
+      wy += dy;
+    }
+  } else {
+    wx = pmx + (e[0] - m.crx) * m.sx;
+    wy = pmy + (e[1] - m.cry) * m.sy;
+  }
+  r[0] = (wx * m.isx + m.crx) - ox;
+  r[1] = (wy * m.isy + m.cry) - oy;
+}
+
+// residual + analytic Jacobian. G: 2x3 row-major d r / d P_c.  Jc: 2 x NC row-major, columns in camera-block
+// order [fL, bL0, B, cx, cy, k0.., t0, t1].
+template <int NC>
+LFBA_HD void obs_eval(const CamModel& m, const TrackCtx& t, const double* e, double ox, double oy, double r[2],
+                      double G[6], double* Jc) {
+  const double ux = e[2], uy = e[3];
+  const double cux = ux * m.gamma, cuy = uy * m.gamma;
+  const double qx = t.Px + t.a1 * cux, qy = t.Py + t.a1 * cuy;
+  const double pmx = (qx - cux * m.inv_fL) * m.gB, pmy = (qy - cuy * m.inv_fL) * m.gB;
+  double wx, wy;
+  double M00 = m.isx, M01 = 0.0, M10 = 0.0, M11 = m.isy;  // diag(1/s) (I + A)
+  double dk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool fwd = m.ml_adjust && m.any_dist;
+  if (m.ml_adjust) {
+    wx = pmx + cux;
+    wy = pmy + cuy;
+    if (m.any_dist) {
+      double dx, dy, A[4];
+      dist_shift_jac(m, wx, wy, dx, dy, A, dk + 0, dk + 2, dk + 4, dk + 6);
+      wx += dx;
+      wy += dy;
+      M00 = m.isx * (1.0 + A[0]);
+      M01 = m.isx * A[1];
+      M10 = m.isy * A[2];
+      M11 = m.isy * (1.0 + A[3]);
+    }
+  } else {
+    wx = pmx + (e[0] - m.crx) * m.sx;
+    wy = pmy + (e[1] - m.cry) * m.sy;
+  }
+  r[0] = (wx * m.isx + m.crx) - ox;
+  r[1] = (wy * m.isy + m.cry) - oy;
+
+  // d r / d P_c = M * g1 * [I | -q]
+  G[0] = M00 * t.g1;
+  G[1] = M01 * t.g1;
+  G[2] = -(G[0] * qx + G[1] * qy);
+  G[3] = M10 * t.g1;
+  G[4] = M11 * t.g1;
+  G[5] = -(G[3] * qx + G[4] * qy);
+
+  // fL, bL0, B
+  {
+    const double dfx = ux * t.af + qx * t.bf, dfy = uy * t.af + qy * t.bf;
+    const double dbx = ux * t.ab + qx * t.bb, dby = uy * t.ab + qy * t.bb;
+    const double dBx = ux * t.aB + qx * t.bB, dBy = uy * t.aB + qy * t.bB;
+    Jc[0] = M00 * dfx + M01 * dfy;
+    Jc[NC + 0] = M10 * dfx + M11 * dfy;
+    Jc[1] = M00 * dbx + M01 * dby;
+    Jc[NC + 1] = M10 * dbx + M11 * dby;
+    Jc[2] = M00 * dBx + M01 * dBy;
+    Jc[NC + 2] = M10 * dBx + M11 * dBy;
+  }
+  // cx, cy: through u (lens table), through cd when !mlAdj, and the additive + c_raw of the output
+  {
+    double d3x = t.kl * e[4], d3y = t.kl * e[5];
+    double d4x = t.kl * e[6], d4y = t.kl * e[7];
+    if (!m.ml_adjust) {
+      d3x += -m.dcrx * m.sx;
+      d4y += -m.dcry * m.sy;
+    }
+    Jc[3] = M00 * d3x + M01 * d3y + m.dcrx;
+    Jc[NC + 3] = M10 * d3x + M11 * d3y;
+    Jc[4] = M00 * d4x + M01 * d4y;
+    Jc[NC + 4] = M10 * d4x + M11 * d4y + m.dcry;
+  }
+  // distortion parameters: through u, plus the direct term of the forward distortion (mlAdj only)
+  if (NC > 5) {
+    int col = 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool live = (k == 0 && m.n_radial > 0) || (k == 1 && m.n_radial > 1) || (k >= 2 && m.tangential);
+      if (!live) continue;
+      if (col < NC) {
+        const double dx = t.kl * e[8 + 2 * k], dy = t.kl * e[9 + 2 * k];
+        double jx = M00 * dx + M01 * dy, jy = M10 * dx + M11 * dy;
+        if (fwd) {
+          jx += dk[2 * k] * m.isx;
+          jy += dk[2 * k + 1] * m.isy;
+        }
+        Jc[col] = jx;
+        Jc[NC + col] = jy;
+      }
+      ++col;
+    }
+  }
+}
+
+// CauchyLoss(a) + Corrector for rho'' < 0: returns sqrt(rho') (the factor applied to r and J) and rho(s).
+// Non-robust: factor 1, rho = s.
+LFBA_HD double robust_scale(const CamModel& m, double s, double& rho) {
+  if (!m.robust) {
+    rho = s;
+    return 1.0;
+  }
+  const double sum = 1.0 + s * m.loss_c;
+  rho = m.loss_b * log(sum);
+  return sqrt(1.0 / sum);
+}
+
+// ---- 3x3 symmetric helpers (storage: [a00,a01,a02,a11,a12,a22]) ----
+// inverse of an SPD 3x3 through its Cholesky factor (what Ceres' InvertPSDMatrix<3> does); false if not PD
+LFBA_HD bool spd3_inverse(const double a[6], double inv[6]) {
+  const double l00s = a[0];
+  if (!(l00s > 0.0)) return false;
+  const double l00 = sqrt(l00s), i00 = 1.0 / l00;
+  const double l10 = a[1] * i00, l20 = a[2] * i00;
+  const double l11s = a[3] - l10 * l10;
+  if (!(l11s > 0.0)) return false;
+  const double l11 = sqrt(l11s), i11 = 1.0 / l11;
+  const double l21 = (a[4] - l20 * l10) * i11;
+  const double l22s = a[5] - l20 * l20 - l21 * l21;
+  if (!(l22s > 0.0)) return false;
+  const double l22 = sqrt(l22s), i22 = 1.0 / l22;
+  // inverse of L (lower): m
+  const double m10 = -l10 * i00 * i11;
+  const double m21 = -l21 * i11 * i22;
+  const double m20 = -(l20 * i00 + l21 * m10) * i22;
+  // inv = L^-T L^-1
+  inv[0] = i00 * i00 + m10 * m10 + m20 * m20;
+  inv[1] = m10 * i11 + m20 * m21;
+  inv[2] = m20 * i22;
+  inv[3] = i11 * i11 + m21 * m21;
+  inv[4] = m21 * i22;
+  inv[5] = i22 * i22;
+  return true;
+}
+LFBA_HD void sym3_vec(const double a[6], const double x[3], double y[3]) {
+  y[0] = a[0] * x[0] + a[1] * x[1] + a[2] * x[2];
+  y[1] = a[1] * x[0] + a[3] * x[1] + a[4] * x[2];
+  y[2] = a[2] * x[0] + a[4] * x[1] + a[5] * x[2];
+}
+
+// distance constraint (src/BundleAdjustment/BundleAdjustment.h:262-267): r = (|p1 - p2| - d) / (sigma + 1e-6),
+// j = d r / d p1 = -(d r / d p2)
+LFBA_HD void distance_eval(const double* p1, const double* p2, double dist, double sigma, double& r, double j[3]) {
+  const double dx = p1[0] - p2[0], dy = p1[1] - p2[1], dz = p1[2] - p2[2];
+  const double n = sqrt(dx * dx + dy * dy + dz * dz);
+  const double w = 1.0 / (sigma + 0.000001);
+  r = (n - dist) * w;
+  const double f = w / n;
+  j[0] = dx * f;
+  j[1] = dy * f;
+  j[2] = dz * f;
+}
+
+}  // namespace lfba

@@ -1,0 +1,319 @@
+// lfba_setup.cu — device-side indexing of the observations (see lfba_setup.cuh).
+#include "lfba_setup.cuh"
+
+namespace lfba {
+
+namespace {
+
+struct Temp {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~Temp() { if (p) cudaFree(p); }
+  void reserve(size_t b) {
+    if (b > bytes) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      LFBA_CUDA(cudaMalloc(&p, b));
+      bytes = b;
+    }
+  }
+};
+
+template <class K, class V>
+void sort_pairs(Temp& tmp, const K* kin, K* kout, const V* vin, V* vout, size_t n, cudaStream_t s, int end_bit,
+                bool descending = false) {
+  if (n == 0) return;
+  size_t bytes = 0;
+  if (descending) {
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s);
+    tmp.reserve(bytes);
+    LFBA_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s));
+  } else {
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s);
+    tmp.reserve(bytes);
+    LFBA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s));
+  }
+}
+template <class T>
+void exclusive_sum(Temp& tmp, const T* in, T* out, size_t n, cudaStream_t s) {
+  if (n == 0) return;
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n, s);
+  tmp.reserve(bytes);
+  LFBA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int64_t)n, s));
+}
+int bits_for(uint64_t v) {
+  int b = 1;
+  while (b < 64 && (v >> b) != 0) ++b;
+  return b;
+}
+
+__global__ void k_make_keys(const int32_t* pt, const int32_t* fr, uint64_t* keys, int32_t* vals, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = ((uint64_t)(uint32_t)pt[i] << 32) | (uint32_t)fr[i];
+  vals[i] = (int32_t)i;
+}
+__global__ void k_gather_obs(const int32_t* perm, const double* ox, const double* oy, const double* mx,
+                             const double* my, double2* obs, uint64_t* ka, uint64_t* kb, int32_t* idx, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t j = perm[i];
+  obs[i] = make_double2(ox[j], oy[j]);
+  ka[i] = (uint64_t)__double_as_longlong(my[j]);
+  kb[i] = (uint64_t)__double_as_longlong(mx[j]);
+  idx[i] = (int32_t)i;
+}
+__global__ void k_copy_in(const double* ox, const double* oy, double2* obs_in, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) obs_in[i] = make_double2(ox[i], oy[i]);
+}
+__global__ void k_head_flags(const uint64_t* keys, int32_t* flags, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+__global__ void k_head_flags2(const uint64_t* ka, const uint64_t* kb, int32_t* flags, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || ka[i] != ka[i - 1] || kb[i] != kb[i - 1]) ? 1 : 0;
+}
+__global__ void k_fill_tracks(const uint64_t* keys, const int32_t* flags, const int32_t* tid, int32_t* trk_begin,
+                              int32_t* trk_point, int32_t* trk_frame, int32_t* pt_count, int32_t* fr_count,
+                              int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n || !flags[i]) return;
+  const int t = tid[i];
+  const int p = (int)(keys[i] >> 32), f = (int)(keys[i] & 0xffffffffu);
+  trk_begin[t] = (int32_t)i;
+  trk_point[t] = p;
+  trk_frame[t] = f;
+  atomicAdd(pt_count + p, 1);
+  atomicAdd(fr_count + f, 1);
+}
+__global__ void k_iota(int32_t* a, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+__global__ void k_track_len(const int32_t* trk_begin, int32_t* len, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) len[t] = trk_begin[t + 1] - trk_begin[t];
+}
+__global__ void k_pair_counts(const int32_t* pt_trk_begin, int32_t* cnt, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int w = pt_trk_begin[p + 1] - pt_trk_begin[p];
+  cnt[p] = w * (w - 1) / 2;
+}
+__global__ void k_fill_pairs(const int32_t* pt_trk_begin, const int32_t* trk_frame, const int32_t* off,
+                             uint64_t* keys, uint64_t* vals, int* bw, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int tb = pt_trk_begin[p], te = pt_trk_begin[p + 1];
+  int o = off[p];
+  int mybw = 0;
+  for (int t1 = tb + 1; t1 < te; ++t1)
+    for (int t2 = tb; t2 < t1; ++t2) {  // tracks of a point are sorted by frame: f1 > f2
+      const int f1 = trk_frame[t1], f2 = trk_frame[t2];
+      keys[o] = ((uint64_t)(uint32_t)f1 << 32) | (uint32_t)f2;
+      vals[o] = ((uint64_t)(uint32_t)t1 << 32) | (uint32_t)t2;
+      mybw = max(mybw, f1 - f2);
+      ++o;
+    }
+  if (mybw > 0) atomicMax(bw, mybw);
+}
+__global__ void k_unpack_pairs(const uint64_t* vals, int32_t* t1, int32_t* t2, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  t1[i] = (int32_t)(vals[i] >> 32);
+  t2[i] = (int32_t)(vals[i] & 0xffffffffu);
+}
+__global__ void k_unpack_pair_keys(const uint64_t* keys, int32_t* f1, int32_t* f2, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  f1[i] = (int32_t)(keys[i] >> 32);
+  f2[i] = (int32_t)(keys[i] & 0xffffffffu);
+}
+__global__ void k_fill_lens(const uint64_t* ka, const uint64_t* kb, const int32_t* flags, const int32_t* lid,
+                            const int32_t* idx, int32_t* lens_id, double* lens_xy, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = lid[i] + flags[i] - 1;  // lid is the EXCLUSIVE scan of the head flags
+  lens_id[idx[i]] = l;
+  if (flags[i]) {
+    lens_xy[2 * (size_t)l] = __longlong_as_double((long long)kb[i]);
+    lens_xy[2 * (size_t)l + 1] = __longlong_as_double((long long)ka[i]);
+  }
+}
+__global__ void k_gather_u64(const uint64_t* src, const int32_t* idx, uint64_t* dst, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_scatter_i32(const int32_t* perm, const int32_t* src, int32_t* dst, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[perm[i]] = src[i];
+}
+
+inline unsigned grid_for(int64_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
+
+}  // namespace
+
+void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64_t* launches) {
+  const int64_t N = pb.n_obs;
+  const int P = pb.n_points, F = pb.n_frames;
+  if (N >= (int64_t)2147483647) throw CudaError("more than 2^31-1 observations per rank", LFBA_INVALID_ARGUMENT);
+  ix.N = N;
+  ix.P = P;
+  ix.F = F;
+  Temp tmp;
+  int64_t nl = 0;
+
+  // raw input (input order)
+  DevBuf<double> ox(N), oy(N), mx(N), my(N);
+  ix.point_in.alloc(N);
+  ix.frame_in.alloc(N);
+  ox.upload(pb.obs_x, N, s);
+  oy.upload(pb.obs_y, N, s);
+  mx.upload(pb.ml_x, N, s);
+  my.upload(pb.ml_y, N, s);
+  ix.point_in.upload(pb.point_idx, N, s);
+  ix.frame_in.upload(pb.frame_idx, N, s);
+  ix.obs_in.alloc(N);
+  ix.obs.alloc(N);
+  ix.lens_id.alloc(N);
+  ix.lens_id_in.alloc(N);
+  ix.perm.alloc(N);
+
+  ix.pt_trk_begin.alloc((size_t)P + 1);
+  ix.frm_begin.alloc((size_t)F + 1);
+  DevBuf<int32_t> pt_count((size_t)P + 1), fr_count((size_t)F + 1);
+  pt_count.zero(s);
+  fr_count.zero(s);
+
+  if (N > 0) {
+    k_copy_in<<<grid_for(N), 256, 0, s>>>(ox.p, oy.p, ix.obs_in.p, N);
+    // ---- sort by (point, frame); radix sort is stable, so observations keep their input order inside a track
+    DevBuf<uint64_t> k0(N), k1(N);
+    DevBuf<int32_t> v0(N);
+    k_make_keys<<<grid_for(N), 256, 0, s>>>(ix.point_in.p, ix.frame_in.p, k0.p, v0.p, N);
+    sort_pairs(tmp, k0.p, k1.p, v0.p, ix.perm.p, (size_t)N, s, 32 + bits_for((uint64_t)(P > 0 ? P - 1 : 0)));
+    nl += 3;
+    // ---- gather; lens keys
+    DevBuf<uint64_t> ka(N), kb(N);
+    DevBuf<int32_t> idx(N);
+    k_gather_obs<<<grid_for(N), 256, 0, s>>>(ix.perm.p, ox.p, oy.p, mx.p, my.p, ix.obs.p, ka.p, kb.p, idx.p, N);
+    ox.release();
+    oy.release();
+    mx.release();
+    my.release();
+    // ---- tracks
+    DevBuf<int32_t> flags(N), tid(N);
+    k_head_flags<<<grid_for(N), 256, 0, s>>>(k1.p, flags.p, N);
+    exclusive_sum(tmp, flags.p, tid.p, (size_t)N, s);
+    int32_t last_tid = 0, last_flag = 0;
+    LFBA_CUDA(cudaMemcpyAsync(&last_tid, tid.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LFBA_CUDA(cudaMemcpyAsync(&last_flag, flags.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LFBA_CUDA(cudaStreamSynchronize(s));
+    const int T = last_tid + last_flag;
+    ix.T = T;
+    ix.trk_begin.alloc((size_t)T + 1);
+    ix.trk_point.alloc(T);
+    ix.trk_frame.alloc(T);
+    k_fill_tracks<<<grid_for(N), 256, 0, s>>>(k1.p, flags.p, tid.p, ix.trk_begin.p, ix.trk_point.p, ix.trk_frame.p,
+                                              pt_count.p, fr_count.p, N);
+    const int32_t n32 = (int32_t)N;
+    LFBA_CUDA(cudaMemcpyAsync(ix.trk_begin.p + T, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    nl += 5;
+    // ---- lenses: lexicographic sort on the (mx, my) bit patterns = two stable 64-bit sorts (LSD order)
+    {
+      DevBuf<uint64_t> ka2(N), kb2(N), kbS(N);
+      DevBuf<int32_t> idx2(N), idxS(N);
+      sort_pairs(tmp, ka.p, ka2.p, idx.p, idx2.p, (size_t)N, s, 64);     // by my
+      k_gather_u64<<<grid_for(N), 256, 0, s>>>(kb.p, idx2.p, kb2.p, N);  // carry mx along
+      sort_pairs(tmp, kb2.p, kbS.p, idx2.p, idxS.p, (size_t)N, s, 64);   // by mx, ties keep the my order
+      k_gather_u64<<<grid_for(N), 256, 0, s>>>(ka.p, idxS.p, ka2.p, N);  // my of the fully sorted sequence
+      k_head_flags2<<<grid_for(N), 256, 0, s>>>(ka2.p, kbS.p, flags.p, N);
+      exclusive_sum(tmp, flags.p, tid.p, (size_t)N, s);
+      int32_t lt = 0, lf = 0;
+      LFBA_CUDA(cudaMemcpyAsync(&lt, tid.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      LFBA_CUDA(cudaMemcpyAsync(&lf, flags.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      LFBA_CUDA(cudaStreamSynchronize(s));
+      ix.NL = lt + lf;
+      ix.lens_xy.alloc((size_t)2 * ix.NL);
+      k_fill_lens<<<grid_for(N), 256, 0, s>>>(ka2.p, kbS.p, flags.p, tid.p, idxS.p, ix.lens_id.p, ix.lens_xy.p, N);
+      k_scatter_i32<<<grid_for(N), 256, 0, s>>>(ix.perm.p, ix.lens_id.p, ix.lens_id_in.p, N);
+      nl += 9;
+    }
+  } else {
+    ix.T = 0;
+    ix.NL = 0;
+    ix.trk_begin.alloc(1);
+    ix.trk_begin.zero(s);
+  }
+  const int T = ix.T;
+  // ---- CSR: point -> tracks (tracks are already grouped by point), frame -> tracks
+  exclusive_sum(tmp, pt_count.p, ix.pt_trk_begin.p, (size_t)P + 1, s);
+  exclusive_sum(tmp, fr_count.p, ix.frm_begin.p, (size_t)F + 1, s);
+  ix.h_frame_count.assign((size_t)F + 1, 0);
+  fr_count.download(ix.h_frame_count.data(), (size_t)F + 1, s);
+  ix.frm_trk.alloc(T);
+  ix.eval_order.alloc(T);
+  if (T > 0) {
+    DevBuf<int32_t> iota(T), keys_out(T), len(T);
+    k_iota<<<grid_for(T), 256, 0, s>>>(iota.p, T);
+    sort_pairs(tmp, ix.trk_frame.p, keys_out.p, iota.p, ix.frm_trk.p, (size_t)T, s, bits_for((uint64_t)(F > 0 ? F - 1 : 0)));
+    k_track_len<<<grid_for(T), 256, 0, s>>>(ix.trk_begin.p, len.p, T);
+    sort_pairs(tmp, len.p, keys_out.p, iota.p, ix.eval_order.p, (size_t)T, s, 32, true);
+    nl += 6;
+  }
+  // ---- co-visible frame pairs
+  ix.npairs = 0;
+  ix.bandwidth = 0;
+  ix.n_pair_items = 0;
+  if (T > 0 && P > 0) {
+    DevBuf<int32_t> pcnt((size_t)P + 1), poff((size_t)P + 1);
+    pcnt.zero(s);
+    k_pair_counts<<<grid_for(P), 256, 0, s>>>(ix.pt_trk_begin.p, pcnt.p, P);
+    exclusive_sum(tmp, pcnt.p, poff.p, (size_t)P + 1, s);
+    int32_t total = 0;
+    LFBA_CUDA(cudaMemcpyAsync(&total, poff.p + P, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LFBA_CUDA(cudaStreamSynchronize(s));
+    if (total < 0) throw CudaError("too many co-visible track pairs", LFBA_INVALID_ARGUMENT);
+    ix.n_pair_items = total;
+    if (total > 0) {
+      DevBuf<uint64_t> pk(total), pv(total), pk2(total), pv2(total);
+      DevBuf<int> bw(1);
+      bw.zero(s);
+      k_fill_pairs<<<grid_for(P), 256, 0, s>>>(ix.pt_trk_begin.p, ix.trk_frame.p, poff.p, pk.p, pv.p, bw.p, P);
+      sort_pairs(tmp, pk.p, pk2.p, pv.p, pv2.p, (size_t)total, s, 32 + bits_for((uint64_t)(F > 0 ? F - 1 : 0)));
+      ix.pair_t1.alloc(total);
+      ix.pair_t2.alloc(total);
+      k_unpack_pairs<<<grid_for(total), 256, 0, s>>>(pv2.p, ix.pair_t1.p, ix.pair_t2.p, total);
+      // run-length encode the sorted keys -> distinct (f1, f2) and their item ranges
+      DevBuf<uint64_t> uniq(total);
+      DevBuf<int32_t> counts((size_t)total + 1), nruns(1);
+      size_t bytes = 0;
+      cub::DeviceRunLengthEncode::Encode(nullptr, bytes, pk2.p, uniq.p, counts.p, nruns.p, total, s);
+      tmp.reserve(bytes);
+      LFBA_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, bytes, pk2.p, uniq.p, counts.p, nruns.p, total, s));
+      int32_t nr = 0;
+      LFBA_CUDA(cudaMemcpyAsync(&nr, nruns.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      LFBA_CUDA(cudaMemcpyAsync(&ix.bandwidth, bw.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      LFBA_CUDA(cudaStreamSynchronize(s));
+      ix.npairs = nr;
+      ix.pair_begin.alloc((size_t)nr + 1);
+      ix.pair_f1.alloc(nr);
+      ix.pair_f2.alloc(nr);
+      LFBA_CUDA(cudaMemsetAsync(counts.p + nr, 0, sizeof(int32_t), s));
+      exclusive_sum(tmp, counts.p, ix.pair_begin.p, (size_t)nr + 1, s);
+      k_unpack_pair_keys<<<grid_for(nr), 256, 0, s>>>(uniq.p, ix.pair_f1.p, ix.pair_f2.p, nr);
+      ix.h_pair_f1.resize(nr);
+      ix.h_pair_f2.resize(nr);
+      ix.pair_f1.download(ix.h_pair_f1.data(), nr, s);
+      ix.pair_f2.download(ix.h_pair_f2.data(), nr, s);
+      nl += 8;
+    }
+  }
+  LFBA_CUDA(cudaStreamSynchronize(s));
+  if (launches) *launches += nl;
+}
+
+}  // namespace lfba

@@ -1,0 +1,848 @@
+// lfba_solver.cu — host side of the C ABI (include/lfba.h): problem set-up, the round loop that enqueues the
+// LM kernels, NCCL plumbing, result read-back.
+//
+// Drop-in boundary: lfba_solve() replaces src/CameraCalibration.cpp:858-965 (ceres::Problem construction,
+// Solver::Options, ceres::Solve); the parameter arrays camera[17], views[6F], p3d_w are updated in place to
+// the last accepted iterate like Ceres does. All LM decisions are taken by device kernels; the host enqueues
+// rounds and polls one flag.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "lfba_device.cuh"
+#include "lfba_kernels.h"
+#include "lfba_setup.cuh"
+
+namespace lfba {
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& m) { g_last_error = m; }
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen): inside a PyTorch process this resolves to the libnccl torch already
+// loaded, so torch.distributed and this library share one NCCL; a plain C++ host gets the system one.
+// ------------------------------------------------------------------------------------------------
+struct Nccl {
+  typedef struct ncclComm* comm_t;
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(comm_t*, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void* handle = nullptr;
+  bool ok = false;
+  static Nccl& get() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      const char* names[] = {"libnccl.so.2", "libnccl.so"};
+      for (const char* nm : names) {
+        n.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (n.handle) break;
+      }
+      if (!n.handle) return;
+      n.GetUniqueId = (int (*)(UniqueId*))dlsym(n.handle, "ncclGetUniqueId");
+      n.CommInitRank = (int (*)(comm_t*, int, UniqueId, int))dlsym(n.handle, "ncclCommInitRank");
+      n.CommDestroy = (int (*)(comm_t))dlsym(n.handle, "ncclCommDestroy");
+      n.AllReduce =
+          (int (*)(const void*, void*, size_t, int, int, comm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
+      n.GetErrorString = (const char* (*)(int))dlsym(n.handle, "ncclGetErrorString");
+      n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce;
+    });
+    return n;
+  }
+};
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclInt32 = 2;    // ncclInt32
+constexpr int kNcclSum = 0, kNcclMax = 2;
+
+__global__ void k_point_flags(const int32_t* pt_trk_begin, const int32_t* pt_coupled, int32_t* pt_active, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) pt_active[p] = (pt_trk_begin[p + 1] > pt_trk_begin[p] || pt_coupled[p] >= 0) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Solver {
+  lfba_options opt;
+  uint32_t config = 0;
+  int calib_type = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Nccl::comm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  ProblemIndex ix;
+  Dev d;
+  int lanes = 4;
+  int frame_splits = 1;
+  int n_tiles = 0;
+  int64_t launches = 0;
+  double setup_time = 0;
+  int64_t n_obs_global = 0;
+
+  DevBuf<int32_t> pt_coupled, coupled_pts, pt_active, frm_active, c_p1, c_p2, tile_first, row_c0;
+  DevBuf<int64_t> row_off;
+  DevBuf<double> c_dist, c_sigma;
+  DevBuf<double> camera[2], views[2], points[2], lens, frames[2], rec[2], camsum[2], pdata, pscale, vw;
+  DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one NCCL all-reduce)
+  DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step;
+  DevBuf<LmState> st;
+  DevBuf<lfba_iteration> log;
+  size_t S_len = 0, red_len = 0;
+  int* h_done = nullptr;  // pinned
+  std::vector<int> h_coupled;
+  cudaEvent_t ev[LFBA_NUM_KERNEL_TIMERS + 1];
+  bool ev_made = false;
+
+  ~Solver() {
+    cudaSetDevice(device);
+    if (ev_made)
+      for (auto& e : ev) cudaEventDestroy(e);
+    if (h_done) cudaFreeHost(h_done);
+    if (comm) Nccl::get().CommDestroy(comm);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  void allreduce(void* buf, size_t count, int dtype, int op) {
+    if (nranks <= 1 || count == 0) return;
+    const int rc = Nccl::get().AllReduce(buf, buf, count, dtype, op, comm, stream);
+    if (rc != 0) throw CudaError(std::string("ncclAllReduce: ") + Nccl::get().GetErrorString(rc), LFBA_NCCL_ERROR);
+  }
+
+  void create(const lfba_problem& pb, const lfba_options& o, const lfba_comm* cm) {
+    const double t0 = now_s();
+    opt = o;
+    config = pb.config;
+    calib_type = pb.calib_type;
+    const bool rposes = (config & LFBA_CFG_REFINE_POSES) != 0, rpoints = (config & LFBA_CFG_REFINE_POINTS) != 0;
+    if (!rposes && rpoints)
+      throw CudaError("refinePoses=0 with refine3Dpoints=1 is invalid (null dereference in the reference, "
+                      "src/BundleAdjustment/BundleAdjustment.h:149-152)", LFBA_INVALID_ARGUMENT);
+    if (pb.n_obs < 0 || pb.n_frames <= 0 || pb.n_points <= 0)
+      throw CudaError("empty problem: need n_frames > 0 and n_points > 0", LFBA_INVALID_ARGUMENT);
+    if (pb.n_obs > 0 && (!pb.obs_x || !pb.obs_y || !pb.ml_x || !pb.ml_y || !pb.point_idx || !pb.frame_idx))
+      throw CudaError("null observation array", LFBA_INVALID_ARGUMENT);
+    for (int64_t i = 0; i < pb.n_obs; ++i)
+      if (pb.point_idx[i] < 0 || pb.point_idx[i] >= pb.n_points || pb.frame_idx[i] < 0 ||
+          pb.frame_idx[i] >= pb.n_frames)
+        throw CudaError("observation index out of range", LFBA_INVALID_ARGUMENT);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      throw CudaError("no CUDA device: the LF-BA path has no CPU fallback", LFBA_NO_DEVICE);
+    if (o.device >= 0) device = o.device; else LFBA_CUDA(cudaGetDevice(&device));
+    LFBA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LFBA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw CudaError("device is not sm_100-class: kernels are built for sm_100a only", LFBA_NO_DEVICE);
+    LFBA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    LFBA_CUDA(cudaMallocHost(&h_done, 4 * sizeof(int)));
+    if (cm && cm->nranks > 1) {
+      Nccl& n = Nccl::get();
+      if (!n.ok) throw CudaError("libnccl.so.2 not found", LFBA_NCCL_ERROR);
+      rank = cm->rank;
+      nranks = cm->nranks;
+      Nccl::UniqueId id;
+      std::memcpy(id.internal, cm->nccl_unique_id, 128);
+      const int rc = n.CommInitRank(&comm, nranks, id, rank);
+      if (rc != 0) throw CudaError(std::string("ncclCommInitRank: ") + n.GetErrorString(rc), LFBA_NCCL_ERROR);
+    }
+
+    build_index(pb, ix, stream, &launches);
+    const int P = ix.P, F = ix.F, T = ix.T;
+    const int nrad = (int)(config & 3u), tang = (config & LFBA_CFG_TANGENTIAL) ? 1 : 0;
+    const int NC = 5 + nrad + 2 * tang;
+    const bool recalib = calib_type == LFBA_RECALIBRATION;
+    const bool use_constraints = rpoints && !recalib && pb.n_constraints > 0;  // :916
+    const int K = use_constraints ? pb.n_constraints : 0;
+
+    // ---- coupled points (touched by a distance constraint): kept in the reduced system ----
+    std::vector<int32_t> h_ptc((size_t)P, -1);
+    h_coupled.clear();
+    for (int k = 0; k < K; ++k) {
+      const int a = pb.c_p1[k], b = pb.c_p2[k];
+      if (a < 0 || a >= P || b < 0 || b >= P) throw CudaError("constraint point id out of range", LFBA_INVALID_ARGUMENT);
+      h_ptc[a] = 0;
+      h_ptc[b] = 0;
+    }
+    for (int p = 0; p < P; ++p)
+      if (h_ptc[p] == 0) {
+        h_ptc[p] = (int)h_coupled.size();
+        h_coupled.push_back(p);
+      }
+    const int Pc = (int)h_coupled.size();
+    pt_coupled.alloc(P);
+    pt_coupled.upload(h_ptc.data(), P, stream);
+    coupled_pts.alloc(std::max(1, Pc));
+    coupled_pts.upload(h_coupled.data(), Pc, stream);
+    pt_active.alloc(P);
+    k_point_flags<<<(P + 255) / 256, 256, 0, stream>>>(ix.pt_trk_begin.p, pt_coupled.p, pt_active.p, P);
+    ++launches;
+    c_p1.alloc(std::max(1, K));
+    c_p2.alloc(std::max(1, K));
+    c_dist.alloc(std::max(1, K));
+    c_sigma.alloc(std::max(1, K));
+    if (K) {
+      c_p1.upload(pb.c_p1, K, stream);
+      c_p2.upload(pb.c_p2, K, stream);
+      c_dist.upload(pb.c_dist, K, stream);
+      c_sigma.upload(pb.c_sigma, K, stream);
+    }
+    // ---- frames with observations anywhere, co-visibility bandwidth, observation count: global ----
+    std::vector<int32_t> h_fa((size_t)F + 2, 0);
+    for (int f = 0; f < F; ++f) h_fa[f] = ix.h_frame_count[f] > 0 ? 1 : 0;
+    h_fa[F] = ix.bandwidth;
+    frm_active.alloc((size_t)F + 2);
+    frm_active.upload(h_fa.data(), (size_t)F + 2, stream);
+    allreduce(frm_active.p, (size_t)F + 1, kNcclInt32, kNcclMax);
+    frm_active.download(h_fa.data(), (size_t)F + 1, stream);
+    DevBuf<double> ncount(1);
+    double h_n = (double)ix.N;
+    ncount.upload(&h_n, 1, stream);
+    allreduce(ncount.p, 1, kNcclFloat64, kNcclSum);
+    ncount.download(&h_n, 1, stream);
+    LFBA_CUDA(cudaStreamSynchronize(stream));
+    n_obs_global = (int64_t)(h_n + 0.5);
+    const int bw = h_fa[F];
+
+    // ---- reduced system layout [poses | coupled points | camera | rhs] and its skyline profile ----
+    std::memset(&d, 0, sizeof(d));
+    d.np6 = rposes ? 6 * F : 0;
+    d.Pc = Pc;
+    int ncr = 0;
+    for (int c = 0; c < kMaxNC; ++c) d.cam_red[c] = -1;
+    for (int c = 0; c < NC; ++c) {
+      if (recalib && (c == 0 || c == 2)) continue;  // SubsetManifold(17, {0, 2}) (:930-940)
+      d.cam_red[c] = d.np6 + 3 * Pc + ncr;
+      ++ncr;
+    }
+    d.n_cam_red = ncr;
+    d.n = d.np6 + 3 * Pc + ncr;
+    const int n = d.n, n_aug = n + 1;
+    std::vector<int32_t> h_c0((size_t)n_aug);
+    std::vector<int64_t> h_off((size_t)n_aug + 1);
+    for (int r = 0; r < n_aug; ++r) {
+      int c0 = 0;
+      if (r < d.np6) c0 = 6 * std::max(0, r / 6 - bw);
+      h_c0[r] = c0;
+    }
+    h_off[0] = 0;
+    for (int r = 0; r < n_aug; ++r) h_off[r + 1] = h_off[r] + (int64_t)(r - h_c0[r] + 1);
+    S_len = (size_t)h_off[n_aug];
+    n_tiles = (n_aug + kTile - 1) / kTile;
+    std::vector<int32_t> h_tf((size_t)n_tiles);
+    for (int t = 0; t < n_tiles; ++t) {
+      int m = std::numeric_limits<int>::max();
+      for (int r = t * kTile; r < std::min(n_aug, (t + 1) * kTile); ++r) m = std::min(m, h_c0[r] / kTile);
+      h_tf[t] = m;
+    }
+    row_c0.alloc(n_aug);
+    row_c0.upload(h_c0.data(), n_aug, stream);
+    row_off.alloc((size_t)n_aug + 1);
+    row_off.upload(h_off.data(), (size_t)n_aug + 1, stream);
+    tile_first.alloc(n_tiles);
+    tile_first.upload(h_tf.data(), n_tiles, stream);
+
+    // ---- buffers ----
+    red_len = S_len + 3 * (size_t)n + SS_COUNT + (size_t)nranks;
+    redbuf.alloc(red_len);
+    rscale.alloc(std::max(1, n));
+    rdamp.alloc(std::max(1, n));
+    y.alloc(std::max(1, n));
+    eval_scalars.alloc(ES_COUNT);
+    eval_scalars.zero(stream);
+    for (int b = 0; b < 2; ++b) {
+      camera[b].alloc(17);
+      views[b].alloc((size_t)6 * F);
+      points[b].alloc((size_t)3 * P);
+      frames[b].alloc((size_t)F * kFrameStride);
+      rec[b].alloc((size_t)std::max(1, T) * rec_stride(NC));
+      camsum[b].alloc(64);
+      camsum[b].zero(stream);
+    }
+    lens.alloc((size_t)std::max(1, ix.NL) * kLensStride);
+    pdata.alloc((size_t)P * kPointStride);
+    pdata.zero(stream);
+    pscale.alloc((size_t)3 * P);
+    vw.alloc((size_t)std::max(1, T) * kVWStride);
+    st.alloc(1);
+    log.alloc(kMaxLog);
+
+    // ---- launch geometry ----
+    const int sms = prop.multiProcessorCount;
+    d.grid_eval = std::max(1, std::min(2 * sms, (T * 4 + 127) / 128));
+    d.grid_pts = std::max(1, std::min(4 * sms, (P + 127) / 128));
+    part_pts.alloc((size_t)d.grid_pts * 64);
+    part_step.alloc((size_t)d.grid_pts * 8);
+    part_pts.zero(stream);
+    part_step.zero(stream);
+    // lanes per track: enough (point, frame) groups to fill the machine, at most ~one observation slot wasted
+    {
+      const double mean_len = T > 0 ? (double)ix.N / T : 1.0;
+      const int64_t threads = (int64_t)d.grid_eval * 128;
+      int L = 1;
+      while (L < 16 && (int64_t)T * L < threads * 2 && L * 2 <= mean_len) L *= 2;
+      if (L < 4 && mean_len >= 8) L = 4;
+      lanes = L;
+      d.grid_eval = std::max(1, (int)std::min<int64_t>(2 * sms, ((int64_t)T * L + 127) / 128));
+    }
+    part_eval.alloc((size_t)d.grid_eval * 64);
+    {
+      const int per_frame = F > 0 ? (T + F - 1) / F : 0;
+      frame_splits = std::max(1, std::min(16, std::min((4 * sms) / std::max(1, F), (per_frame + 255) / 256)));
+    }
+
+    // ---- Dev ----
+    d.N = ix.N; d.T = T; d.P = P; d.F = F; d.NL = ix.NL; d.K = K; d.NC = NC;
+    d.rank = rank; d.nranks = nranks; d.config = config; d.recalib = recalib ? 1 : 0;
+    d.refine_poses = rposes ? 1 : 0; d.refine_points = rpoints ? 1 : 0;
+    d.spx = pb.spx; d.spy = pb.spy; d.scale = pb.scale;
+    d.opt.max_iter = o.max_num_iterations; d.opt.ftol = o.function_tolerance; d.opt.ptol = o.parameter_tolerance;
+    d.opt.gtol = o.gradient_tolerance; d.opt.r0 = o.initial_trust_region_radius; d.opt.rmax = o.max_trust_region_radius;
+    d.opt.rmin = o.min_trust_region_radius; d.opt.min_rel_dec = o.min_relative_decrease;
+    d.opt.min_diag = o.min_lm_diagonal; d.opt.max_diag = o.max_lm_diagonal;
+    d.opt.max_invalid = o.max_num_consecutive_invalid_steps; d.opt.loss_a = o.loss_scale;
+    d.obs = ix.obs.p; d.lens_id = ix.lens_id.p; d.trk_point = ix.trk_point.p; d.trk_frame = ix.trk_frame.p;
+    d.trk_begin = ix.trk_begin.p; d.pt_trk_begin = ix.pt_trk_begin.p; d.frm_begin = ix.frm_begin.p;
+    d.frm_trk = ix.frm_trk.p; d.pair_begin = ix.pair_begin.p; d.pair_f1 = ix.pair_f1.p; d.pair_f2 = ix.pair_f2.p;
+    d.pair_t1 = ix.pair_t1.p; d.pair_t2 = ix.pair_t2.p; d.npairs = ix.npairs; d.eval_order = ix.eval_order.p;
+    d.pt_coupled = pt_coupled.p; d.coupled_pts = coupled_pts.p; d.pt_active = pt_active.p; d.frm_active = frm_active.p;
+    d.c_p1 = c_p1.p; d.c_p2 = c_p2.p; d.c_dist = c_dist.p; d.c_sigma = c_sigma.p;
+    for (int c = 0; c < 17; ++c) {
+      d.cam_lo[c] = -std::numeric_limits<double>::max();
+      d.cam_hi[c] = std::numeric_limits<double>::max();
+    }
+    for (int b = 0; b < 2; ++b) {
+      d.camera[b] = camera[b].p; d.views[b] = views[b].p; d.points[b] = points[b].p;
+      d.frames[b] = frames[b].p; d.rec[b] = rec[b].p; d.camsum[b] = camsum[b].p;
+    }
+    d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p;
+    d.S = redbuf.p; d.row_off = row_off.p; d.row_c0 = row_c0.p;
+    d.g = redbuf.p + S_len; d.gfull = d.g + n; d.hdiag = d.gfull + n; d.sys_scalars = d.hdiag + n;
+    d.rscale = rscale.p; d.rdamp = rdamp.p; d.y = y.p; d.eval_scalars = eval_scalars.p;
+    d.part_eval = part_eval.p; d.part_pts = part_pts.p; d.part_step = part_step.p;
+    d.st = st.p; d.log = log.p;
+    for (auto& e : ev) LFBA_CUDA(cudaEventCreate(&e));
+    ev_made = true;
+    LFBA_CUDA(cudaStreamSynchronize(stream));
+    setup_time = now_s() - t0;
+  }
+
+  void set_parameters(const double* cam, const double* vw_, const double* pts) {
+    LFBA_CUDA(cudaSetDevice(device));
+    // the accepted-state slot is 0 until the first accept flips it; the initial point enters as candidate (slot 1)
+    for (int b = 0; b < 2; ++b) {
+      camera[b].upload(cam, 17, stream);
+      views[b].upload(vw_, (size_t)6 * ix.F, stream);
+      points[b].upload(pts, (size_t)3 * ix.P, stream);
+    }
+    if (calib_type == LFBA_RECALIBRATION) {  // bounds from the INITIAL values (:943-951)
+      const int bj[3] = {1, 3, 4};
+      for (int k = 0; k < 3; ++k) {
+        d.cam_lo[bj[k]] = 0.7 * cam[bj[k]];
+        d.cam_hi[bj[k]] = 1.3 * cam[bj[k]];
+      }
+    }
+    LFBA_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  void get_parameters(int which, double* cam, double* vw_, double* pts) {
+    LFBA_CUDA(cudaSetDevice(device));
+    if (cam) camera[which].download(cam, 17, stream);
+    if (vw_) views[which].download(vw_, (size_t)6 * ix.F, stream);
+    if (pts) points[which].download(pts, (size_t)3 * ix.P, stream);
+    LFBA_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  LmState h_state{};
+
+  int run(lfba_summary* sum) {
+    LFBA_CUDA(cudaSetDevice(device));
+    const double t0 = now_s();
+    const int64_t launches0 = launches;
+    LmState init;
+    std::memset(&init, 0, sizeof(init));
+    init.cur = 0;
+    init.solve_ok = 1;
+    init.radius = opt.initial_trust_region_radius;
+    init.decrease_factor = 2.0;
+    // the caller's current parameters live in slot `cur` after a previous run; copy them into the candidate slot
+    LFBA_CUDA(cudaMemcpyAsync(&h_state, st.p, sizeof(LmState), cudaMemcpyDeviceToHost, stream));
+    LFBA_CUDA(cudaMemcpyAsync(st.p, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
+    if (calib_type == LFBA_RECALIBRATION) {
+      // IterationZero of a bounds-constrained problem projects the start point into the box
+      double cam[17];
+      camera[1].download(cam, 17, stream);
+      LFBA_CUDA(cudaStreamSynchronize(stream));
+      for (int c = 0; c < 17; ++c) cam[c] = std::min(std::max(cam[c], d.cam_lo[c]), d.cam_hi[c]);
+      camera[1].upload(cam, 17, stream);
+    }
+    cudaEvent_t e_begin = ev[LFBA_NUM_KERNEL_TIMERS];
+    double kms[LFBA_NUM_KERNEL_TIMERS] = {0};
+    int64_t kcalls[LFBA_NUM_KERNEL_TIMERS] = {0};
+    const bool prof = opt.profile != 0;
+    const bool debug = std::getenv("LFBA_DEBUG") != nullptr;
+    cudaEvent_t e_run0, e_run1;
+    LFBA_CUDA(cudaEventCreate(&e_run0));
+    LFBA_CUDA(cudaEventCreate(&e_run1));
+    LFBA_CUDA(cudaEventRecord(e_run0, stream));
+    launch_init_norms(d, stream);
+    ++launches;
+
+    auto mark = [&](int slot) { if (prof) LFBA_CUDA(cudaEventRecord(ev[slot], stream)); };
+    const int max_rounds = opt.max_num_iterations + 8;
+    int rounds = 0;
+    for (; rounds < max_rounds; ++rounds) {
+      if (prof) LFBA_CUDA(cudaEventRecord(e_begin, stream));
+      launch_tables(d, stream);
+      mark(LFBA_T_LENS);
+      launch_eval(d, lanes, stream);
+      mark(LFBA_T_EVAL);
+      launch_reduce_eval(d, stream);
+      allreduce(d.eval_scalars, ES_COUNT, kNcclFloat64, kNcclSum);
+      launch_control_accept(d, stream);
+      mark(LFBA_T_CONTROL);
+      LFBA_CUDA(cudaMemsetAsync(redbuf.p, 0, red_len * sizeof(double), stream));
+      launches += 5;
+      launches += launch_assembly(d, frame_splits, stream);
+      mark(LFBA_T_SCHUR);
+      allreduce(redbuf.p, red_len, kNcclFloat64, kNcclSum);
+      mark(LFBA_T_ALLREDUCE);
+      launch_finalize(d, stream);
+      mark(LFBA_T_DAMP);
+      launches += 1 + launch_reduced_solve(d, n_tiles, tile_first.p, stream);
+      mark(LFBA_T_CHOL);
+      launches += launch_steps(d, stream);
+      mark(LFBA_T_POINTSTEP);
+      LFBA_CUDA(cudaMemcpyAsync(h_done, &st.p->done, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      LFBA_CUDA(cudaStreamSynchronize(stream));
+      if (prof) {
+        const int order[] = {LFBA_T_LENS, LFBA_T_EVAL, LFBA_T_CONTROL, LFBA_T_SCHUR, LFBA_T_ALLREDUCE, LFBA_T_DAMP,
+                             LFBA_T_CHOL, LFBA_T_POINTSTEP};
+        cudaEvent_t prev = e_begin;
+        for (int k : order) {
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, prev, ev[k]);
+          kms[k] += ms;
+          kcalls[k] += 1;
+          prev = ev[k];
+        }
+      }
+      if (debug) {
+        double es[ES_COUNT];
+        LmState hs;
+        LFBA_CUDA(cudaMemcpy(es, d.eval_scalars, sizeof(es), cudaMemcpyDeviceToHost));
+        LFBA_CUDA(cudaMemcpy(&hs, st.p, sizeof(hs), cudaMemcpyDeviceToHost));
+        std::vector<double> hp((size_t)d.grid_pts * 8), hy((size_t)std::max(1, d.n));
+        part_step.download(hp.data(), hp.size(), stream);
+        y.download(hy.data(), (size_t)d.n, stream);
+        LFBA_CUDA(cudaStreamSynchronize(stream));
+        std::fprintf(stderr, "[lfba dbg] round %d: es cost=%.10e mcc=%.10e step2=%.6e norm2=%.6e gd=%.6e bad=%g | st iter=%d cur=%d "
+                     "done=%d skip=%d ok=%d x_cost=%.10e radius=%.4e red: mcc=%.6e step2=%.6e norm2=%.6e | part_step[0]=%.6e %.6e %.6e\n",
+                     rounds, es[0], es[1], es[2], es[3], es[4], es[5], hs.iter, hs.cur, hs.done, hs.eval_skip, hs.solve_ok,
+                     hs.x_cost, hs.radius, hs.mcc_red, hs.step2_red, hs.norm2_red, hp[0], hp[1], hp[2]);
+        double ymax = 0;
+        for (int j = 0; j < d.n; ++j) ymax = std::max(ymax, std::fabs(hy[j]));
+        std::fprintf(stderr, "[lfba dbg]   |y|max=%.6e y[0..5]=%.4e %.4e %.4e %.4e %.4e %.4e\n", ymax, hy[0], hy[1], hy[2],
+                     d.n > 3 ? hy[3] : 0.0, d.n > 4 ? hy[4] : 0.0, d.n > 5 ? hy[5] : 0.0);
+      }
+      if (*h_done) {
+        ++rounds;
+        break;
+      }
+    }
+    LFBA_CUDA(cudaEventRecord(e_run1, stream));
+    LFBA_CUDA(cudaMemcpyAsync(&h_state, st.p, sizeof(LmState), cudaMemcpyDeviceToHost, stream));
+    LFBA_CUDA(cudaStreamSynchronize(stream));
+    float run_ms = 0.f;
+    cudaEventElapsedTime(&run_ms, e_run0, e_run1);
+    cudaEventDestroy(e_run0);
+    cudaEventDestroy(e_run1);
+    int status = h_state.status;
+    if (h_state.ls_needed) {
+      set_error("projected line search had to contract the step (recalib): not supported by the device loop yet");
+      status = LFBA_FAILURE;
+    }
+    if (!h_state.done) {  // safety net: the round budget ran out (cannot happen: max_iter is tested on device)
+      h_state.termination = LFBA_NO_CONVERGENCE;
+      h_state.stop_reason = LFBA_STOP_MAX_ITERATIONS;
+    }
+    if (sum) {
+      lfba_iteration* rows = sum->iterations;
+      const int cap = sum->iterations_capacity;
+      std::memset(sum, 0, sizeof(*sum));
+      sum->iterations = rows;
+      sum->iterations_capacity = cap;
+      sum->termination_type = h_state.termination;
+      sum->stop_reason = h_state.stop_reason;
+      sum->num_iterations = h_state.n_rows;
+      sum->num_successful_steps = h_state.n_success;
+      sum->num_unsuccessful_steps = h_state.n_fail;
+      sum->reduced_system_size = d.n;
+      sum->final_cost = h_state.x_cost;
+      sum->num_jacobian_evals = h_state.n_jac_evals;
+      sum->num_observations = n_obs_global;
+      sum->num_tracks = ix.T;
+      sum->num_lenses = ix.NL;
+      sum->gpu_launches = launches - launches0;
+      sum->setup_time_s = setup_time;
+      sum->solve_time_s = now_s() - t0;
+      sum->solve_gpu_ms = run_ms;
+      for (int k = 0; k < LFBA_NUM_KERNEL_TIMERS; ++k) {
+        sum->kernel_ms[k] = kms[k];
+        sum->kernel_calls[k] = kcalls[k];
+      }
+      const int nrows = std::min(h_state.n_rows, kMaxLog);
+      std::vector<lfba_iteration> hl((size_t)std::max(1, nrows));
+      if (nrows > 0) log.download(hl.data(), nrows, stream);
+      LFBA_CUDA(cudaStreamSynchronize(stream));
+      if (nrows > 0) sum->initial_cost = hl[0].cost;
+      if (rows)
+        for (int i = 0; i < std::min(nrows, cap); ++i) rows[i] = hl[i];
+      if (opt.minimizer_progress_to_stdout && rank == 0) {  // Ceres' progress table
+        std::printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter  iter_time  total_time\n");
+        for (int i = 0; i < nrows; ++i)
+          std::printf("% 4d % 8e   % 3.2e   % 3.2e  % 3.2e  % 3.2e % 3.2e     % 4d   % 3.2e   % 3.2e\n", hl[i].iteration,
+                      hl[i].cost, hl[i].cost_change, hl[i].gradient_max_norm, hl[i].step_norm, hl[i].relative_decrease,
+                      hl[i].trust_region_radius, 1, hl[i].iteration_time_s, hl[i].cumulative_time_s);
+      }
+    }
+    return status;
+  }
+};
+
+}  // namespace lfba
+
+using namespace lfba;
+
+struct lfba_solver {
+  Solver s;
+};
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const CudaError& e) {
+    set_error(e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_error(e.what());
+    return LFBA_CUDA_ERROR;
+  }
+}
+
+extern "C" {
+
+int lfba_version(void) { return LFBA_VERSION; }
+const char* lfba_last_error(void) { return g_last_error.c_str(); }
+const char* lfba_status_string(int s) {
+  switch (s) {
+    case LFBA_OK: return "ok";
+    case LFBA_INVALID_ARGUMENT: return "invalid argument";
+    case LFBA_NO_DEVICE: return "no usable CUDA device (no CPU fallback)";
+    case LFBA_CUDA_ERROR: return "CUDA error";
+    case LFBA_NCCL_ERROR: return "NCCL error";
+    case LFBA_OUT_OF_MEMORY: return "out of device memory";
+    case LFBA_FAILURE: return "solver failure";
+    default: return "unknown";
+  }
+}
+void lfba_options_init(lfba_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 200;    // src/CameraCalibration.cpp:960
+  o->function_tolerance = 1e-6;   // :958
+  o->parameter_tolerance = 1e-8;  // :959
+  o->gradient_tolerance = 1e-10;  // Ceres default
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->loss_scale = 0.5;                   // ceres::CauchyLoss(0.5), :892
+  o->minimizer_progress_to_stdout = 1;   // :957
+  o->device = -1;
+  o->num_gpus = 1;
+  o->profile = 0;
+}
+int lfba_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major >= 10) ++ok;
+  }
+  return ok;
+}
+int lfba_comm_unique_id(char out[128]) {
+  Nccl& n = Nccl::get();
+  if (!n.ok) {
+    set_error("libnccl.so.2 not found");
+    return LFBA_NCCL_ERROR;
+  }
+  Nccl::UniqueId id;
+  if (n.GetUniqueId(&id) != 0) return LFBA_NCCL_ERROR;
+  std::memcpy(out, id.internal, 128);
+  return LFBA_OK;
+}
+
+int lfba_solver_create(const lfba_problem* pb, const lfba_options* opt, const lfba_comm* comm, lfba_solver** out) {
+  if (!pb || !opt || !out) return LFBA_INVALID_ARGUMENT;
+  *out = nullptr;
+  lfba_solver* h = new lfba_solver();
+  const int rc = guarded([&] {
+    h->s.create(*pb, *opt, comm);
+    return (int)LFBA_OK;
+  });
+  if (rc != LFBA_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return LFBA_OK;
+}
+int lfba_solver_set_parameters(lfba_solver* h, const double* c, const double* v, const double* p) {
+  if (!h || !c || !v || !p) return LFBA_INVALID_ARGUMENT;
+  return guarded([&] {
+    h->s.set_parameters(c, v, p);
+    return (int)LFBA_OK;
+  });
+}
+int lfba_solver_get_parameters(lfba_solver* h, double* c, double* v, double* p) {
+  if (!h) return LFBA_INVALID_ARGUMENT;
+  return guarded([&] {
+    h->s.get_parameters(h->s.h_state.cur, c, v, p);
+    return (int)LFBA_OK;
+  });
+}
+int lfba_solver_run(lfba_solver* h, lfba_summary* sum) {
+  if (!h) return LFBA_INVALID_ARGUMENT;
+  return guarded([&] { return h->s.run(sum); });
+}
+void lfba_solver_destroy(lfba_solver* h) { delete h; }
+
+int lfba_solver_time_eval(lfba_solver* h, int reps, int materialize, double* mean_ms) {
+  if (!h || reps <= 0 || !mean_ms) return LFBA_INVALID_ARGUMENT;
+  return guarded([&] {
+    Solver& s = h->s;
+    LFBA_CUDA(cudaSetDevice(s.device));
+    // evaluate at the accepted parameters: present them as the candidate of a fresh state
+    LmState init;
+    std::memset(&init, 0, sizeof(init));
+    init.cur = 1 - s.h_state.cur;
+    init.solve_ok = 1;
+    LFBA_CUDA(cudaMemcpyAsync(s.st.p, &init, sizeof(LmState), cudaMemcpyHostToDevice, s.stream));
+    cudaEvent_t e0, e1;
+    LFBA_CUDA(cudaEventCreate(&e0));
+    LFBA_CUDA(cudaEventCreate(&e1));
+    DevBuf<double> res, jc, jv, jp, stats;
+    EvalIn in{s.ix.obs_in.p, s.ix.lens_id_in.p, s.ix.point_in.p, s.ix.frame_in.p};
+    EvalOut out{nullptr, nullptr, nullptr, nullptr, nullptr, 1.0};
+    if (materialize) {
+      res.alloc((size_t)2 * s.ix.N);
+      jc.alloc((size_t)34 * s.ix.N);
+      jv.alloc((size_t)12 * s.ix.N);
+      jp.alloc((size_t)6 * s.ix.N);
+      stats.alloc(8);
+      stats.zero(s.stream);
+      out = EvalOut{res.p, jc.p, jv.p, jp.p, stats.p, 1.0};
+    }
+    const int which = s.h_state.cur;
+    launch_tables(s.d, s.stream);
+    if (materialize) launch_tables_for(s.d, which, s.stream);
+    if (materialize) launch_eval_only(s.d, in, out, which, s.stream); else launch_eval(s.d, s.lanes, s.stream);
+    LFBA_CUDA(cudaEventRecord(e0, s.stream));
+    for (int r = 0; r < reps; ++r) {
+      if (materialize) launch_eval_only(s.d, in, out, which, s.stream); else launch_eval(s.d, s.lanes, s.stream);
+    }
+    LFBA_CUDA(cudaEventRecord(e1, s.stream));
+    LFBA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    s.launches += reps + 2;
+    *mean_ms = ms / reps;
+    return (int)LFBA_OK;
+  });
+}
+
+int lfba_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return LFBA_INVALID_ARGUMENT;
+  return guarded([&] {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError("no CUDA device", LFBA_NO_DEVICE);
+    if (device >= 0) LFBA_CUDA(cudaSetDevice(device));
+    *tflops = measure_fp64_tflops(0);
+    return (int)LFBA_OK;
+  });
+}
+
+int lfba_eval(const lfba_problem* pb, const lfba_options* opt_in, const double* cam, const double* views,
+              const double* points, double* residuals, double* jac_camera, double* jac_view, double* jac_point,
+              double* cost, lfba_reproj_stats* stats, double inlier_threshold) {
+  if (!pb || !cam || !views || !points) return LFBA_INVALID_ARGUMENT;
+  lfba_options o;
+  if (opt_in) o = *opt_in; else lfba_options_init(&o);
+  return guarded([&] {
+    Solver s;
+    s.create(*pb, o, nullptr);
+    s.set_parameters(cam, views, points);
+    const int64_t N = s.ix.N;
+    DevBuf<double> res((size_t)2 * N), jc, jv, jp, st(8);
+    if (jac_camera) jc.alloc((size_t)34 * N);
+    if (jac_view) jv.alloc((size_t)12 * N);
+    if (jac_point) jp.alloc((size_t)6 * N);
+    st.zero(s.stream);
+    EvalIn in{s.ix.obs_in.p, s.ix.lens_id_in.p, s.ix.point_in.p, s.ix.frame_in.p};
+    EvalOut out{res.p, jc.p, jv.p, jp.p, st.p, inlier_threshold * inlier_threshold};
+    launch_tables_for(s.d, 0, s.stream);
+    launch_eval_only(s.d, in, out, 0, s.stream);
+    if (residuals) res.download(residuals, (size_t)2 * N, s.stream);
+    if (jac_camera) jc.download(jac_camera, (size_t)34 * N, s.stream);
+    if (jac_view) jv.download(jac_view, (size_t)12 * N, s.stream);
+    if (jac_point) jp.download(jac_point, (size_t)6 * N, s.stream);
+    double hs[8];
+    st.download(hs, 8, s.stream);
+    LFBA_CUDA(cudaStreamSynchronize(s.stream));
+    if (cost) {
+      double c = hs[5];
+      for (int k = 0; k < s.d.K; ++k) {
+        double r, j[3];
+        distance_eval(points + 3 * pb->c_p1[k], points + 3 * pb->c_p2[k], pb->c_dist[k], pb->c_sigma[k], r, j);
+        c += 0.5 * r * r;
+      }
+      *cost = c;
+    }
+    if (stats) {
+      stats->std_x = N > 0 ? std::sqrt(hs[0] / (double)N) : 0.0;
+      stats->std_y = N > 0 ? std::sqrt(hs[1] / (double)N) : 0.0;
+      stats->mae_x = hs[2];
+      stats->mae_y = hs[3];
+      stats->num_points = N;
+      stats->num_inliers = (int64_t)(hs[4] + 0.5);
+    }
+    return (int)LFBA_OK;
+  });
+}
+
+// Single-process entry: one GPU, or `num_gpus` GPUs with one host thread per GPU (points are split into
+// contiguous ranges balanced by observation count; every observation of a point goes to the point's owner).
+int lfba_solve(const lfba_problem* pb, const lfba_options* opt_in, double* cam, double* views, double* points,
+               lfba_summary* sum) {
+  if (!pb || !cam || !views || !points) return LFBA_INVALID_ARGUMENT;
+  lfba_options o;
+  if (opt_in) o = *opt_in; else lfba_options_init(&o);
+  const int G = std::max(1, o.num_gpus);
+  if (G == 1) {
+    return guarded([&] {
+      Solver s;
+      s.create(*pb, o, nullptr);
+      s.set_parameters(cam, views, points);
+      const int rc = s.run(sum);
+      if (rc == LFBA_OK || s.h_state.n_rows > 0) s.get_parameters(s.h_state.cur, cam, views, points);
+      return rc;
+    });
+  }
+  // ---- multi-GPU in one process ----
+  const int avail = lfba_device_count();
+  if (avail < G) {
+    set_error("num_gpus exceeds the number of usable devices");
+    return LFBA_NO_DEVICE;
+  }
+  const int P = pb->n_points;
+  const int64_t N = pb->n_obs;
+  std::vector<int64_t> cnt((size_t)P + 1, 0);
+  for (int64_t i = 0; i < N; ++i) cnt[pb->point_idx[i] + 1]++;
+  for (int p = 0; p < P; ++p) cnt[p + 1] += cnt[p];
+  std::vector<int> owner((size_t)P, 0);
+  for (int p = 0; p < P; ++p) owner[p] = (int)std::min<int64_t>(G - 1, (cnt[p] * G) / std::max<int64_t>(1, N));
+  const bool use_c = (pb->config & LFBA_CFG_REFINE_POINTS) && pb->calib_type != LFBA_RECALIBRATION;
+  if (use_c)
+    for (int k = 0; k < pb->n_constraints; ++k) owner[pb->c_p1[k]] = owner[pb->c_p2[k]] = 0;
+  struct Shard {
+    std::vector<double> ox, oy, mx, my;
+    std::vector<int32_t> pi, fi;
+  };
+  std::vector<Shard> sh((size_t)G);
+  for (int64_t i = 0; i < N; ++i) {
+    Shard& s = sh[(size_t)owner[pb->point_idx[i]]];
+    s.ox.push_back(pb->obs_x[i]);
+    s.oy.push_back(pb->obs_y[i]);
+    s.mx.push_back(pb->ml_x[i]);
+    s.my.push_back(pb->ml_y[i]);
+    s.pi.push_back(pb->point_idx[i]);
+    s.fi.push_back(pb->frame_idx[i]);
+  }
+  lfba_comm base;
+  std::memset(&base, 0, sizeof(base));
+  base.nranks = G;
+  int rc0 = lfba_comm_unique_id(base.nccl_unique_id);
+  if (rc0 != LFBA_OK) return rc0;
+  std::vector<int> rcs((size_t)G, LFBA_OK);
+  std::vector<std::string> errs((size_t)G);
+  std::vector<std::vector<double>> pts_out((size_t)G);
+  std::vector<std::thread> th;
+  for (int r = 0; r < G; ++r)
+    th.emplace_back([&, r] {
+      rcs[r] = guarded([&] {
+        lfba_problem lp = *pb;
+        lp.n_obs = (int64_t)sh[r].ox.size();
+        lp.obs_x = sh[r].ox.data();
+        lp.obs_y = sh[r].oy.data();
+        lp.ml_x = sh[r].mx.data();
+        lp.ml_y = sh[r].my.data();
+        lp.point_idx = sh[r].pi.data();
+        lp.frame_idx = sh[r].fi.data();
+        lfba_options lo = o;
+        lo.device = r;
+        lfba_comm c = base;
+        c.rank = r;
+        Solver s;
+        s.create(lp, lo, &c);
+        s.set_parameters(cam, views, points);
+        lfba_summary local;
+        std::memset(&local, 0, sizeof(local));
+        lfba_summary* ps = (r == 0) ? sum : &local;
+        const int rc = s.run(ps);
+        pts_out[r].resize((size_t)3 * P);
+        if (r == 0) {
+          std::vector<double> c17(17), v6((size_t)6 * pb->n_frames);
+          s.get_parameters(s.h_state.cur, c17.data(), v6.data(), pts_out[r].data());
+          std::memcpy(cam, c17.data(), 17 * sizeof(double));
+          std::memcpy(views, v6.data(), v6.size() * sizeof(double));
+        } else {
+          s.get_parameters(s.h_state.cur, nullptr, nullptr, pts_out[r].data());
+        }
+        return rc;
+      });
+      errs[r] = g_last_error;
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < G; ++r)
+    if (rcs[r] != LFBA_OK) {
+      set_error("rank " + std::to_string(r) + ": " + errs[r]);
+      return rcs[r];
+    }
+  for (int p = 0; p < P; ++p)
+    for (int j = 0; j < 3; ++j) points[3 * (size_t)p + j] = pts_out[(size_t)owner[p]][3 * (size_t)p + j];
+  return LFBA_OK;
+}
+
+}  // extern "C"

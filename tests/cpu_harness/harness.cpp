@@ -1,0 +1,74 @@
+// tests/cpu_harness/harness.cpp — TEST INFRASTRUCTURE.
+// Runs the product's __host__ __device__ per-item math (lifcal_b200/csrc/lfba_math.cuh — the very functions the
+// CUDA kernels call) on the CPU, so the analytic Jacobian and the per-track chain rule can be checked against
+// the oracle in the no-GPU test tier. It is NOT a fallback: it is built only by the tests, lives outside the
+// package and is never loaded by lifcal_b200/.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/lfba.h"
+#include "../../lifcal_b200/csrc/lfba_math.cuh"
+
+using namespace lfba;
+
+template <int NC>
+static void eval_all(const lfba_problem* pb, const CamModel& m, const double* views, const double* points,
+                     double* res, double* jc, double* jv, double* jp) {
+  const bool rp = pb->config & LFBA_CFG_REFINE_POSES, r3 = pb->config & LFBA_CFG_REFINE_POINTS;
+  for (int64_t i = 0; i < pb->n_obs; ++i) {
+    double le[kLensStride], fe[kFrameStride], Pc[3];
+    lens_entry(m, pb->ml_x[i], pb->ml_y[i], le);
+    frame_entry(views + 6 * pb->frame_idx[i], fe);
+    const double* X = points + 3 * pb->point_idx[i];
+    track_point(fe, X, Pc);
+    TrackCtx t;
+    track_setup(m, Pc, t);
+    double r[2], G[6], J[2 * NC];
+    obs_eval<NC>(m, t, le, pb->obs_x[i], pb->obs_y[i], r, G, J);
+    double r2[2];
+    obs_residual(m, t, le, pb->obs_x[i], pb->obs_y[i], r2);
+    res[2 * i] = r[0];
+    res[2 * i + 1] = r[1];
+    if (r2[0] != r[0] || r2[1] != r[1]) res[2 * i] = 1e300;  // the two code paths must agree exactly
+    for (int row = 0; row < 2; ++row) {
+      for (int c = 0; c < 17; ++c) jc[34 * i + 17 * row + c] = c < NC ? J[NC * row + c] : 0.0;
+      // pose block: [G dR0 X, G dR1 X, G dR2 X, G]
+      for (int k = 0; k < 3; ++k) {
+        double mk[3];
+        mat3_vec(fe + 9 + 9 * k, X, mk);
+        jv[12 * i + 6 * row + k] = rp ? G[3 * row] * mk[0] + G[3 * row + 1] * mk[1] + G[3 * row + 2] * mk[2] : 0.0;
+        jv[12 * i + 6 * row + 3 + k] = rp ? G[3 * row + k] : 0.0;
+      }
+      // point block: G R
+      for (int k = 0; k < 3; ++k)
+        jp[6 * i + 3 * row + k] =
+            r3 ? G[3 * row] * fe[k] + G[3 * row + 1] * fe[3 + k] + G[3 * row + 2] * fe[6 + k] : 0.0;
+    }
+  }
+}
+
+extern "C" int harness_eval(const lfba_problem* pb, const double* camera, const double* views, const double* points,
+                            double* res, double* jc, double* jv, double* jp) {
+  CamModel m;
+  cam_model_init(m, camera, pb->config, pb->spx, pb->spy, pb->scale, 0.5);
+  switch (m.nc) {
+    case 5: eval_all<5>(pb, m, views, points, res, jc, jv, jp); break;
+    case 6: eval_all<6>(pb, m, views, points, res, jc, jv, jp); break;
+    case 7: eval_all<7>(pb, m, views, points, res, jc, jv, jp); break;
+    case 8: eval_all<8>(pb, m, views, points, res, jc, jv, jp); break;
+    case 9: eval_all<9>(pb, m, views, points, res, jc, jv, jp); break;
+    default: return 1;
+  }
+  return 0;
+}
+
+extern "C" int harness_spd3_inverse(const double* a6, double* inv6) { return spd3_inverse(a6, inv6) ? 1 : 0; }
+extern "C" void harness_distance(const double* p1, const double* p2, double d, double s, double* r, double* j) {
+  distance_eval(p1, p2, d, s, *r, j);
+}
+extern "C" void harness_robust(const double* camera, uint32_t config, double s, double* scale, double* rho) {
+  CamModel m;
+  cam_model_init(m, camera, config, 0.011, 0.011, 2.0, 0.5);
+  *scale = robust_scale(m, s, *rho);
+}
