@@ -182,13 +182,13 @@ __global__ void __launch_bounds__(256) k_backsolve(Dev d) {
   }
 }
 
+// per-device opt-in to > 48 KB of dynamic shared memory (call once per device with that device current)
+void prepare_device_kernels() {
+  cudaFuncSetAttribute(k_chol_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * TS * LD * sizeof(double)));
+}
+
 int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, cudaStream_t s) {
-  static bool attr_set = false;
   const size_t smem = 3 * TS * LD * sizeof(double);
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_chol_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
   for (int k = 0; k < n_tiles; ++k) k_chol_column<<<n_tiles - k, 256, smem, s>>>(d, k, d_tile_first);
   k_backsolve<<<1, 256, 0, s>>>(d);
   return n_tiles + 1;

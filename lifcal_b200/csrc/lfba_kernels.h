@@ -19,6 +19,7 @@ int launch_steps(const Dev& d, cudaStream_t s);
 // ---- lfba_chol.cu: reduced system ----
 // In-place tiled Cholesky of the skyline matrix (n + 1 rows: the last row is the rhs, which comes out
 // forward-substituted), then the backward substitution into d.y. Returns the number of kernels launched.
+void prepare_device_kernels();
 int launch_reduced_solve(const Dev& d, int n_tiles, const int* h_tile_first /*[n_tiles] first nonzero tile col*/,
                          cudaStream_t s);
 

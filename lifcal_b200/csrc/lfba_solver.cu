@@ -97,6 +97,7 @@ struct Solver {
   DevBuf<int32_t> pt_coupled, coupled_pts, pt_active, frm_active, c_p1, c_p2, tile_first, row_c0;
   DevBuf<int64_t> row_off;
   DevBuf<double> c_dist, c_sigma;
+  DevBuf<double> camera0, views0, points0;  // parameters given by the caller: every run() starts from them
   DevBuf<double> camera[2], views[2], points[2], lens, frames[2], rec[2], camsum[2], pdata, pscale, vw;
   DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one NCCL all-reduce)
   DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step;
@@ -337,6 +338,7 @@ struct Solver {
     d.st = st.p; d.log = log.p;
     for (auto& e : ev) LFBA_CUDA(cudaEventCreate(&e));
     ev_made = true;
+    prepare_device_kernels();
     LFBA_CUDA(cudaStreamSynchronize(stream));
     setup_time = now_s() - t0;
   }
@@ -344,11 +346,13 @@ struct Solver {
   void set_parameters(const double* cam, const double* vw_, const double* pts) {
     LFBA_CUDA(cudaSetDevice(device));
     // the accepted-state slot is 0 until the first accept flips it; the initial point enters as candidate (slot 1)
-    for (int b = 0; b < 2; ++b) {
-      camera[b].upload(cam, 17, stream);
-      views[b].upload(vw_, (size_t)6 * ix.F, stream);
-      points[b].upload(pts, (size_t)3 * ix.P, stream);
-    }
+    camera0.alloc(17);
+    views0.alloc((size_t)6 * ix.F);
+    points0.alloc((size_t)3 * ix.P);
+    camera0.upload(cam, 17, stream);
+    views0.upload(vw_, (size_t)6 * ix.F, stream);
+    points0.upload(pts, (size_t)3 * ix.P, stream);
+    reset_parameters();
     if (calib_type == LFBA_RECALIBRATION) {  // bounds from the INITIAL values (:943-951)
       const int bj[3] = {1, 3, 4};
       for (int k = 0; k < 3; ++k) {
@@ -357,6 +361,14 @@ struct Solver {
       }
     }
     LFBA_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  void reset_parameters() {
+    for (int b = 0; b < 2; ++b) {
+      LFBA_CUDA(cudaMemcpyAsync(camera[b].p, camera0.p, 17 * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      LFBA_CUDA(cudaMemcpyAsync(views[b].p, views0.p, (size_t)6 * ix.F * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      LFBA_CUDA(cudaMemcpyAsync(points[b].p, points0.p, (size_t)3 * ix.P * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    }
   }
 
   void get_parameters(int which, double* cam, double* vw_, double* pts) {
@@ -379,8 +391,8 @@ struct Solver {
     init.solve_ok = 1;
     init.radius = opt.initial_trust_region_radius;
     init.decrease_factor = 2.0;
-    // the caller's current parameters live in slot `cur` after a previous run; copy them into the candidate slot
-    LFBA_CUDA(cudaMemcpyAsync(&h_state, st.p, sizeof(LmState), cudaMemcpyDeviceToHost, stream));
+    if (!camera0.p) throw CudaError("lfba_solver_run before lfba_solver_set_parameters", LFBA_INVALID_ARGUMENT);
+    reset_parameters();  // every run starts from the parameters last given by the caller
     LFBA_CUDA(cudaMemcpyAsync(st.p, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
     if (calib_type == LFBA_RECALIBRATION) {
       // IterationZero of a bounds-constrained problem projects the start point into the box
