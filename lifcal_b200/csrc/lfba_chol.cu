@@ -18,6 +18,7 @@ namespace lfba {
 
 constexpr int TS = kTile;      // 64
 constexpr int LD = TS + 1;     // padded leading dimension in shared memory
+constexpr int kBandedSmemMax = 220 * 1024;
 
 __device__ __forceinline__ double sky_load(const Dev& d, int r, int c, int n_aug) {
   if (r >= n_aug || c > r) return 0.0;
@@ -182,12 +183,316 @@ __global__ void __launch_bounds__(256) k_backsolve(Dev d) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Banded-arrowhead Cholesky, one CTA, everything on chip.
+//
+// With windowed visibility the reduced system is [block-banded pose part | dense border], border =
+// coupled points + camera + the rhs row. A right-looking factorisation by 6x6 pose blocks only ever touches the
+// (bw+1) frames of the current window plus the border: that window (6(bw+1)+nb)^2 lives in shared memory as a
+// circular buffer of frame slots, finished columns of L stream back to HBM once, and the chain of F block pivots
+// runs without a single kernel launch or global synchronisation. The rhs row rides along as a border row
+// (forward substitution for free); the backward substitution is done by the same CTA, block by block.
+// Cost: O(F * (6 bw + nb)^2 * 6) flops instead of n^3/3; latency ~1 us per frame instead of ~150 us per 64-tile.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bslot(int f, int bw1) { return 6 * (f % bw1); }
+
+// Address arithmetic of the skyline for pose rows (no dependent index loads on the critical path):
+// row r = 6f+i starts at column c0 = 6 max(0, f-bw) and holds r-c0+1 entries; rows of a frame are consecutive.
+struct SkyPose {
+  const long long* frame_off;  // smem: offset of row 6f
+  int bw;
+  __device__ __forceinline__ int c0(int f) const { return 6 * max(0, f - bw); }
+  __device__ __forceinline__ long long row(int f, int i) const {
+    const int len0 = 6 * f - c0(f) + 1;
+    return frame_off[f] + (long long)i * len0 + (i * (i - 1)) / 2;
+  }
+};
+
+constexpr int kPrefMax = 6;  // prefetch registers per thread (band) — (6*NBAND + 255)/256 <= kPrefMax is checked on the host
+
+__global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
+  LmState* st = d.st;
+  if (st->done || !st->solve_ok) return;
+  extern __shared__ double sm[];
+  const int F = d.np6 / 6;
+  const int bw1 = bw + 1;
+  const int NBAND = 6 * bw1;
+  const int W = NBAND + nb;
+  const int LDW = W | 1;
+  double* A = sm;
+  double* ys = sm + (size_t)W * LDW;                               // n
+  double* dinv_all = ys + d.n;                                      // n: 1 / L_cc of the pose pivots
+  long long* frame_off = reinterpret_cast<long long*>(dinv_all + d.n);  // F + 1
+  long long* border_off = frame_off + (F + 1);                      // nb
+  int* lrow = reinterpret_cast<int*>(border_off + nb);              // W (local row of panel row i)
+  __shared__ double dinv[6];
+  __shared__ double tvec[6];
+  __shared__ double Lkk[21];
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int npiv = nb - 1;  // border unknowns (the last border row is the rhs)
+
+  for (int e = tid; e < W * LDW; e += nt) A[e] = 0.0;
+  for (int f = tid; f < F; f += nt) frame_off[f] = d.row_off[6 * f];
+  for (int b = tid; b < nb; b += nt) border_off[b] = d.row_off[d.np6 + b];
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  SkyPose sky{frame_off, bw};
+
+  // element e of a frame's row block: (i, cc) -> value; the block has 6 rows of up to NBAND entries
+  auto band_fetch = [&](int f, int e, int& lidx) -> double {
+    const int i = e / NBAND, cc = e - i * NBAND;
+    const int c0 = sky.c0(f);
+    const int c = c0 + cc;
+    if (i >= 6 || c > 6 * f + i) { lidx = -1; return 0.0; }
+    const int fc = c / 6;
+    lidx = (bslot(f, bw1) + i) * LDW + bslot(fc, bw1) + (c - 6 * fc);
+    return d.S[sky.row(f, i) + cc];
+  };
+  auto border_fetch = [&](int f, int e, int& lidx) -> double {
+    const int b = e / 6, j = e - 6 * b;
+    if (b >= nb) { lidx = -1; return 0.0; }
+    lidx = (NBAND + b) * LDW + bslot(f, bw1) + j;
+    return d.S[border_off[b] + 6 * f + j];
+  };
+  for (int f = 0; f <= min(bw, F - 1); ++f) {
+    for (int e = tid; e < 6 * NBAND; e += nt) { int li; const double v = band_fetch(f, e, li); if (li >= 0) A[li] = v; }
+    for (int e = tid; e < 6 * nb; e += nt) { int li; const double v = border_fetch(f, e, li); if (li >= 0) A[li] = v; }
+  }
+  for (int e = tid; e < nb * nb; e += nt) {
+    const int b1 = e / nb, b2 = e % nb;
+    if (b2 <= b1 && !(b1 == npiv && b2 == npiv)) A[(NBAND + b1) * LDW + NBAND + b2] = d.S[border_off[b1] + d.np6 + b2];
+  }
+  __syncthreads();
+
+  const int tx = tid & 15, ty = tid >> 4;
+  for (int k = 0; k < F; ++k) {
+    const int s = bslot(k, bw1);
+    // ---- prefetch the frame that will take this slot (k + bw + 1): loads in flight during the whole step ----
+    const int fn = k + bw1;
+    double pv[kPrefMax], pb = 0.0;
+    int pl[kPrefMax], plb = -1;
+    if (fn < F) {
+#pragma unroll
+      for (int q = 0; q < kPrefMax; ++q) {
+        const int e = tid + q * nt;
+        pl[q] = -1;
+        pv[q] = 0.0;
+        if (e < 6 * NBAND) pv[q] = band_fetch(fn, e, pl[q]);
+      }
+      if (tid < 6 * nb) pb = border_fetch(fn, tid, plb);
+    }
+    // ---- 6x6 Cholesky of the pivot block: one thread, registers only (the latency chain of the whole solve) ----
+    if (tid == 0) {
+      double a[21];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = A[(s + i) * LDW + s + j];
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double piv = a[c * (c + 1) / 2 + c];
+        const bool okp = piv > 0.0;
+        bad |= !okp;
+        const double r = okp ? rsqrt(piv) : 0.0;
+        a[c * (c + 1) / 2 + c] = okp ? piv * r : 1.0;
+        dinv[c] = r;
+        dinv_all[6 * k + c] = r;
+#pragma unroll
+        for (int i = c + 1; i < 6; ++i) a[i * (i + 1) / 2 + c] *= r;
+#pragma unroll
+        for (int i = c + 1; i < 6; ++i)
+#pragma unroll
+          for (int j = c + 1; j <= i; ++j) a[i * (i + 1) / 2 + j] = fma(-a[i * (i + 1) / 2 + c], a[j * (j + 1) / 2 + c], a[i * (i + 1) / 2 + j]);
+      }
+      if (bad) s_fail = 1;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) A[(s + i) * LDW + s + j] = a[i * (i + 1) / 2 + j];
+    }
+    const int nbf = min(bw, F - 1 - k);
+    const int mrows = 6 * nbf + nb;
+    for (int i = tid; i < mrows; i += nt)
+      lrow[i] = i < 6 * nbf ? bslot(k + 1 + i / 6, bw1) + i % 6 : NBAND + (i - 6 * nbf);
+    __syncthreads();
+    // ---- panel: rows of the frames k+1..k+bw and the border; X = A L^-T ----
+    for (int i = tid; i < mrows; i += nt) {
+      const int lr = lrow[i];
+      long long goff;
+      if (i < 6 * nbf) {
+        const int f = k + 1 + i / 6;
+        goff = sky.row(f, i % 6) + (6 * k - sky.c0(f));
+      } else {
+        goff = border_off[i - 6 * nbf] + 6 * k;
+      }
+      double x[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double a = A[lr * LDW + s + c];
+#pragma unroll
+        for (int j = 0; j < c; ++j) a -= x[j] * A[(s + c) * LDW + s + j];
+        x[c] = a * dinv[c];
+      }
+      double* dst = d.S + goff;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        A[lr * LDW + s + c] = x[c];
+        dst[c] = x[c];
+      }
+    }
+    if (tid >= 224 && tid < 245) {  // L_kk to HBM
+      int i = 0, j = tid - 224;
+      while (j > i) { j -= i + 1; ++i; }
+      d.S[sky.row(k, i) + (6 * k + j - sky.c0(k))] = A[(s + i) * LDW + s + j];
+    }
+    __syncthreads();
+    // ---- trailing update of the window: A[i][j] -= X_i . X_j, i >= j in global order (16 x 16 thread grid) ----
+    for (int i = ty; i < mrows; i += 16) {
+      const int li = lrow[i];
+      const double* xi = A + li * LDW + s;
+      const double x0 = xi[0], x1 = xi[1], x2 = xi[2], x3 = xi[3], x4 = xi[4], x5 = xi[5];
+      for (int j = tx; j <= i; j += 16) {
+        const int lj = lrow[j];
+        const double* xj = A + lj * LDW + s;
+        A[li * LDW + lj] -= x0 * xj[0] + x1 * xj[1] + x2 * xj[2] + x3 * xj[3] + x4 * xj[4] + x5 * xj[5];
+      }
+    }
+    __syncthreads();
+    // ---- slide the window: frame k+bw+1 takes the slot of frame k ----
+    if (fn < F) {
+#pragma unroll
+      for (int q = 0; q < kPrefMax; ++q)
+        if (pl[q] >= 0) A[pl[q]] = pv[q];
+      if (plb >= 0) A[plb] = pb;
+      for (int e = tid + nt; e < 6 * nb; e += nt) { int li; const double v = border_fetch(fn, e, li); if (li >= 0) A[li] = v; }
+      __syncthreads();
+    }
+  }
+  // ---- dense Cholesky of the border block (coupled points + camera); the rhs row is not a pivot ----
+  for (int c = 0; c < npiv; ++c) {
+    __syncthreads();
+    const double piv = A[(NBAND + c) * LDW + NBAND + c];
+    const bool okp = piv > 0.0;
+    const double r = okp ? rsqrt(piv) : 0.0;
+    __syncthreads();
+    if (tid == 0) {
+      if (!okp) s_fail = 1;
+      A[(NBAND + c) * LDW + NBAND + c] = okp ? piv * r : 1.0;
+    } else if (tid < nb - c) {
+      A[(NBAND + c + tid) * LDW + NBAND + c] *= r;
+    }
+    __syncthreads();
+    const int m = nb - 1 - c;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = c + 1 + e / m, j = c + 1 + e % m;
+      if (j <= i) A[(NBAND + i) * LDW + NBAND + j] -= A[(NBAND + i) * LDW + NBAND + c] * A[(NBAND + j) * LDW + NBAND + c];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * nb; e += nt) {
+    const int b1 = e / nb, b2 = e % nb;
+    if (b2 <= b1 && !(b1 == npiv && b2 == npiv)) d.S[border_off[b1] + d.np6 + b2] = A[(NBAND + b1) * LDW + NBAND + b2];
+  }
+  if (tid == 0 && s_fail) st->solve_ok = 0;
+  if (s_fail) return;
+  // ---- backward substitution L^T y = z, z = the factorised rhs row ----
+  if (tid == 0) {
+    for (int b = npiv - 1; b >= 0; --b) {
+      double v = A[(NBAND + npiv) * LDW + NBAND + b];
+      for (int b2 = b + 1; b2 < npiv; ++b2) v -= A[(NBAND + b2) * LDW + NBAND + b] * ys[d.np6 + b2];
+      ys[d.np6 + b] = v / A[(NBAND + b) * LDW + NBAND + b];
+    }
+  }
+  __syncthreads();
+  const double* zrow = d.S + border_off[npiv];
+  // software pipeline: the L entries of block column k-1 are loaded while block k is being solved
+  const int per = 8;  // entries per lane per output column: mrows <= 32 * per is checked on the host
+  double lv[per];
+  double lkk = 0.0, zk = 0.0;
+  auto fetch_col = [&](int k) {
+    const int nbf = min(bw, F - 1 - k);
+    const int mrows = 6 * nbf + npiv;
+    if (warp < 6) {
+#pragma unroll
+      for (int q = 0; q < per; ++q) {
+        const int i = lane + 32 * q;
+        lv[q] = 0.0;
+        if (i < mrows) {
+          const long long off = i < 6 * nbf ? sky.row(k + 1 + i / 6, i % 6) + (6 * k + warp - sky.c0(k + 1 + i / 6))
+                                            : border_off[i - 6 * nbf] + 6 * k + warp;
+          lv[q] = d.S[off];
+        }
+      }
+      if (lane == 0) zk = zrow[6 * k + warp];
+    } else if (warp == 6 && lane < 21) {
+      int i = 0, j = lane;
+      while (j > i) { j -= i + 1; ++i; }
+      lkk = d.S[sky.row(k, i) + (6 * k + j - sky.c0(k))];
+    }
+  };
+  if (F > 0) fetch_col(F - 1);
+  for (int k = F - 1; k >= 0; --k) {
+    const int nbf = min(bw, F - 1 - k);
+    const int mrows = 6 * nbf + npiv;
+    if (warp < 6) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < per; ++q) {
+        const int i = lane + 32 * q;
+        if (i < mrows) acc += lv[q] * ys[i < 6 * nbf ? 6 * (k + 1) + i : d.np6 + (i - 6 * nbf)];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) tvec[warp] = zk - acc;
+    } else if (warp == 6 && lane < 21) {
+      Lkk[lane] = lkk;
+    }
+    if (k > 0) fetch_col(k - 1);
+    __syncthreads();
+    if (tid == 0) {
+      double yk[6];
+#pragma unroll
+      for (int c = 5; c >= 0; --c) {
+        double v = tvec[c];
+#pragma unroll
+        for (int c2 = 5; c2 > c; --c2) v -= Lkk[c2 * (c2 + 1) / 2 + c] * yk[c2];
+        yk[c] = v * dinv_all[6 * k + c];
+        ys[6 * k + c] = yk[c];
+      }
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < d.n; j += nt) d.y[j] = ys[j];
+}
+
 // per-device opt-in to > 48 KB of dynamic shared memory (call once per device with that device current)
 void prepare_device_kernels() {
   cudaFuncSetAttribute(k_chol_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * TS * LD * sizeof(double)));
+  cudaFuncSetAttribute(k_chol_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
 }
 
-int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, cudaStream_t s) {
+// shared memory needed by k_chol_banded, or 0 when the banded path does not apply / does not fit
+size_t banded_smem_bytes(const Dev& d, int bw, int nb) {
+  if (d.np6 == 0) return 0;
+  const size_t NBAND = 6 * (size_t)(bw + 1), W = NBAND + nb, LDW = W | 1;
+  const size_t F = d.np6 / 6;
+  if ((6 * NBAND + 255) / 256 > (size_t)kPrefMax) return 0;   // prefetch registers of k_chol_banded
+  if (6 * (size_t)bw + nb > 32 * 8) return 0;                 // backward-substitution lanes
+  if ((size_t)6 * nb > 2 * 256 + 256) {}                      // (border prefetch falls back to a loop)
+  const size_t bytes = (W * LDW + 2 * (size_t)d.n + (F + 1) + nb + 8) * sizeof(double) + W * sizeof(int);
+  return bytes <= (size_t)kBandedSmemMax ? bytes : 0;
+}
+
+int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, int bw, cudaStream_t s) {
+  const int nb = d.n - d.np6 + 1;
+  const size_t bsm = banded_smem_bytes(d, bw, nb);
+  if (bsm > 0) {
+    k_chol_banded<<<1, 256, bsm, s>>>(d, bw, nb);
+    return 1;
+  }
   const size_t smem = 3 * TS * LD * sizeof(double);
   for (int k = 0; k < n_tiles; ++k) k_chol_column<<<n_tiles - k, 256, smem, s>>>(d, k, d_tile_first);
   k_backsolve<<<1, 256, 0, s>>>(d);

@@ -32,7 +32,7 @@ __global__ void k_tables_for(Dev d, int which) {
   if (i < d.F) frame_entry(d.views[which] + 6 * i, d.frames[which] + (size_t)i * kFrameStride);
 }
 
-template <int NC>
+template <int NC, int NRAD>
 __global__ void __launch_bounds__(128) k_eval_only(Dev d, EvalIn in, EvalOut out, int which) {
   __shared__ CamModel cm;
   __shared__ double sred[4 * 6];
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128) k_eval_only(Dev d, EvalIn in, EvalOut out
     TrackCtx tc;
     track_setup(cm, Pc, tc);
     double r[2], G[6], J[2 * NC];
-    obs_eval<NC>(cm, tc, e, o.x, o.y, r, G, J);
+    obs_eval<NC, NRAD>(cm, tc, e, o.x, o.y, r, G, J);
     out.residuals[2 * i] = r[0];
     out.residuals[2 * i + 1] = r[1];
     if (out.jac_camera) {
@@ -129,12 +129,14 @@ void launch_tables_for(const Dev& d, int which, cudaStream_t s) {
 void launch_eval_only(const Dev& d, const EvalIn& in, const EvalOut& out, int which, cudaStream_t s) {
   if (d.N == 0) return;
   const unsigned grid = (unsigned)((d.N + 127) / 128);
-  switch (d.NC) {
-    case 5: k_eval_only<5><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    case 6: k_eval_only<6><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    case 7: k_eval_only<7><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    case 8: k_eval_only<8><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    default: k_eval_only<9><<<grid, 128, 0, s>>>(d, in, out, which); break;
+  const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
+  switch (nrad * 2 + tang) {
+    case 0: k_eval_only<5, 0><<<grid, 128, 0, s>>>(d, in, out, which); break;
+    case 1: k_eval_only<7, 0><<<grid, 128, 0, s>>>(d, in, out, which); break;
+    case 2: k_eval_only<6, 1><<<grid, 128, 0, s>>>(d, in, out, which); break;
+    case 3: k_eval_only<8, 1><<<grid, 128, 0, s>>>(d, in, out, which); break;
+    case 4: k_eval_only<7, 2><<<grid, 128, 0, s>>>(d, in, out, which); break;
+    default: k_eval_only<9, 2><<<grid, 128, 0, s>>>(d, in, out, which); break;
   }
 }
 

@@ -23,6 +23,9 @@
 //      k_reduced_step      candidate camera/poses/coupled points (manifold + bounds), reduced-part scalars
 // Scatter into the reduced system is gather-by-destination (per frame, per frame pair): no atomics on the hot
 // blocks and a fixed summation order.
+#include <cuda_pipeline.h>
+#include <stdlib.h>
+#include <cstdlib>
 #include <float.h>
 
 #include "lfba_device.cuh"
@@ -99,22 +102,34 @@ __global__ void k_tables(Dev d) {
 // track sums (A 6, b 3, C 3xNC) are combined with xor-shuffles inside the L-lane group; the camera block
 // (Hcc, gc) and the cost stay in per-thread accumulators for the whole kernel and are reduced once per CTA.
 // Algorithmic HBM traffic: 20 B per observation (double2 + int32) + REC*8 B per track written.
-template <int NC, int L>
-__global__ void __launch_bounds__(128) k_eval_tracks(Dev d) {
+// PART selects which accumulators a launch keeps (the evaluation itself is identical):
+//   0  everything in one pass: track records (A, b, C) + camera block (Hcc, gc) + cost      [255 registers, 8 warps/SM]
+//   1  track records + gc + cost                                                             } two passes, each at
+//   2  Hcc only                                                                              } roughly half the registers
+// The split recomputes the residual/Jacobian (about 150 FP64 ops) but doubles the resident warps and removes the
+// register spills; which variant is faster is a measured choice, not a semantic one.
+template <int NC, int NRAD, int L, int PART>
+__global__ void __launch_bounds__(128, PART == 0 ? 2 : 3) k_eval_tracks(Dev d) {
   const LmState* st = d.st;
   if (st->done || st->eval_skip) return;
   const int cand = 1 - st->cur;
   constexpr int NH = NC * (NC + 1) / 2;
   constexpr int NV = NH + NC + 1;
   constexpr int RS = 9 + 3 * NC;
+  constexpr bool kRec = PART != 2, kHcc = PART != 1;
+  constexpr int NA = PART == 0 ? NV : (PART == 1 ? NC + 1 : NH);  // per-thread accumulators of this launch
+  constexpr int AOFF = PART == 1 ? NH : 0;                         // their offset inside the NV-vector
   __shared__ CamModel cm;
-  __shared__ double red[4 * NV];
+  __shared__ double red[4 * NA];
   if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
   __syncthreads();
 
-  double acc[NV];
+  double acc[NA];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  for (int v = 0; v < NA; ++v) acc[v] = 0.0;
+  // views into acc
+  double* hcc = acc;                          // PART 0/2
+  double* gcv = acc + (PART == 0 ? NH : 0);   // PART 0/1: gc[NC], cost
 
   const int lig = threadIdx.x % L;
   const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
@@ -129,9 +144,11 @@ __global__ void __launch_bounds__(128) k_eval_tracks(Dev d) {
     const int slot = group + it * ngroups;
     const bool valid = slot < d.T;
     const int t = valid ? (d.eval_order ? d.eval_order[slot] : slot) : 0;
-    double tr[RS];
+    double tr[kRec ? RS : 1];
+    if (kRec) {
 #pragma unroll
-    for (int v = 0; v < RS; ++v) tr[v] = 0.0;
+      for (int v = 0; v < RS; ++v) tr[v] = 0.0;
+    }
     if (valid) {
       const int p = d.trk_point[t], f = d.trk_frame[t];
       const int ob = d.trk_begin[t], oe = d.trk_begin[t + 1];
@@ -150,7 +167,187 @@ __global__ void __launch_bounds__(128) k_eval_tracks(Dev d) {
           e[2 * k + 1] = v2.y;
         }
         double r[2], G[6], J[2 * NC];
-        obs_eval<NC>(cm, tc, e, o.x, o.y, r, G, J);
+        obs_eval<NC, NRAD>(cm, tc, e, o.x, o.y, r, G, J);
+        const double s = r[0] * r[0] + r[1] * r[1];
+        if (robust) {
+          double rho;
+          const double sw = robust_scale(cm, s, rho);
+          if (kRec) gcv[NC] += 0.5 * rho;
+          r[0] *= sw;
+          r[1] *= sw;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) G[k] *= sw;
+#pragma unroll
+          for (int k = 0; k < 2 * NC; ++k) J[k] *= sw;
+        } else {
+          if (kRec) gcv[NC] += 0.5 * s;
+        }
+        if (kRec) {
+          // track blocks (explicit fma chains: 2 DFMA per entry instead of DMUL + DFMA + DADD)
+          tr[0] = fma(G[0], G[0], fma(G[3], G[3], tr[0]));
+          tr[1] = fma(G[0], G[1], fma(G[3], G[4], tr[1]));
+          tr[2] = fma(G[0], G[2], fma(G[3], G[5], tr[2]));
+          tr[3] = fma(G[1], G[1], fma(G[4], G[4], tr[3]));
+          tr[4] = fma(G[1], G[2], fma(G[4], G[5], tr[4]));
+          tr[5] = fma(G[2], G[2], fma(G[5], G[5], tr[5]));
+#pragma unroll
+          for (int k = 0; k < 3; ++k) tr[6 + k] = fma(G[k], r[0], fma(G[3 + k], r[1], tr[6 + k]));
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              tr[9 + k * NC + c] = fma(G[k], J[c], fma(G[3 + k], J[NC + c], tr[9 + k * NC + c]));
+#pragma unroll
+          for (int c = 0; c < NC; ++c) gcv[c] = fma(J[c], r[0], fma(J[NC + c], r[1], gcv[c]));
+        }
+        if (kHcc) {
+          int h = 0;
+#pragma unroll
+          for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+            for (int c2 = 0; c2 <= c1; ++c2) {
+              hcc[h] = fma(J[c1], J[c2], fma(J[NC + c1], J[NC + c2], hcc[h]));
+              ++h;
+            }
+        }
+      }
+    }
+    if (kRec) {
+      if (L > 1) {
+#pragma unroll
+        for (int v = 0; v < RS; ++v)
+#pragma unroll
+          for (int o = L / 2; o > 0; o >>= 1) tr[v] += __shfl_xor_sync(0xffffffffu, tr[v], o);
+      }
+      if (valid) {
+        double* dst = recs + (size_t)t * RS;
+#pragma unroll
+        for (int v = 0; v < RS; ++v)
+          if ((v % L) == lig) dst[v] = tr[v];
+      }
+    }
+  }
+  block_reduce_store<NA>(acc, d.part_eval + (size_t)blockIdx.x * 64 + AOFF, red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_eval_stream: the same fused evaluation as k_eval_tracks, organised as a software-pipelined stream.
+//   * every L-lane group owns a CONTIGUOUS range of tracks (tracks are stored sorted by (point, frame), and a
+//     track's observations are contiguous), so each group walks one contiguous slice of the observation arrays;
+//   * groups are decoupled (no warp-wide lock step): the only cross-lane traffic is the xor-shuffle reduction of the
+//     36 track sums inside the group when ITS track ends;
+//   * the observation (double2) and lens id of the item two steps ahead are prefetched into registers, the 128-byte
+//     lens-table entry of the item one step ahead is prefetched with cp.async (LDGSTS) into a per-thread,
+//     bank-conflict-free shared-memory slot, so the dependent load lens_id -> lens entry is off the critical path.
+// The kernel is FP64-issue bound by design; with 255 registers per thread only 8 warps fit on an SM, so latency has
+// to be hidden by this explicit pipeline rather than by occupancy.
+// ------------------------------------------------------------------------------------------------
+struct LensSlot {
+  const double2* base;  // &slot[0][tid]; element k2 lives 128 double2 further
+  __device__ __forceinline__ double operator[](int k) const {
+    const double2 v = base[(k >> 1) * 128];
+    return (k & 1) ? v.y : v.x;
+  }
+};
+
+template <int NC, int NRAD, int L>
+__global__ void __launch_bounds__(128) k_eval_stream(Dev d) {
+  const LmState* st = d.st;
+  if (st->done || st->eval_skip) return;
+  const int cand = 1 - st->cur;
+  constexpr int NH = NC * (NC + 1) / 2;
+  constexpr int NV = NH + NC + 1;
+  constexpr int RS = 9 + 3 * NC;
+  __shared__ CamModel cm;
+  __shared__ double red[4 * NV];
+  __shared__ double2 lens_s[2 * 8 * 128];  // [slot][k2][thread]
+  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+  __syncthreads();
+
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+
+  const int lig = threadIdx.x % L;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int ngroups = (gridDim.x * blockDim.x) / L;
+  const int per = (d.T + ngroups - 1) / ngroups;
+  const int t_begin = min(d.T, group * per), t_end = min(d.T, t_begin + per);
+  const double* __restrict__ frames = d.frames[cand];
+  const double* __restrict__ points = d.points[cand];
+  double* __restrict__ recs = d.rec[cand];
+  const bool robust = cm.robust != 0;
+  const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << ((threadIdx.x & 31) / L * L));
+
+  if (t_begin < t_end) {
+    const int i_end = d.trk_begin[t_end];  // end of this group's observation slice
+    // step bases: b0 = current, b1 = next, b2 = next-next. A step never crosses a track end.
+    int t = t_begin;
+    int te = d.trk_begin[t + 1];           // end of the current track
+    int t1 = t, te1 = te;                   // track of b1
+    int t2 = t, te2 = te;                   // track of b2
+    int b0 = d.trk_begin[t];
+    auto next_base = [&](int b, int& tt, int& tte) -> int {
+      int nb = b + L;
+      if (nb >= tte) {
+        nb = tte;
+        if (tte < i_end) {
+          ++tt;
+          tte = d.trk_begin[tt + 1];
+        }
+      }
+      return nb;
+    };
+    int b1 = next_base(b0, t1, te1);
+    t2 = t1;
+    te2 = te1;
+    int b2 = next_base(b1, t2, te2);
+    // pipeline registers
+    double2 o0 = make_double2(0.0, 0.0), o1 = o0, o2 = o0;
+    int l1 = 0, l2 = 0;
+    bool v0 = b0 + lig < te, v1 = (b1 < i_end) && (b1 + lig < te1), v2 = (b2 < i_end) && (b2 + lig < te2);
+    int slot = 0;
+    double2* myslot = lens_s + threadIdx.x;
+    auto issue_lens = [&](int lid, int sl) {
+      const double2* src = reinterpret_cast<const double2*>(d.lens + (size_t)lid * kLensStride);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) __pipeline_memcpy_async(myslot + (sl * 8 + k) * 128, src + k, 16);
+    };
+    if (v0) {
+      o0 = d.obs[b0 + lig];
+      issue_lens(d.lens_id[b0 + lig], 0);
+    }
+    __pipeline_commit();
+    if (v1) {
+      o1 = d.obs[b1 + lig];
+      l1 = d.lens_id[b1 + lig];
+    }
+    // track state
+    double tr[RS];
+    TrackCtx tc;
+    bool fresh = true;  // b0 is the first step of a track
+    while (b0 < i_end) {
+      // ---- prefetch: lens entry of the next step (cp.async), observation + lens id of the step after ----
+      if (v1) issue_lens(l1, slot ^ 1);
+      __pipeline_commit();
+      if (v2) {
+        o2 = d.obs[b2 + lig];
+        l2 = d.lens_id[b2 + lig];
+      }
+      if (fresh) {
+        const int p = d.trk_point[t], f = d.trk_frame[t];
+        double Pc[3];
+        track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
+        track_setup(cm, Pc, tc);
+#pragma unroll
+        for (int v = 0; v < RS; ++v) tr[v] = 0.0;
+        fresh = false;
+      }
+      __pipeline_wait_prior(1);  // the current step's lens entry has landed
+      if (v0) {
+        LensSlot e{myslot + slot * 8 * 128};
+        double r[2], G[6], J[2 * NC];
+        obs_eval<NC, NRAD>(cm, tc, e, o0.x, o0.y, r, G, J);
         const double s = r[0] * r[0] + r[1] * r[1];
         if (robust) {
           double rho;
@@ -165,45 +362,209 @@ __global__ void __launch_bounds__(128) k_eval_tracks(Dev d) {
         } else {
           acc[NH + NC] += 0.5 * s;
         }
-        // track blocks
-        tr[0] += G[0] * G[0] + G[3] * G[3];
-        tr[1] += G[0] * G[1] + G[3] * G[4];
-        tr[2] += G[0] * G[2] + G[3] * G[5];
-        tr[3] += G[1] * G[1] + G[4] * G[4];
-        tr[4] += G[1] * G[2] + G[4] * G[5];
-        tr[5] += G[2] * G[2] + G[5] * G[5];
+        tr[0] = fma(G[0], G[0], fma(G[3], G[3], tr[0]));
+        tr[1] = fma(G[0], G[1], fma(G[3], G[4], tr[1]));
+        tr[2] = fma(G[0], G[2], fma(G[3], G[5], tr[2]));
+        tr[3] = fma(G[1], G[1], fma(G[4], G[4], tr[3]));
+        tr[4] = fma(G[1], G[2], fma(G[4], G[5], tr[4]));
+        tr[5] = fma(G[2], G[2], fma(G[5], G[5], tr[5]));
 #pragma unroll
-        for (int k = 0; k < 3; ++k) tr[6 + k] += G[k] * r[0] + G[3 + k] * r[1];
+        for (int k = 0; k < 3; ++k) tr[6 + k] = fma(G[k], r[0], fma(G[3 + k], r[1], tr[6 + k]));
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
-          for (int c = 0; c < NC; ++c) tr[9 + k * NC + c] += G[k] * J[c] + G[3 + k] * J[NC + c];
-        // camera block
+          for (int c = 0; c < NC; ++c) tr[9 + k * NC + c] = fma(G[k], J[c], fma(G[3 + k], J[NC + c], tr[9 + k * NC + c]));
         int h = 0;
 #pragma unroll
         for (int c1 = 0; c1 < NC; ++c1)
 #pragma unroll
           for (int c2 = 0; c2 <= c1; ++c2) {
-            acc[h] += J[c1] * J[c2] + J[NC + c1] * J[NC + c2];
+            acc[h] = fma(J[c1], J[c2], fma(J[NC + c1], J[NC + c2], acc[h]));
             ++h;
           }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[NH + c] += J[c] * r[0] + J[NC + c] * r[1];
+        for (int c = 0; c < NC; ++c) acc[NH + c] = fma(J[c], r[0], fma(J[NC + c], r[1], acc[NH + c]));
+      }
+      // ---- end of the track: combine the L lanes, write the record ----
+      if (b1 >= te) {  // the next step starts another track (or the slice is finished)
+        if (L > 1) {
+#pragma unroll
+          for (int v = 0; v < RS; ++v)
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) tr[v] += __shfl_xor_sync(gmask, tr[v], o);
+        }
+        double* dst = recs + (size_t)t * RS;
+#pragma unroll
+        for (int v = 0; v < RS; ++v)
+          if ((v % L) == lig) dst[v] = tr[v];
+        t = t1;
+        te = te1;
+        fresh = true;
+      }
+      // ---- rotate the pipeline ----
+      b0 = b1;
+      v0 = v1;
+      o0 = o1;
+      slot ^= 1;
+      b1 = b2;
+      t1 = t2;
+      te1 = te2;
+      v1 = v2;
+      o1 = o2;
+      l1 = l2;
+      b2 = next_base(b1, t2, te2);
+      v2 = (b2 < i_end) && (b2 + lig < te2);
+    }
+    __pipeline_wait_prior(0);
+  }
+  block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_eval_gram: fused evaluation in FEATURE form (lfba_math.cuh, obs_features / GramMap).
+// Per observation the thread accumulates the Gram matrix of NC+1 two-component features (65 running sums for NC = 9)
+// instead of 91 Jacobian-block sums; when a track ends its L lanes combine the Gram sums with xor-shuffles and
+// expand them — once per track, split over the L lanes — into the track record (A, b, C) and the camera block
+// (Hcc, gc), whose running totals live in a per-thread column of shared memory because they are touched once per
+// track, not once per observation. Result: ~35% fewer FP64 instructions per observation and no register spills.
+// ------------------------------------------------------------------------------------------------
+template <int NC, int NRAD, int L>
+__global__ void __launch_bounds__(128, 2) k_eval_gram(Dev d) {
+  const LmState* st = d.st;
+  if (st->done || st->eval_skip) return;
+  const int cand = 1 - st->cur;
+  constexpr int NH = NC * (NC + 1) / 2;
+  constexpr int NV = NH + NC + 1;
+  constexpr int RS = 9 + 3 * NC;
+  constexpr int NF = FeatDims<NC>::NF, NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
+  typedef GramMap<NC> GM;
+  __shared__ CamModel cm;
+  __shared__ double red[4 * NV];
+  extern __shared__ double pers[];  // [NV][128]: per-thread camera-block totals
+  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) pers[v * 128 + threadIdx.x] = 0.0;
+  __syncthreads();
+
+  const int lig = threadIdx.x % L;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int ngroups = (gridDim.x * blockDim.x) / L;
+  const int iters = (d.T + ngroups - 1) / ngroups;
+  const double* __restrict__ frames = d.frames[cand];
+  const double* __restrict__ points = d.points[cand];
+  double* __restrict__ recs = d.rec[cand];
+  const bool robust = cm.robust != 0;
+  double cost = 0.0;
+
+  for (int it = 0; it < iters; ++it) {
+    const int slot = group + it * ngroups;
+    const bool valid = slot < d.T;
+    const int t = valid ? (d.eval_order ? d.eval_order[slot] : slot) : 0;
+    double g[NG];
+#pragma unroll
+    for (int v = 0; v < NG; ++v) g[v] = 0.0;
+    TrackCtx tc;
+    if (valid) {
+      const int p = d.trk_point[t], f = d.trk_frame[t];
+      const int ob = d.trk_begin[t], oe = d.trk_begin[t + 1];
+      double Pc[3];
+      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
+      track_setup(cm, Pc, tc);
+      for (int i = ob + lig; i < oe; i += L) {
+        const double2 o = d.obs[i];
+        const double2* lp = reinterpret_cast<const double2*>(d.lens + (size_t)d.lens_id[i] * kLensStride);
+        double e[kLensStride];
+#pragma unroll
+        for (int k = 0; k < kLensStride / 2; ++k) {
+          const double2 v2 = __ldg(lp + k);
+          e[2 * k] = v2.x;
+          e[2 * k + 1] = v2.y;
+        }
+        double r[2], F[2 * NF];
+        obs_features<NC, NRAD>(cm, tc, e, o.x, o.y, r, F);
+        const double s = r[0] * r[0] + r[1] * r[1];
+        if (robust) {
+          double rho;
+          const double sw = robust_scale(cm, s, rho);
+          cost += 0.5 * rho;
+          r[0] *= sw;
+          r[1] *= sw;
+#pragma unroll
+          for (int k = 0; k < 2 * NF; ++k) F[k] *= sw;
+        } else {
+          cost += 0.5 * s;
+        }
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < NF; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            g[q] = fma(F[a], F[b], fma(F[NF + a], F[NF + b], g[q]));
+            ++q;
+          }
+#pragma unroll
+        for (int a = 0; a < NF; ++a) g[NQ + a] = fma(F[a], r[0], fma(F[NF + a], r[1], g[NQ + a]));
       }
     }
     if (L > 1) {
 #pragma unroll
-      for (int v = 0; v < RS; ++v)
+      for (int v = 0; v < NG; ++v)
 #pragma unroll
-        for (int o = L / 2; o > 0; o >>= 1) tr[v] += __shfl_xor_sync(0xffffffffu, tr[v], o);
+        for (int o = L / 2; o > 0; o >>= 1) g[v] += __shfl_xor_sync(0xffffffffu, g[v], o);
     }
     if (valid) {
+      // expand the Gram sums into the track record and the camera block; entries are split over the L lanes
+      const double* h = g + NQ;
       double* dst = recs + (size_t)t * RS;
+      int v = 0;
 #pragma unroll
-      for (int v = 0; v < RS; ++v)
-        if ((v % L) == lig) dst[v] = tr[v];
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+          if ((v % L) == lig) dst[v] = GM::gg(tc, g, i, j);
+          ++v;
+        }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if ((v % L) == lig) dst[v] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
+        ++v;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if ((v % L) == lig) dst[v] = GM::gcam(tc, g, i, c);
+          ++v;
+        }
+      int hh = 0;
+#pragma unroll
+      for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+        for (int c2 = 0; c2 <= c1; ++c2) {
+          if ((hh % L) == lig) pers[hh * 128 + threadIdx.x] += GM::cc(tc, g, c1, c2);
+          ++hh;
+        }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (((NH + c) % L) == lig) {
+          double gcv;
+          if (c < 3) {
+            double a, b;
+            GM::geo(tc, c, a, b);
+            gcv = a * h[3] + b * h[2];
+          } else {
+            gcv = h[c + 1];
+          }
+          pers[(NH + c) * 128 + threadIdx.x] += gcv;
+        }
+      }
     }
   }
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV - 1; ++v) acc[v] = pers[v * 128 + threadIdx.x];
+  acc[NV - 1] = cost;
   block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
 }
 
@@ -1074,16 +1435,69 @@ __global__ void __launch_bounds__(128) k_init_norms(Dev d) {
 // ================================================================================================
 // launchers
 // ================================================================================================
-template <int NC>
-static void launch_eval_nc(const Dev& d, int L, int grid, cudaStream_t s) {
+template <int NC, int NRAD, int PART>
+static void launch_eval_part(const Dev& d, int L, int grid, cudaStream_t s) {
   switch (L) {
-    case 1: k_eval_tracks<NC, 1><<<grid, 128, 0, s>>>(d); break;
-    case 2: k_eval_tracks<NC, 2><<<grid, 128, 0, s>>>(d); break;
-    case 4: k_eval_tracks<NC, 4><<<grid, 128, 0, s>>>(d); break;
-    case 8: k_eval_tracks<NC, 8><<<grid, 128, 0, s>>>(d); break;
-    default: k_eval_tracks<NC, 16><<<grid, 128, 0, s>>>(d); break;
+    case 1: k_eval_tracks<NC, NRAD, 1, PART><<<grid, 128, 0, s>>>(d); break;
+    case 2: k_eval_tracks<NC, NRAD, 2, PART><<<grid, 128, 0, s>>>(d); break;
+    case 4: k_eval_tracks<NC, NRAD, 4, PART><<<grid, 128, 0, s>>>(d); break;
+    case 8: k_eval_tracks<NC, NRAD, 8, PART><<<grid, 128, 0, s>>>(d); break;
+    default: k_eval_tracks<NC, NRAD, 16, PART><<<grid, 128, 0, s>>>(d); break;
   }
 }
+// mode 0: direct Jacobian-block sums, one pass; 1: the same in two passes; 2: software-pipelined stream kernel;
+// 3 (default): feature/Gram form
+static int eval_mode() {
+  static const int m = [] {
+    const char* e = std::getenv("LFBA_EVAL_MODE");
+    return e ? std::atoi(e) : 3;
+  }();
+  return m;
+}
+template <int NC, int NRAD>
+static int launch_eval_nc(const Dev& d, int L, int grid, cudaStream_t s) {
+  const int mode = eval_mode();
+  if (mode == 2) {
+    switch (L) {
+      case 1: k_eval_stream<NC, NRAD, 1><<<grid, 128, 0, s>>>(d); break;
+      case 2: k_eval_stream<NC, NRAD, 2><<<grid, 128, 0, s>>>(d); break;
+      case 4: k_eval_stream<NC, NRAD, 4><<<grid, 128, 0, s>>>(d); break;
+      case 8: k_eval_stream<NC, NRAD, 8><<<grid, 128, 0, s>>>(d); break;
+      default: k_eval_stream<NC, NRAD, 16><<<grid, 128, 0, s>>>(d); break;
+    }
+    return 1;
+  }
+  if (mode == 0) {
+    launch_eval_part<NC, NRAD, 0>(d, L, grid, s);
+    return 1;
+  }
+  if (mode == 3) {
+    constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
+    const size_t smem = (size_t)NV * 128 * sizeof(double);
+    switch (L) {
+      case 1: k_eval_gram<NC, NRAD, 1><<<grid, 128, smem, s>>>(d); break;
+      case 2: k_eval_gram<NC, NRAD, 2><<<grid, 128, smem, s>>>(d); break;
+      case 4: k_eval_gram<NC, NRAD, 4><<<grid, 128, smem, s>>>(d); break;
+      case 8: k_eval_gram<NC, NRAD, 8><<<grid, 128, smem, s>>>(d); break;
+      default: k_eval_gram<NC, NRAD, 16><<<grid, 128, smem, s>>>(d); break;
+    }
+    return 1;
+  }
+  launch_eval_part<NC, NRAD, 1>(d, L, grid, s);
+  launch_eval_part<NC, NRAD, 2>(d, L, grid, s);
+  return 2;
+}
+
+// (nRadial, tangential) -> compile-time <NC, NRAD>
+#define LFBA_DISPATCH_MODEL(NRADV, TANV, CALL)                                         \
+  switch ((NRADV) * 2 + ((TANV) ? 1 : 0)) {                                            \
+    case 0: { constexpr int NC = 5, NRAD = 0; CALL; } break;                           \
+    case 1: { constexpr int NC = 7, NRAD = 0; CALL; } break;                           \
+    case 2: { constexpr int NC = 6, NRAD = 1; CALL; } break;                           \
+    case 3: { constexpr int NC = 8, NRAD = 1; CALL; } break;                           \
+    case 4: { constexpr int NC = 7, NRAD = 2; CALL; } break;                           \
+    default: { constexpr int NC = 9, NRAD = 2; CALL; } break;                          \
+  }
 
 #define LFBA_DISPATCH_NC(NCV, CALL)   \
   switch (NCV) {                      \
@@ -1094,12 +1508,33 @@ static void launch_eval_nc(const Dev& d, int L, int grid, cudaStream_t s) {
     default: { constexpr int NC = 9; CALL; } break; \
   }
 
+template <int NC, int NRAD>
+static void prepare_eval_nc() {
+  constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
+  const int smem = NV * 128 * (int)sizeof(double);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+void prepare_eval_kernels() {
+  prepare_eval_nc<5, 0>();
+  prepare_eval_nc<7, 0>();
+  prepare_eval_nc<6, 1>();
+  prepare_eval_nc<8, 1>();
+  prepare_eval_nc<7, 2>();
+  prepare_eval_nc<9, 2>();
+}
 void launch_tables(const Dev& d, cudaStream_t s) {
   const int n = d.NL > d.F ? d.NL : d.F;
   k_tables<<<(n + 127) / 128, 128, 0, s>>>(d);
 }
-void launch_eval(const Dev& d, int L, cudaStream_t s) {
-  LFBA_DISPATCH_NC(d.NC, launch_eval_nc<NC>(d, L, d.grid_eval, s));
+int launch_eval(const Dev& d, int L, cudaStream_t s) {
+  int n = 1;
+  const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
+  LFBA_DISPATCH_MODEL(nrad, tang, (n = launch_eval_nc<NC, NRAD>(d, L, d.grid_eval, s)));
+  return n;
 }
 void launch_reduce_eval(const Dev& d, cudaStream_t s) { k_reduce_eval<<<1, 128, 0, s>>>(d); }
 void launch_control_accept(const Dev& d, cudaStream_t s) { k_control_accept<<<1, 1, 0, s>>>(d); }

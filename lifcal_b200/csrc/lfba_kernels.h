@@ -9,7 +9,7 @@ namespace lfba {
 // ---- lfba_kernels.cu: one LM round ----
 void launch_init_norms(const Dev& d, cudaStream_t s);
 void launch_tables(const Dev& d, cudaStream_t s);
-void launch_eval(const Dev& d, int lanes_per_track, cudaStream_t s);
+int launch_eval(const Dev& d, int lanes_per_track, cudaStream_t s);  // returns the number of kernels launched
 void launch_reduce_eval(const Dev& d, cudaStream_t s);
 void launch_control_accept(const Dev& d, cudaStream_t s);
 int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s);  // returns the number of kernels launched
@@ -20,8 +20,9 @@ int launch_steps(const Dev& d, cudaStream_t s);
 // In-place tiled Cholesky of the skyline matrix (n + 1 rows: the last row is the rhs, which comes out
 // forward-substituted), then the backward substitution into d.y. Returns the number of kernels launched.
 void prepare_device_kernels();
-int launch_reduced_solve(const Dev& d, int n_tiles, const int* h_tile_first /*[n_tiles] first nonzero tile col*/,
-                         cudaStream_t s);
+void prepare_eval_kernels();
+int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first /*[n_tiles] first nonzero tile col*/,
+                         int bandwidth_frames, cudaStream_t s);
 
 // ---- lfba_eval.cu: eval-only kernel (residuals + Jacobians materialised in Ceres' block layout) ----
 struct EvalOut {

@@ -90,6 +90,7 @@ struct Solver {
   int lanes = 4;
   int frame_splits = 1;
   int n_tiles = 0;
+  int band_frames = 0;
   int64_t launches = 0;
   double setup_time = 0;
   int64_t n_obs_global = 0;
@@ -218,6 +219,7 @@ struct Solver {
     LFBA_CUDA(cudaStreamSynchronize(stream));
     n_obs_global = (int64_t)(h_n + 0.5);
     const int bw = h_fa[F];
+    band_frames = bw;
 
     // ---- reduced system layout [poses | coupled points | camera | rhs] and its skyline profile ----
     std::memset(&d, 0, sizeof(d));
@@ -339,6 +341,7 @@ struct Solver {
     for (auto& e : ev) LFBA_CUDA(cudaEventCreate(&e));
     ev_made = true;
     prepare_device_kernels();
+    prepare_eval_kernels();
     LFBA_CUDA(cudaStreamSynchronize(stream));
     setup_time = now_s() - t0;
   }
@@ -421,7 +424,7 @@ struct Solver {
       if (prof) LFBA_CUDA(cudaEventRecord(e_begin, stream));
       launch_tables(d, stream);
       mark(LFBA_T_LENS);
-      launch_eval(d, lanes, stream);
+      launches += launch_eval(d, lanes, stream) - 1;
       mark(LFBA_T_EVAL);
       launch_reduce_eval(d, stream);
       allreduce(d.eval_scalars, ES_COUNT, kNcclFloat64, kNcclSum);
@@ -435,7 +438,7 @@ struct Solver {
       mark(LFBA_T_ALLREDUCE);
       launch_finalize(d, stream);
       mark(LFBA_T_DAMP);
-      launches += 1 + launch_reduced_solve(d, n_tiles, tile_first.p, stream);
+      launches += 1 + launch_reduced_solve(d, n_tiles, tile_first.p, band_frames, stream);
       mark(LFBA_T_CHOL);
       launches += launch_steps(d, stream);
       mark(LFBA_T_POINTSTEP);

@@ -4,6 +4,7 @@
 // the oracle in the no-GPU test tier. It is NOT a fallback: it is built only by the tests, lives outside the
 // package and is never loaded by lifcal_b200/.
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -12,7 +13,12 @@
 
 using namespace lfba;
 
-template <int NC>
+static double g_feature_worst = 0.0;
+static double g_cancel_sum[3] = {0,0,0}, g_cancel_n[3] = {0,0,0}, g_cancel_max[3] = {0,0,0};
+extern "C" void harness_cancel(double* out) { for (int c = 0; c < 3; ++c) { out[2*c] = g_cancel_sum[c] / (g_cancel_n[c] + 1e-300); out[2*c+1] = g_cancel_max[c]; } }
+extern "C" double harness_feature_worst(void) { return g_feature_worst; }
+
+template <int NC, int NRAD>
 static void eval_all(const lfba_problem* pb, const CamModel& m, const double* views, const double* points,
                      double* res, double* jc, double* jv, double* jp) {
   const bool rp = pb->config & LFBA_CFG_REFINE_POSES, r3 = pb->config & LFBA_CFG_REFINE_POINTS;
@@ -25,9 +31,41 @@ static void eval_all(const lfba_problem* pb, const CamModel& m, const double* vi
     TrackCtx t;
     track_setup(m, Pc, t);
     double r[2], G[6], J[2 * NC];
-    obs_eval<NC>(m, t, le, pb->obs_x[i], pb->obs_y[i], r, G, J);
+    obs_eval<NC, NRAD>(m, t, le, pb->obs_x[i], pb->obs_y[i], r, G, J);
     double r2[2];
     obs_residual(m, t, le, pb->obs_x[i], pb->obs_y[i], r2);
+    {  // feature form must reproduce the same Jacobian blocks through the Gram expansion (single observation)
+      constexpr int NF = NC + 1, NQ = NF * (NF + 1) / 2;
+      double rf[2], F[2 * NF], g[NQ + NF];
+      obs_features<NC, NRAD>(m, t, le, pb->obs_x[i], pb->obs_y[i], rf, F);
+      int q = 0;
+      for (int a = 0; a < NF; ++a)
+        for (int b = 0; b <= a; ++b) g[q++] = F[a] * F[b] + F[NF + a] * F[NF + b];
+      for (int a = 0; a < NF; ++a) g[NQ + a] = F[a] * rf[0] + F[NF + a] * rf[1];
+      double worst = 0.0;
+      auto chk = [&](double a, double b) {
+        const double den = fabs(a) > fabs(b) ? fabs(a) : fabs(b);
+        if (den > 0 && fabs(a - b) / den > worst) worst = fabs(a - b) / den;
+      };
+      if (rf[0] != r[0] || rf[1] != r[1]) worst = 1.0;
+      for (int c1 = 0; c1 < NC; ++c1)
+        for (int c2 = 0; c2 <= c1; ++c2)
+          chk(GramMap<NC>::cc(t, g, c1, c2), J[c1] * J[c2] + J[NC + c1] * J[NC + c2]);
+      for (int a = 0; a < 3; ++a) {
+        for (int c = 0; c < NC; ++c) chk(GramMap<NC>::gcam(t, g, a, c), G[a] * J[c] + G[3 + a] * J[NC + c]);
+        for (int b = 0; b < 3; ++b) chk(GramMap<NC>::gg(t, g, a, b), G[a] * G[b] + G[3 + a] * G[3 + b]);
+      }
+      if (worst > g_feature_worst) g_feature_worst = worst;
+      for (int c = 0; c < 3; ++c) {
+        double a, b;
+        GramMap<NC>::geo(t, c, a, b);
+        for (int row = 0; row < 2; ++row) {
+          const double t1 = (a + b * t.a1 * m.gamma) * F[row * NF + 3], t2 = b * (t.Px * F[row * NF + 0] + t.Py * F[row * NF + 1]);
+          const double ratio = (fabs(t1) + fabs(t2)) / (fabs(t1 + t2) + 1e-300);
+          g_cancel_sum[c] += (fabs(t1) + fabs(t2)) * (fabs(t1) + fabs(t2)); g_cancel_n[c] += (t1 + t2) * (t1 + t2); if (ratio > g_cancel_max[c]) g_cancel_max[c] = ratio;
+        }
+      }
+    }
     res[2 * i] = r[0];
     res[2 * i + 1] = r[1];
     if (r2[0] != r[0] || r2[1] != r[1]) res[2 * i] = 1e300;  // the two code paths must agree exactly
@@ -52,12 +90,13 @@ extern "C" int harness_eval(const lfba_problem* pb, const double* camera, const 
                             double* res, double* jc, double* jv, double* jp) {
   CamModel m;
   cam_model_init(m, camera, pb->config, pb->spx, pb->spy, pb->scale, 0.5);
-  switch (m.nc) {
-    case 5: eval_all<5>(pb, m, views, points, res, jc, jv, jp); break;
-    case 6: eval_all<6>(pb, m, views, points, res, jc, jv, jp); break;
-    case 7: eval_all<7>(pb, m, views, points, res, jc, jv, jp); break;
-    case 8: eval_all<8>(pb, m, views, points, res, jc, jv, jp); break;
-    case 9: eval_all<9>(pb, m, views, points, res, jc, jv, jp); break;
+  switch (m.n_radial * 2 + m.tangential) {
+    case 0: eval_all<5, 0>(pb, m, views, points, res, jc, jv, jp); break;
+    case 1: eval_all<7, 0>(pb, m, views, points, res, jc, jv, jp); break;
+    case 2: eval_all<6, 1>(pb, m, views, points, res, jc, jv, jp); break;
+    case 3: eval_all<8, 1>(pb, m, views, points, res, jc, jv, jp); break;
+    case 4: eval_all<7, 2>(pb, m, views, points, res, jc, jv, jp); break;
+    case 5: eval_all<9, 2>(pb, m, views, points, res, jc, jv, jp); break;
     default: return 1;
   }
   return 0;
