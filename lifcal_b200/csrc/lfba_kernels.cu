@@ -84,6 +84,16 @@ __global__ void k_tables(Dev d) {
   if (i < d.NL) {
     double e[kLensStride];
     lens_entry(cm, d.lens_xy[2 * i], d.lens_xy[2 * i + 1], e);
+    {  // how far is the implicit-function derivative from the exact ten-step recurrence? (see lens_implicit_derivs)
+      double im[12], num = 0.0, den = 0.0;
+      lens_implicit_derivs(cm, e[2], e[3], im);
+      for (int k = 0; k < 12; ++k) {
+        num = fmax(num, fabs(im[k] - e[4 + k]));
+        den = fmax(den, fabs(e[4 + k]));
+      }
+      const double dev = den > 0.0 ? num / den : 0.0;
+      if (dev > 0.0) atomicMax(d.lens_dev, (unsigned long long)__double_as_longlong(dev));
+    }
     double2* dst = reinterpret_cast<double2*>(d.lens + (size_t)i * kLensStride);
 #pragma unroll
     for (int k = 0; k < kLensStride / 2; ++k) dst[k] = make_double2(e[2 * k], e[2 * k + 1]);
@@ -429,10 +439,12 @@ __global__ void __launch_bounds__(128) k_eval_stream(Dev d) {
 // (Hcc, gc), whose running totals live in a per-thread column of shared memory because they are touched once per
 // track, not once per observation. Result: ~35% fewer FP64 instructions per observation and no register spills.
 // ------------------------------------------------------------------------------------------------
-template <int NC, int NRAD, int L>
+template <int NC, int NRAD, int L, bool IMPLICIT>
 __global__ void __launch_bounds__(128, 2) k_eval_gram(Dev d) {
   const LmState* st = d.st;
   if (st->done || st->eval_skip) return;
+  // two instantiations are launched back to back; exactly one of them does the work (device-side decision)
+  if ((__longlong_as_double((long long)*d.lens_dev) <= d.implicit_tol) != IMPLICIT) return;
   const int cand = 1 - st->cur;
   constexpr int NH = NC * (NC + 1) / 2;
   constexpr int NV = NH + NC + 1;
@@ -475,11 +487,21 @@ __global__ void __launch_bounds__(128, 2) k_eval_gram(Dev d) {
         const double2 o = d.obs[i];
         const double2* lp = reinterpret_cast<const double2*>(d.lens + (size_t)d.lens_id[i] * kLensStride);
         double e[kLensStride];
+        if (IMPLICIT) {
+          // one 32-byte sector per observation: (mx, my, ux, uy); the derivatives are recomputed from u
+          const double2 v0 = __ldg(lp), v1 = __ldg(lp + 1);
+          e[0] = v0.x;
+          e[1] = v0.y;
+          e[2] = v1.x;
+          e[3] = v1.y;
+          lens_implicit_derivs(cm, e[2], e[3], e + 4);
+        } else {
 #pragma unroll
-        for (int k = 0; k < kLensStride / 2; ++k) {
-          const double2 v2 = __ldg(lp + k);
-          e[2 * k] = v2.x;
-          e[2 * k + 1] = v2.y;
+          for (int k = 0; k < kLensStride / 2; ++k) {
+            const double2 v2 = __ldg(lp + k);
+            e[2 * k] = v2.x;
+            e[2 * k + 1] = v2.y;
+          }
         }
         double r[2], F[2 * NF];
         obs_features<NC, NRAD>(cm, tc, e, o.x, o.y, r, F);
@@ -567,6 +589,229 @@ __global__ void __launch_bounds__(128, 2) k_eval_gram(Dev d) {
   acc[NV - 1] = cost;
   block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
 }
+
+
+// k_eval_gram with the lens-entry gather software-pipelined (cp.async into per-thread shared-memory slots, observation
+// and lens id prefetched two steps ahead): the dependent load lens_id -> lens entry leaves the critical path.
+template <int NC, int NRAD, int L>
+__global__ void __launch_bounds__(128, 2) k_eval_gram_pf(Dev d) {
+  const LmState* st = d.st;
+  if (st->done || st->eval_skip) return;
+  const int cand = 1 - st->cur;
+  constexpr int NH = NC * (NC + 1) / 2;
+  constexpr int NV = NH + NC + 1;
+  constexpr int RS = 9 + 3 * NC;
+  constexpr int NF = FeatDims<NC>::NF, NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
+  typedef GramMap<NC> GM;
+  __shared__ CamModel cm;
+  __shared__ double red[4 * NV];
+  extern __shared__ double pers[];  // [NV][128]: per-thread camera-block totals, then [2][8][128] double2 lens slots
+  double2* lens_s = reinterpret_cast<double2*>(pers + NV * 128);
+  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) pers[v * 128 + threadIdx.x] = 0.0;
+  __syncthreads();
+
+  const int lig = threadIdx.x % L;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+  const int ngroups = (gridDim.x * blockDim.x) / L;
+  const int iters = (d.T + ngroups - 1) / ngroups;
+  const double* __restrict__ frames = d.frames[cand];
+  const double* __restrict__ points = d.points[cand];
+  double* __restrict__ recs = d.rec[cand];
+  const bool robust = cm.robust != 0;
+  double cost = 0.0;
+
+  // ---- software pipeline over the lane's observation steps (see k_eval_stream for the idea; here the groups of a
+  //      warp stay in lock step per track round, so there is no extra divergence) ----
+  double2* myslot = lens_s + threadIdx.x;
+  auto issue_lens = [&](int lid, int sl) {
+    const double2* src = reinterpret_cast<const double2*>(d.lens + (size_t)lid * kLensStride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) __pipeline_memcpy_async(myslot + (sl * 8 + k) * 128, src + k, 16);
+  };
+  auto load_track = [&](int slot, int& tt, int& b, int& e2, bool& ok) {
+    ok = slot < d.T;
+    tt = ok ? (d.eval_order ? d.eval_order[slot] : slot) : 0;
+    b = ok ? d.trk_begin[tt] : 0;
+    e2 = ok ? d.trk_begin[tt + 1] : 0;
+  };
+  int t, ob, oe, nt, nob, noe;
+  bool valid, nvalid;
+  load_track(group, t, ob, oe, valid);
+  load_track(group + ngroups, nt, nob, noe, nvalid);
+  // pipeline registers: current (c), next (n), next-next (nn)
+  double2 o_c = make_double2(0.0, 0.0), o_n = o_c, o_nn = o_c;
+  int lid_n = 0, lid_nn = 0;
+  bool v_c = false, v_n = false, have_n = true, v_nn = false, have_nn = true;
+  int sl = 0;
+  {  // prologue: step (0,0) current, step +1 as next
+    const int i0 = ob + lig;
+    v_c = valid && i0 < oe;
+    if (v_c) {
+      o_c = d.obs[i0];
+      issue_lens(d.lens_id[i0], 0);
+    }
+    __pipeline_commit();
+    const int ns0 = valid ? (oe - ob + L - 1) / L : 0;
+    int i1;
+    if (1 < ns0) { i1 = ob + lig + L; v_n = i1 < oe; }
+    else { i1 = nob + lig; v_n = nvalid && i1 < noe; }
+    if (v_n) {
+      o_n = d.obs[i1];
+      lid_n = d.lens_id[i1];
+    }
+  }
+
+  for (int it = 0; it < iters; ++it) {
+    double g[NG];
+#pragma unroll
+    for (int v = 0; v < NG; ++v) g[v] = 0.0;
+    TrackCtx tc;
+    const int nsteps = valid ? (oe - ob + L - 1) / L : 0;
+    const int nsteps_next = nvalid ? (noe - nob + L - 1) / L : 0;
+    if (valid) {
+      const int p = d.trk_point[t], f = d.trk_frame[t];
+      double Pc[3];
+      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
+      track_setup(cm, Pc, tc);
+    }
+    for (int m = 0; m < nsteps; ++m) {
+      // next step's lens entry: cp.async into the other slot (its lens id was loaded one step ago)
+      if (v_n && !have_n) {  // rare: the look-ahead could not see this item (track of <= L observations)
+        const bool same = m + 1 < nsteps;
+        const int i1 = same ? ob + lig + L * (m + 1) : nob + lig;
+        v_n = same ? (i1 < oe) : (nvalid && i1 < noe);
+        have_n = true;
+        if (v_n) {
+          o_n = d.obs[i1];
+          lid_n = d.lens_id[i1];
+        }
+      }
+      if (v_n) issue_lens(lid_n, sl ^ 1);
+      __pipeline_commit();
+      // observation + lens id two steps ahead
+      {
+        int i2 = 0;
+        have_nn = true;
+        if (m + 2 < nsteps) { i2 = ob + lig + L * (m + 2); v_nn = i2 < oe; }
+        else if (m + 1 < nsteps) { i2 = nob + lig; v_nn = nvalid && i2 < noe; }
+        else if (nsteps_next > 1) { i2 = nob + lig + L; v_nn = nvalid && i2 < noe; }
+        else { v_nn = true; have_nn = false; }  // belongs to the round after next: fetched when it becomes "next"
+        if (v_nn && have_nn) {
+          o_nn = d.obs[i2];
+          lid_nn = d.lens_id[i2];
+        }
+      }
+      __pipeline_wait_prior(1);
+      if (v_c) {
+        LensSlot e{myslot + sl * 8 * 128};
+        double r[2], F[2 * NF];
+        obs_features<NC, NRAD>(cm, tc, e, o_c.x, o_c.y, r, F);
+        const double s = r[0] * r[0] + r[1] * r[1];
+        if (robust) {
+          double rho;
+          const double sw = robust_scale(cm, s, rho);
+          cost += 0.5 * rho;
+          r[0] *= sw;
+          r[1] *= sw;
+#pragma unroll
+          for (int k = 0; k < 2 * NF; ++k) F[k] *= sw;
+        } else {
+          cost += 0.5 * s;
+        }
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < NF; ++a)
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            g[q] = fma(F[a], F[b], fma(F[NF + a], F[NF + b], g[q]));
+            ++q;
+          }
+#pragma unroll
+        for (int a = 0; a < NF; ++a) g[NQ + a] = fma(F[a], r[0], fma(F[NF + a], r[1], g[NQ + a]));
+      }
+      // rotate
+      o_c = o_n;
+      v_c = v_n;
+      sl ^= 1;
+      o_n = o_nn;
+      lid_n = lid_nn;
+      v_n = v_nn;
+      have_n = have_nn;
+    }
+    if (L > 1) {
+#pragma unroll
+      for (int v = 0; v < NG; ++v)
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) g[v] += __shfl_xor_sync(0xffffffffu, g[v], o);
+    }
+    if (valid) {
+      // expand the Gram sums into the track record and the camera block; entries are split over the L lanes
+      const double* h = g + NQ;
+      double* dst = recs + (size_t)t * RS;
+      int v = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+          if ((v % L) == lig) dst[v] = GM::gg(tc, g, i, j);
+          ++v;
+        }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if ((v % L) == lig) dst[v] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
+        ++v;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if ((v % L) == lig) dst[v] = GM::gcam(tc, g, i, c);
+          ++v;
+        }
+      int hh = 0;
+#pragma unroll
+      for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+        for (int c2 = 0; c2 <= c1; ++c2) {
+          if ((hh % L) == lig) pers[hh * 128 + threadIdx.x] += GM::cc(tc, g, c1, c2);
+          ++hh;
+        }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (((NH + c) % L) == lig) {
+          double gcv;
+          if (c < 3) {
+            double a, b;
+            GM::geo(tc, c, a, b);
+            gcv = a * h[3] + b * h[2];
+          } else {
+            gcv = h[c + 1];
+          }
+          pers[(NH + c) * 128 + threadIdx.x] += gcv;
+        }
+      }
+    }
+    // next round: the prefetched track becomes current; fetch the one after
+    t = nt;
+    ob = nob;
+    oe = noe;
+    valid = nvalid;
+    load_track(group + (it + 2) * ngroups, nt, nob, noe, nvalid);
+    if (!valid) {  // an invalid round has no steps: the "next" item of the dead round must not leak into a live one
+      v_c = false;
+      v_n = false;
+    }
+  }
+  __pipeline_wait_prior(0);
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV - 1; ++v) acc[v] = pers[v * 128 + threadIdx.x];
+  acc[NV - 1] = cost;
+  block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
+}
+
 
 // Sum the CTA partials of k_eval_tracks (fixed order) -> camsum[cand]; sum the step partials of
 // k_point_step (previous round); candidate cost of the distance constraints; assemble eval_scalars.
@@ -1475,11 +1720,23 @@ static int launch_eval_nc(const Dev& d, int L, int grid, cudaStream_t s) {
     constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
     const size_t smem = (size_t)NV * 128 * sizeof(double);
     switch (L) {
-      case 1: k_eval_gram<NC, NRAD, 1><<<grid, 128, smem, s>>>(d); break;
-      case 2: k_eval_gram<NC, NRAD, 2><<<grid, 128, smem, s>>>(d); break;
-      case 4: k_eval_gram<NC, NRAD, 4><<<grid, 128, smem, s>>>(d); break;
-      case 8: k_eval_gram<NC, NRAD, 8><<<grid, 128, smem, s>>>(d); break;
-      default: k_eval_gram<NC, NRAD, 16><<<grid, 128, smem, s>>>(d); break;
+      case 1: k_eval_gram<NC, NRAD, 1, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 1, false><<<grid, 128, smem, s>>>(d); break;
+      case 2: k_eval_gram<NC, NRAD, 2, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 2, false><<<grid, 128, smem, s>>>(d); break;
+      case 4: k_eval_gram<NC, NRAD, 4, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 4, false><<<grid, 128, smem, s>>>(d); break;
+      case 8: k_eval_gram<NC, NRAD, 8, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 8, false><<<grid, 128, smem, s>>>(d); break;
+      default: k_eval_gram<NC, NRAD, 16, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 16, false><<<grid, 128, smem, s>>>(d); break;
+    }
+    return 2;
+  }
+  if (mode == 4) {
+    constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
+    const size_t smem = (size_t)NV * 128 * sizeof(double) + 2 * 8 * 128 * sizeof(double2);
+    switch (L) {
+      case 1: k_eval_gram_pf<NC, NRAD, 1><<<grid, 128, smem, s>>>(d); break;
+      case 2: k_eval_gram_pf<NC, NRAD, 2><<<grid, 128, smem, s>>>(d); break;
+      case 4: k_eval_gram_pf<NC, NRAD, 4><<<grid, 128, smem, s>>>(d); break;
+      case 8: k_eval_gram_pf<NC, NRAD, 8><<<grid, 128, smem, s>>>(d); break;
+      default: k_eval_gram_pf<NC, NRAD, 16><<<grid, 128, smem, s>>>(d); break;
     }
     return 1;
   }
@@ -1512,11 +1769,22 @@ template <int NC, int NRAD>
 static void prepare_eval_nc() {
   constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
   const int smem = NV * 128 * (int)sizeof(double);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem2 = smem + 2 * 8 * 128 * (int)sizeof(double2);
+  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
 }
 void prepare_eval_kernels() {
   prepare_eval_nc<5, 0>();

@@ -1,6 +1,10 @@
 // lfba_setup.cu — device-side indexing of the observations (see lfba_setup.cuh).
 #include "lfba_setup.cuh"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 namespace lfba {
 
 namespace {
@@ -8,12 +12,12 @@ namespace {
 struct Temp {
   void* p = nullptr;
   size_t bytes = 0;
-  ~Temp() { if (p) cudaFree(p); }
+  ~Temp() { if (p) cudaFreeAsync(p, alloc_stream()); }
   void reserve(size_t b) {
     if (b > bytes) {
-      if (p) cudaFree(p);
+      if (p) cudaFreeAsync(p, alloc_stream());
       p = nullptr;
-      LFBA_CUDA(cudaMalloc(&p, b));
+      LFBA_CUDA(cudaMallocAsync(&p, b, alloc_stream()));
       bytes = b;
     }
   }
@@ -25,22 +29,22 @@ void sort_pairs(Temp& tmp, const K* kin, K* kout, const V* vin, V* vout, size_t 
   if (n == 0) return;
   size_t bytes = 0;
   if (descending) {
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s);
     tmp.reserve(bytes);
-    LFBA_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s));
+    LFBA_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
   } else {
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s);
     tmp.reserve(bytes);
-    LFBA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int64_t)n, 0, end_bit, s));
+    LFBA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
   }
 }
 template <class T>
 void exclusive_sum(Temp& tmp, const T* in, T* out, size_t n, cudaStream_t s) {
   if (n == 0) return;
   size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, s);
   tmp.reserve(bytes);
-  LFBA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int64_t)n, s));
+  LFBA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, s));
 }
 int bits_for(uint64_t v) {
   int b = 1;
@@ -48,20 +52,35 @@ int bits_for(uint64_t v) {
   return b;
 }
 
-__global__ void k_make_keys(const int32_t* pt, const int32_t* fr, uint64_t* keys, int32_t* vals, int64_t n) {
+__global__ void k_make_keys(const int32_t* pt, const int32_t* fr, uint64_t* keys, int32_t* vals, int64_t n, int P, int F,
+                            int* bad) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  keys[i] = ((uint64_t)(uint32_t)pt[i] << 32) | (uint32_t)fr[i];
+  const int p = pt[i], f = fr[i];
+  if (p < 0 || p >= P || f < 0 || f >= F) {  // index validation happens here, not in an O(N) host loop
+    *bad = 1;
+    keys[i] = 0;
+    vals[i] = (int32_t)i;
+    return;
+  }
+  keys[i] = ((uint64_t)(uint32_t)p << 32) | (uint32_t)f;
   vals[i] = (int32_t)i;
 }
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
 __global__ void k_gather_obs(const int32_t* perm, const double* ox, const double* oy, const double* mx,
-                             const double* my, double2* obs, uint64_t* ka, uint64_t* kb, int32_t* idx, int64_t n) {
+                             const double* my, double2* obs, uint64_t* ka, uint64_t* kb, uint64_t* kh, int32_t* idx, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int32_t j = perm[i];
   obs[i] = make_double2(ox[j], oy[j]);
-  ka[i] = (uint64_t)__double_as_longlong(my[j]);
-  kb[i] = (uint64_t)__double_as_longlong(mx[j]);
+  const uint64_t a = (uint64_t)__double_as_longlong(my[j]), b = (uint64_t)__double_as_longlong(mx[j]);
+  ka[i] = a;
+  kb[i] = b;
+  if (kh) kh[i] = mix64(a + 0x9e3779b97f4a7c15ull) ^ mix64(b * 0xd1342543de82ef95ull + 1);
   idx[i] = (int32_t)i;
 }
 __global__ void k_copy_in(const double* ox, const double* oy, double2* obs_in, int64_t n) {
@@ -75,6 +94,28 @@ __global__ void k_head_flags(const uint64_t* keys, int32_t* flags, int64_t n) {
 __global__ void k_head_flags2(const uint64_t* ka, const uint64_t* kb, int32_t* flags, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) flags[i] = (i == 0 || ka[i] != ka[i - 1] || kb[i] != kb[i - 1]) ? 1 : 0;
+}
+// heads of runs in hash order: a new lens starts where the hash OR the actual centre differs from the predecessor.
+// (A hash collision between two different centres can only split one lens into two table entries, never merge two.)
+__global__ void k_head_flags_hash(const uint64_t* kh, const uint64_t* ka, const uint64_t* kb, const int32_t* idx,
+                                  int32_t* flags, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0) { flags[i] = 1; return; }
+  const int32_t a = idx[i], b = idx[i - 1];
+  flags[i] = (kh[i] != kh[i - 1] || ka[a] != ka[b] || kb[a] != kb[b]) ? 1 : 0;
+}
+__global__ void k_fill_lens_hash(const uint64_t* ka, const uint64_t* kb, const int32_t* flags, const int32_t* lid,
+                                 const int32_t* idx, int32_t* lens_id, double* lens_xy, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = lid[i] + flags[i] - 1;
+  const int32_t src = idx[i];
+  lens_id[src] = l;
+  if (flags[i]) {
+    lens_xy[2 * (size_t)l] = __longlong_as_double((long long)kb[src]);
+    lens_xy[2 * (size_t)l + 1] = __longlong_as_double((long long)ka[src]);
+  }
 }
 __global__ void k_fill_tracks(const uint64_t* keys, const int32_t* flags, const int32_t* tid, int32_t* trk_begin,
                               int32_t* trk_point, int32_t* trk_frame, int32_t* pt_count, int32_t* fr_count,
@@ -152,6 +193,79 @@ __global__ void k_scatter_i32(const int32_t* perm, const int32_t* src, int32_t* 
   if (i < n) dst[perm[i]] = src[i];
 }
 
+// ---- distinct micro-lens centres through an exact open-addressing hash table (two-word keys, CAS per word) ----
+constexpr uint64_t kEmpty = 0xffffffffffffffffull;
+__global__ void k_lens_insert(const double* mx, const double* my, unsigned long long* keyA, unsigned long long* keyB,
+                              uint32_t mask, int32_t* slot_of, int* overflow, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long a = (unsigned long long)__double_as_longlong(mx[i]);
+  const unsigned long long b = (unsigned long long)__double_as_longlong(my[i]);
+  uint32_t h = (uint32_t)(mix64(a + 0x9e3779b97f4a7c15ull) ^ mix64(b * 0xd1342543de82ef95ull + 1)) & mask;
+  for (int probe = 0; probe < 4096; ++probe) {
+    unsigned long long ua = keyA[h];
+    if (ua == kEmpty) {
+      const unsigned long long old = atomicCAS(keyA + h, kEmpty, a);
+      ua = old == kEmpty ? a : old;
+    }
+    if (ua == a) {
+      unsigned long long ub = keyB[h];
+      if (ub == kEmpty) {
+        const unsigned long long old = atomicCAS(keyB + h, kEmpty, b);
+        ub = old == kEmpty ? b : old;
+      }
+      if (ub == b) {
+        slot_of[i] = (int32_t)h;
+        return;
+      }
+    }
+    h = (h + 1) & mask;
+  }
+  slot_of[i] = 0;
+  *overflow = 1;
+}
+__global__ void k_lens_mark(const unsigned long long* keyA, const unsigned long long* keyB, int32_t* occ, int cap) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < cap) occ[h] = (keyA[h] != kEmpty && keyB[h] != kEmpty) ? 1 : 0;
+}
+__global__ void k_lens_table(const unsigned long long* keyA, const unsigned long long* keyB, const int32_t* occ,
+                             const int32_t* id, double* lens_xy, int cap) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < cap && occ[h]) {
+    lens_xy[2 * (size_t)id[h]] = __longlong_as_double((long long)keyA[h]);
+    lens_xy[2 * (size_t)id[h] + 1] = __longlong_as_double((long long)keyB[h]);
+  }
+}
+__global__ void k_lens_assign(const int32_t* slot_of, const int32_t* id, int32_t* lens_id_in, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) lens_id_in[i] = id[slot_of[i]];
+}
+__global__ void k_check_sorted(const int32_t* pt, const int32_t* fr, int* unsorted, int* bad, int P, int F, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = pt[i], f = fr[i];
+  if (p < 0 || p >= P || f < 0 || f >= F) {
+    *bad = 1;
+    return;
+  }
+  if (i > 0) {
+    const int pp = pt[i - 1], pf = fr[i - 1];
+    if (pp > p || (pp == p && pf > f)) *unsorted = 1;
+  }
+}
+__global__ void k_keys_from_sorted_input(const int32_t* pt, const int32_t* fr, uint64_t* keys, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = ((uint64_t)(uint32_t)pt[i] << 32) | (uint32_t)fr[i];
+}
+__global__ void k_gather_sorted(const int32_t* perm, const double2* obs_in, const int32_t* lens_in, double2* obs,
+                                int32_t* lens, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t j = perm[i];
+  obs[i] = obs_in[j];
+  lens[i] = lens_in[j];
+}
+
 inline unsigned grid_for(int64_t n, int b = 256) { return (unsigned)((n + b - 1) / b); }
 
 }  // namespace
@@ -165,8 +279,17 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
   ix.F = F;
   Temp tmp;
   int64_t nl = 0;
+  const bool dbg = std::getenv("LFBA_DEBUG") != nullptr;
+  double tp = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  auto phase = [&](const char* name) {
+    if (!dbg) return;
+    cudaStreamSynchronize(s);
+    const double t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    std::fprintf(stderr, "[lfba dbg]   index %-26s %8.2f ms\n", name, 1e3 * (t - tp));
+    tp = t;
+  };
 
-  // raw input (input order)
+  // raw input (input order); the ox/oy/mx/my staging buffers live only until the indexed copies exist
   DevBuf<double> ox(N), oy(N), mx(N), my(N);
   ix.point_in.alloc(N);
   ix.frame_in.alloc(N);
@@ -177,33 +300,74 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
   ix.point_in.upload(pb.point_idx, N, s);
   ix.frame_in.upload(pb.frame_idx, N, s);
   ix.obs_in.alloc(N);
-  ix.obs.alloc(N);
-  ix.lens_id.alloc(N);
   ix.lens_id_in.alloc(N);
-  ix.perm.alloc(N);
 
   ix.pt_trk_begin.alloc((size_t)P + 1);
   ix.frm_begin.alloc((size_t)F + 1);
   DevBuf<int32_t> pt_count((size_t)P + 1), fr_count((size_t)F + 1);
   pt_count.zero(s);
   fr_count.zero(s);
-
+  phase("alloc+H2D");
   if (N > 0) {
     k_copy_in<<<grid_for(N), 256, 0, s>>>(ox.p, oy.p, ix.obs_in.p, N);
-    // ---- sort by (point, frame); radix sort is stable, so observations keep their input order inside a track
-    DevBuf<uint64_t> k0(N), k1(N);
-    DevBuf<int32_t> v0(N);
-    k_make_keys<<<grid_for(N), 256, 0, s>>>(ix.point_in.p, ix.frame_in.p, k0.p, v0.p, N);
-    sort_pairs(tmp, k0.p, k1.p, v0.p, ix.perm.p, (size_t)N, s, 32 + bits_for((uint64_t)(P > 0 ? P - 1 : 0)));
-    nl += 3;
-    // ---- gather; lens keys
-    DevBuf<uint64_t> ka(N), kb(N);
-    DevBuf<int32_t> idx(N);
-    k_gather_obs<<<grid_for(N), 256, 0, s>>>(ix.perm.p, ox.p, oy.p, mx.p, my.p, ix.obs.p, ka.p, kb.p, idx.p, N);
     ox.release();
     oy.release();
+    // ---- index validation + "is the input already sorted by (point, frame)?" in one pass ----
+    DevBuf<int> flags2(3);
+    flags2.zero(s);
+    k_check_sorted<<<grid_for(N), 256, 0, s>>>(ix.point_in.p, ix.frame_in.p, flags2.p, flags2.p + 1, P, F, N);
+    // ---- distinct lenses: exact hash table on the (mx, my) bit patterns ----
+    int cap = 1 << 16;
+    while (cap < (1 << 24) && (int64_t)cap < 4 * std::min<int64_t>(N, (int64_t)1 << 22)) cap <<= 1;
+    DevBuf<unsigned long long> keyA(cap), keyB(cap);
+    DevBuf<int32_t> slot_of(N), occ((size_t)cap + 1), oid((size_t)cap + 1);
+    LFBA_CUDA(cudaMemsetAsync(keyA.p, 0xff, (size_t)cap * 8, s));
+    LFBA_CUDA(cudaMemsetAsync(keyB.p, 0xff, (size_t)cap * 8, s));
+    occ.zero(s);
+    k_lens_insert<<<grid_for(N), 256, 0, s>>>(mx.p, my.p, keyA.p, keyB.p, (uint32_t)(cap - 1), slot_of.p, flags2.p + 2, N);
+    k_lens_mark<<<grid_for(cap), 256, 0, s>>>(keyA.p, keyB.p, occ.p, cap);
+    exclusive_sum(tmp, occ.p, oid.p, (size_t)cap + 1, s);
+    int h_flags[3] = {0, 0, 0};
+    int32_t h_nl = 0;
+    flags2.download(h_flags, 3, s);
+    LFBA_CUDA(cudaMemcpyAsync(&h_nl, oid.p + cap, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    LFBA_CUDA(cudaStreamSynchronize(s));
+    if (h_flags[1]) throw CudaError("observation index out of range", LFBA_INVALID_ARGUMENT);
+    if (h_flags[2]) throw CudaError("more than ~4M distinct micro-lens centres: lens table overflow", LFBA_INVALID_ARGUMENT);
+    ix.NL = h_nl;
+    ix.lens_xy.alloc((size_t)2 * std::max(1, ix.NL));
+    k_lens_table<<<grid_for(cap), 256, 0, s>>>(keyA.p, keyB.p, occ.p, oid.p, ix.lens_xy.p, cap);
+    k_lens_assign<<<grid_for(N), 256, 0, s>>>(slot_of.p, oid.p, ix.lens_id_in.p, N);
     mx.release();
     my.release();
+    nl += 8;
+    phase("lenses (hash)");
+    // ---- order by (point, frame) ----
+    DevBuf<uint64_t> k1(N);
+    ix.presorted = h_flags[0] == 0;
+    if (ix.presorted) {
+      // the caller's order is already (point, frame)-major: no sort, no copy — the sorted view IS the input view
+      k_keys_from_sorted_input<<<grid_for(N), 256, 0, s>>>(ix.point_in.p, ix.frame_in.p, k1.p, N);
+      ix.obs_sorted = ix.obs_in.p;
+      ix.lens_id_sorted = ix.lens_id_in.p;
+      nl += 1;
+    } else {
+      // radix sort is stable, so observations keep their input order inside a track
+      DevBuf<uint64_t> k0(N);
+      DevBuf<int32_t> v0(N);
+      DevBuf<int> bad(1);
+      bad.zero(s);
+      ix.perm.alloc(N);
+      ix.obs.alloc(N);
+      ix.lens_id.alloc(N);
+      k_make_keys<<<grid_for(N), 256, 0, s>>>(ix.point_in.p, ix.frame_in.p, k0.p, v0.p, N, P, F, bad.p);
+      sort_pairs(tmp, k0.p, k1.p, v0.p, ix.perm.p, (size_t)N, s, 32 + bits_for((uint64_t)(P > 0 ? P - 1 : 0)));
+      k_gather_sorted<<<grid_for(N), 256, 0, s>>>(ix.perm.p, ix.obs_in.p, ix.lens_id_in.p, ix.obs.p, ix.lens_id.p, N);
+      ix.obs_sorted = ix.obs.p;
+      ix.lens_id_sorted = ix.lens_id.p;
+      nl += 4;
+    }
+    phase("order (point,frame)");
     // ---- tracks
     DevBuf<int32_t> flags(N), tid(N);
     k_head_flags<<<grid_for(N), 256, 0, s>>>(k1.p, flags.p, N);
@@ -221,32 +385,16 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
                                               pt_count.p, fr_count.p, N);
     const int32_t n32 = (int32_t)N;
     LFBA_CUDA(cudaMemcpyAsync(ix.trk_begin.p + T, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    nl += 5;
-    // ---- lenses: lexicographic sort on the (mx, my) bit patterns = two stable 64-bit sorts (LSD order)
-    {
-      DevBuf<uint64_t> ka2(N), kb2(N), kbS(N);
-      DevBuf<int32_t> idx2(N), idxS(N);
-      sort_pairs(tmp, ka.p, ka2.p, idx.p, idx2.p, (size_t)N, s, 64);     // by my
-      k_gather_u64<<<grid_for(N), 256, 0, s>>>(kb.p, idx2.p, kb2.p, N);  // carry mx along
-      sort_pairs(tmp, kb2.p, kbS.p, idx2.p, idxS.p, (size_t)N, s, 64);   // by mx, ties keep the my order
-      k_gather_u64<<<grid_for(N), 256, 0, s>>>(ka.p, idxS.p, ka2.p, N);  // my of the fully sorted sequence
-      k_head_flags2<<<grid_for(N), 256, 0, s>>>(ka2.p, kbS.p, flags.p, N);
-      exclusive_sum(tmp, flags.p, tid.p, (size_t)N, s);
-      int32_t lt = 0, lf = 0;
-      LFBA_CUDA(cudaMemcpyAsync(&lt, tid.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      LFBA_CUDA(cudaMemcpyAsync(&lf, flags.p + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      LFBA_CUDA(cudaStreamSynchronize(s));
-      ix.NL = lt + lf;
-      ix.lens_xy.alloc((size_t)2 * ix.NL);
-      k_fill_lens<<<grid_for(N), 256, 0, s>>>(ka2.p, kbS.p, flags.p, tid.p, idxS.p, ix.lens_id.p, ix.lens_xy.p, N);
-      k_scatter_i32<<<grid_for(N), 256, 0, s>>>(ix.perm.p, ix.lens_id.p, ix.lens_id_in.p, N);
-      nl += 9;
-    }
+    nl += 3;
+    phase("tracks");
   } else {
     ix.T = 0;
     ix.NL = 0;
     ix.trk_begin.alloc(1);
     ix.trk_begin.zero(s);
+    ix.lens_xy.alloc(2);
+    ix.obs_sorted = ix.obs_in.p;
+    ix.lens_id_sorted = ix.lens_id_in.p;
   }
   const int T = ix.T;
   // ---- CSR: point -> tracks (tracks are already grouped by point), frame -> tracks
@@ -264,6 +412,7 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
     sort_pairs(tmp, len.p, keys_out.p, iota.p, ix.eval_order.p, (size_t)T, s, 32, true);
     nl += 6;
   }
+  phase("csr+orders");
   // ---- co-visible frame pairs
   ix.npairs = 0;
   ix.bandwidth = 0;
@@ -313,6 +462,7 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
     }
   }
   LFBA_CUDA(cudaStreamSynchronize(s));
+  phase("pairs");
   if (launches) *launches += nl;
 }
 

@@ -32,27 +32,38 @@ struct CudaError : std::runtime_error {
                       e_ == cudaErrorMemoryAllocation ? LFBA_OUT_OF_MEMORY : LFBA_CUDA_ERROR);       \
   } while (0)
 
+// Stream-ordered allocations from the device's default memory pool (cudaMallocAsync): with the pool's release
+// threshold raised (Solver::create) the memory of a finished solve is reused by the next one, so repeated
+// drop-in calls do not pay cudaMalloc/cudaFree of several GB each time. Every buffer of a solver is allocated,
+// used and freed on that solver's one stream.
+inline cudaStream_t& alloc_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t st = nullptr;
   DevBuf() {}
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) LFBA_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    st = alloc_stream();
+    if (count) LFBA_CUDA(cudaMallocAsync(&p, count * sizeof(T), st));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
     p = nullptr;
     n = 0;
   }
@@ -70,8 +81,11 @@ struct ProblemIndex {
   int64_t N = 0;
   int T = 0, P = 0, F = 0, NL = 0, npairs = 0, bandwidth = 0;
   int64_t n_pair_items = 0;
-  DevBuf<double2> obs;        // sorted by (point, frame)
+  DevBuf<double2> obs;        // sorted by (point, frame)   (empty when the input already was: see obs_sorted)
   DevBuf<int32_t> lens_id;    // sorted order
+  const double2* obs_sorted = nullptr;    // -> obs or obs_in
+  const int32_t* lens_id_sorted = nullptr;  // -> lens_id or lens_id_in
+  bool presorted = false;
   DevBuf<int32_t> perm;       // sorted position -> input position
   DevBuf<int32_t> trk_point, trk_frame, trk_begin, pt_trk_begin, frm_begin, frm_trk;
   DevBuf<int32_t> pair_begin, pair_f1, pair_f2, pair_t1, pair_t2;

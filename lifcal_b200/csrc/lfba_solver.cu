@@ -77,7 +77,20 @@ __global__ void k_point_flags(const int32_t* pt_trk_begin, const int32_t* pt_cou
 }
 
 // ------------------------------------------------------------------------------------------------
+struct StreamHolder {  // declared first in Solver => destroyed last, after every stream-ordered free has been queued
+  cudaStream_t s = nullptr;
+  int device = 0;
+  ~StreamHolder() {
+    if (s) {
+      cudaSetDevice(device);
+      cudaStreamSynchronize(s);
+      cudaStreamDestroy(s);
+    }
+  }
+};
+
 struct Solver {
+  StreamHolder sh;
   lfba_options opt;
   uint32_t config = 0;
   int calib_type = 0;
@@ -102,6 +115,7 @@ struct Solver {
   DevBuf<double> camera[2], views[2], points[2], lens, frames[2], rec[2], camsum[2], pdata, pscale, vw;
   DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one NCCL all-reduce)
   DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step;
+  DevBuf<unsigned long long> lens_dev;
   DevBuf<LmState> st;
   DevBuf<lfba_iteration> log;
   size_t S_len = 0, red_len = 0;
@@ -116,7 +130,7 @@ struct Solver {
       for (auto& e : ev) cudaEventDestroy(e);
     if (h_done) cudaFreeHost(h_done);
     if (comm) Nccl::get().CommDestroy(comm);
-    if (stream) cudaStreamDestroy(stream);
+    alloc_stream() = stream;  // member buffers are freed (stream-ordered) right after this body
   }
 
   void allreduce(void* buf, size_t count, int dtype, int op) {
@@ -127,6 +141,15 @@ struct Solver {
 
   void create(const lfba_problem& pb, const lfba_options& o, const lfba_comm* cm) {
     const double t0 = now_s();
+    const bool dbg = std::getenv("LFBA_DEBUG") != nullptr;
+    double tp = t0;
+    auto phase = [&](const char* name) {
+      if (!dbg) return;
+      cudaStreamSynchronize(stream);
+      const double t = now_s();
+      std::fprintf(stderr, "[lfba dbg] setup %-28s %8.2f ms\n", name, 1e3 * (t - tp));
+      tp = t;
+    };
     opt = o;
     config = pb.config;
     calib_type = pb.calib_type;
@@ -138,10 +161,6 @@ struct Solver {
       throw CudaError("empty problem: need n_frames > 0 and n_points > 0", LFBA_INVALID_ARGUMENT);
     if (pb.n_obs > 0 && (!pb.obs_x || !pb.obs_y || !pb.ml_x || !pb.ml_y || !pb.point_idx || !pb.frame_idx))
       throw CudaError("null observation array", LFBA_INVALID_ARGUMENT);
-    for (int64_t i = 0; i < pb.n_obs; ++i)
-      if (pb.point_idx[i] < 0 || pb.point_idx[i] >= pb.n_points || pb.frame_idx[i] < 0 ||
-          pb.frame_idx[i] >= pb.n_frames)
-        throw CudaError("observation index out of range", LFBA_INVALID_ARGUMENT);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
       throw CudaError("no CUDA device: the LF-BA path has no CPU fallback", LFBA_NO_DEVICE);
@@ -151,6 +170,16 @@ struct Solver {
     LFBA_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) throw CudaError("device is not sm_100-class: kernels are built for sm_100a only", LFBA_NO_DEVICE);
     LFBA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    sh.s = stream;
+    sh.device = device;
+    alloc_stream() = stream;
+    {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;  // keep freed memory in the pool for the next solve
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    }
     LFBA_CUDA(cudaMallocHost(&h_done, 4 * sizeof(int)));
     if (cm && cm->nranks > 1) {
       Nccl& n = Nccl::get();
@@ -163,7 +192,19 @@ struct Solver {
       if (rc != 0) throw CudaError(std::string("ncclCommInitRank: ") + n.GetErrorString(rc), LFBA_NCCL_ERROR);
     }
 
+    auto poolstat = [&](const char* w) {
+      if (!dbg) return;
+      cudaMemPool_t pool;
+      unsigned long long res = 0, used = 0;
+      cudaDeviceGetDefaultMemPool(&pool, device);
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res);
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+      std::fprintf(stderr, "[lfba dbg] pool %-10s reserved %.2f GB used %.2f GB\n", w, res / 1e9, used / 1e9);
+    };
+    poolstat("start");
+    phase("validate+device+stream");
     build_index(pb, ix, stream, &launches);
+    phase("build_index");
     const int P = ix.P, F = ix.F, T = ix.T;
     const int nrad = (int)(config & 3u), tang = (config & LFBA_CFG_TANGENTIAL) ? 1 : 0;
     const int NC = 5 + nrad + 2 * tang;
@@ -221,6 +262,7 @@ struct Solver {
     const int bw = h_fa[F];
     band_frames = bw;
 
+    phase("flags+global counts");
     // ---- reduced system layout [poses | coupled points | camera | rhs] and its skyline profile ----
     std::memset(&d, 0, sizeof(d));
     d.np6 = rposes ? 6 * F : 0;
@@ -259,6 +301,7 @@ struct Solver {
     tile_first.alloc(n_tiles);
     tile_first.upload(h_tf.data(), n_tiles, stream);
 
+    phase("layout");
     // ---- buffers ----
     red_len = S_len + 3 * (size_t)n + SS_COUNT + (size_t)nranks;
     redbuf.alloc(red_len);
@@ -283,6 +326,8 @@ struct Solver {
     vw.alloc((size_t)std::max(1, T) * kVWStride);
     st.alloc(1);
     log.alloc(kMaxLog);
+    lens_dev.alloc(1);
+    lens_dev.zero(stream);
 
     // ---- launch geometry ----
     const int sms = prop.multiProcessorCount;
@@ -318,7 +363,7 @@ struct Solver {
     d.opt.rmin = o.min_trust_region_radius; d.opt.min_rel_dec = o.min_relative_decrease;
     d.opt.min_diag = o.min_lm_diagonal; d.opt.max_diag = o.max_lm_diagonal;
     d.opt.max_invalid = o.max_num_consecutive_invalid_steps; d.opt.loss_a = o.loss_scale;
-    d.obs = ix.obs.p; d.lens_id = ix.lens_id.p; d.trk_point = ix.trk_point.p; d.trk_frame = ix.trk_frame.p;
+    d.obs = ix.obs_sorted; d.lens_id = ix.lens_id_sorted; d.trk_point = ix.trk_point.p; d.trk_frame = ix.trk_frame.p;
     d.trk_begin = ix.trk_begin.p; d.pt_trk_begin = ix.pt_trk_begin.p; d.frm_begin = ix.frm_begin.p;
     d.frm_trk = ix.frm_trk.p; d.pair_begin = ix.pair_begin.p; d.pair_f1 = ix.pair_f1.p; d.pair_f2 = ix.pair_f2.p;
     d.pair_t1 = ix.pair_t1.p; d.pair_t2 = ix.pair_t2.p; d.npairs = ix.npairs; d.eval_order = ix.eval_order.p;
@@ -332,7 +377,9 @@ struct Solver {
       d.camera[b] = camera[b].p; d.views[b] = views[b].p; d.points[b] = points[b].p;
       d.frames[b] = frames[b].p; d.rec[b] = rec[b].p; d.camsum[b] = camsum[b].p;
     }
-    d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p;
+    d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.lens_dev = lens_dev.p;
+    // measured on B200: the implicit form (fewer gathered bytes, ~75 more FP64 ops) is slower than the table: opt-in only
+    d.implicit_tol = std::getenv("LFBA_IMPLICIT_TOL") ? std::atof(std::getenv("LFBA_IMPLICIT_TOL")) : -1.0; d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p;
     d.S = redbuf.p; d.row_off = row_off.p; d.row_c0 = row_c0.p;
     d.g = redbuf.p + S_len; d.gfull = d.g + n; d.hdiag = d.gfull + n; d.sys_scalars = d.hdiag + n;
     d.rscale = rscale.p; d.rdamp = rdamp.p; d.y = y.p; d.eval_scalars = eval_scalars.p;
@@ -343,11 +390,14 @@ struct Solver {
     prepare_device_kernels();
     prepare_eval_kernels();
     LFBA_CUDA(cudaStreamSynchronize(stream));
+    phase("buffers");
+    poolstat("end");
     setup_time = now_s() - t0;
   }
 
   void set_parameters(const double* cam, const double* vw_, const double* pts) {
     LFBA_CUDA(cudaSetDevice(device));
+    alloc_stream() = stream;
     // the accepted-state slot is 0 until the first accept flips it; the initial point enters as candidate (slot 1)
     camera0.alloc(17);
     views0.alloc((size_t)6 * ix.F);
@@ -396,6 +446,7 @@ struct Solver {
     init.decrease_factor = 2.0;
     if (!camera0.p) throw CudaError("lfba_solver_run before lfba_solver_set_parameters", LFBA_INVALID_ARGUMENT);
     reset_parameters();  // every run starts from the parameters last given by the caller
+    lens_dev.zero(stream);
     LFBA_CUDA(cudaMemcpyAsync(st.p, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
     if (calib_type == LFBA_RECALIBRATION) {
       // IterationZero of a bounds-constrained problem projects the start point into the box
@@ -471,6 +522,11 @@ struct Solver {
                      hs.x_cost, hs.radius, hs.mcc_red, hs.step2_red, hs.norm2_red, hp[0], hp[1], hp[2]);
         double ymax = 0;
         for (int j = 0; j < d.n; ++j) ymax = std::max(ymax, std::fabs(hy[j]));
+        unsigned long long hdev = 0;
+        LFBA_CUDA(cudaMemcpy(&hdev, lens_dev.p, 8, cudaMemcpyDeviceToHost));
+        double ddev;
+        std::memcpy(&ddev, &hdev, 8);
+        std::fprintf(stderr, "[lfba dbg]   lens implicit-vs-exact deviation = %.3e\n", ddev);
         std::fprintf(stderr, "[lfba dbg]   |y|max=%.6e y[0..5]=%.4e %.4e %.4e %.4e %.4e %.4e\n", ymax, hy[0], hy[1], hy[2],
                      d.n > 3 ? hy[3] : 0.0, d.n > 4 ? hy[4] : 0.0, d.n > 5 ? hy[5] : 0.0);
       }
@@ -657,6 +713,7 @@ int lfba_solver_time_eval(lfba_solver* h, int reps, int materialize, double* mea
   return guarded([&] {
     Solver& s = h->s;
     LFBA_CUDA(cudaSetDevice(s.device));
+    alloc_stream() = s.stream;
     // evaluate at the accepted parameters: present them as the candidate of a fresh state
     LmState init;
     std::memset(&init, 0, sizeof(init));
