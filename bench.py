@@ -218,7 +218,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -248,11 +248,12 @@ def main():
     n_local = pa.n_obs
     opt = api.default_options(device=local_rank)
 
-    uid = None
+    comm = None
     if world > 1:
         uid = broadcast_unique_id(api.comm_unique_id() if rank == 0 else None)
+        comm = api.Communicator(rank, world, uid)  # one NCCL communicator per rank for the whole run
     t_setup = time.perf_counter()
-    ds = api.DeviceSolver(pa, opt, rank=rank, nranks=world, unique_id=uid)
+    ds = api.DeviceSolver(pa, opt, communicator=comm)
     ds.set_parameters(sc.camera_init, sc.views_init, sc.points_init)
     t_setup = time.perf_counter() - t_setup
 
@@ -333,8 +334,7 @@ def main():
             for k in range(1 + min(2, args.steps)):
                 barrier()
                 t1 = time.perf_counter()
-                d2 = api.DeviceSolver(ppa, o2, rank=rank, nranks=world, unique_id=broadcast_unique_id(
-                    api.comm_unique_id() if rank == 0 else None))
+                d2 = api.DeviceSolver(ppa, o2, communicator=comm)
                 d2.set_parameters(sc.camera_init, sc.views_init, sc.points_init)
                 s2 = d2.run()
                 d2.get_parameters()
@@ -352,8 +352,11 @@ def main():
                "d2h_bytes_per_step": int(8 * (17 + 6 * F + 3 * P)), "s_per_solve": tot / len(ts),
                "api": "lfba_solve (C ABI, pinned host buffers)" if world == 1 else "lfba_solver_create+run per rank"}
 
+    if comm is not None:
+        comm.close()
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -367,8 +370,9 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in run_cpu_baseline(args.workload, small=False).items()
                                 if k in ("value", "unit", "cores", "kind", "sample", "lm_iters_per_s")}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -196,6 +196,7 @@ typedef struct lfba_comm {
   int32_t rank;
   int32_t nranks;
   char nccl_unique_id[128];
+  void* handle; /* optional: a communicator made by lfba_comm_create() (reused across solves); NULL = create one */
 } lfba_comm;
 
 typedef struct lfba_solver lfba_solver; /* opaque, device-resident problem */
@@ -228,6 +229,10 @@ int lfba_eval(const lfba_problem* problem, const lfba_options* options, const do
 
 /* ---- device-resident session API (what lfba_solve / lfba_eval are built from) ---- */
 int lfba_comm_unique_id(char out[128]);
+/* Persistent NCCL communicator for this rank (collective: every rank calls it). Pass it in lfba_comm.handle so that
+ * repeated lfba_solver_create() calls do not pay ncclCommInitRank each time. The device must be current. */
+int lfba_comm_create(const lfba_comm* comm, void** handle);
+void lfba_comm_destroy(void* handle);
 /* comm == NULL: single GPU (options->device). Uploads and indexes the problem (sort by point/frame,
  * track table, lens table). */
 int lfba_solver_create(const lfba_problem* problem, const lfba_options* options, const lfba_comm* comm,

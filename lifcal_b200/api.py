@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 
 _EXPORTS = ["lfba_version", "lfba_last_error", "lfba_status_string", "lfba_options_init", "lfba_device_count",
-            "lfba_solve", "lfba_eval", "lfba_comm_unique_id", "lfba_solver_create", "lfba_solver_set_parameters",
+            "lfba_solve", "lfba_eval", "lfba_comm_unique_id", "lfba_comm_create", "lfba_comm_destroy", "lfba_solver_create", "lfba_solver_set_parameters",
             "lfba_solver_get_parameters", "lfba_solver_run", "lfba_solver_time_eval", "lfba_measure_fp64_peak",
             "lfba_solver_destroy"]
 
@@ -49,6 +49,8 @@ def load():
     L.lfba_eval.argtypes = [C.POINTER(capi.Problem), C.POINTER(capi.Options), dp, dp, dp, dp, dp, dp, dp, dp,
                             C.POINTER(capi.ReprojStats), C.c_double]
     L.lfba_comm_unique_id.argtypes = [C.c_char_p]
+    L.lfba_comm_create.argtypes = [C.POINTER(capi.Comm), C.POINTER(C.c_void_p)]
+    L.lfba_comm_destroy.argtypes = [C.c_void_p]
     L.lfba_solver_create.argtypes = [C.POINTER(capi.Problem), C.POINTER(capi.Options), C.POINTER(capi.Comm),
                                      C.POINTER(C.c_void_p)]
     L.lfba_solver_set_parameters.argtypes = [C.c_void_p, dp, dp, dp]
@@ -138,18 +140,41 @@ def measure_fp64_peak(device: int = -1) -> float:
     return v.value
 
 
+class Communicator:
+    """Persistent NCCL communicator of this rank (lfba_comm_create); collective over all ranks."""
+
+    def __init__(self, rank: int, nranks: int, unique_id: bytes):
+        self._L = load()
+        self.rank, self.nranks = rank, nranks
+        c = capi.Comm()
+        c.rank, c.nranks = rank, nranks
+        C.memmove(C.addressof(c) + capi.Comm.nccl_unique_id.offset, unique_id, 128)
+        self._h = C.c_void_p()
+        _check(self._L.lfba_comm_create(C.byref(c), C.byref(self._h)), "lfba_comm_create")
+
+    def close(self):
+        if self._h:
+            self._L.lfba_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 class DeviceSolver:
     """Device-resident session (lfba_solver_*): upload/index once, then set parameters / run repeatedly."""
 
     def __init__(self, pa: capi.ProblemArrays, options: capi.Options | None = None, rank: int = 0, nranks: int = 1,
-                 unique_id: bytes | None = None):
+                 unique_id: bytes | None = None, communicator: "Communicator | None" = None):
         self._L = load()
         self.pa = pa
         self.options = options if options is not None else default_options()
         self._h = C.c_void_p()
         p = pa.as_struct()
         comm = None
-        if nranks > 1:
+        if communicator is not None:
+            c = capi.Comm()
+            c.rank, c.nranks = communicator.rank, communicator.nranks
+            c.handle = communicator._h
+            comm = C.byref(c)
+        elif nranks > 1:
             c = capi.Comm()
             c.rank, c.nranks = rank, nranks
             C.memmove(C.addressof(c) + capi.Comm.nccl_unique_id.offset, unique_id, 128)

@@ -98,7 +98,7 @@ class ReprojStats(C.Structure):
 
 
 class Comm(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_char * 128)]
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_char * 128), ("handle", C.c_void_p)]
 
 
 class SceneSpec(C.Structure):

@@ -97,6 +97,7 @@ struct Solver {
   int device = 0;
   cudaStream_t stream = nullptr;
   Nccl::comm_t comm = nullptr;
+  bool own_comm = false;
   int rank = 0, nranks = 1;
   ProblemIndex ix;
   Dev d;
@@ -129,7 +130,7 @@ struct Solver {
     if (ev_made)
       for (auto& e : ev) cudaEventDestroy(e);
     if (h_done) cudaFreeHost(h_done);
-    if (comm) Nccl::get().CommDestroy(comm);
+    if (comm && own_comm) Nccl::get().CommDestroy(comm);
     alloc_stream() = stream;  // member buffers are freed (stream-ordered) right after this body
   }
 
@@ -186,10 +187,15 @@ struct Solver {
       if (!n.ok) throw CudaError("libnccl.so.2 not found", LFBA_NCCL_ERROR);
       rank = cm->rank;
       nranks = cm->nranks;
-      Nccl::UniqueId id;
-      std::memcpy(id.internal, cm->nccl_unique_id, 128);
-      const int rc = n.CommInitRank(&comm, nranks, id, rank);
-      if (rc != 0) throw CudaError(std::string("ncclCommInitRank: ") + n.GetErrorString(rc), LFBA_NCCL_ERROR);
+      if (cm->handle) {
+        comm = (Nccl::comm_t)cm->handle;
+      } else {
+        Nccl::UniqueId id;
+        std::memcpy(id.internal, cm->nccl_unique_id, 128);
+        const int rc = n.CommInitRank(&comm, nranks, id, rank);
+        if (rc != 0) throw CudaError(std::string("ncclCommInitRank: ") + n.GetErrorString(rc), LFBA_NCCL_ERROR);
+        own_comm = true;
+      }
     }
 
     auto poolstat = [&](const char* w) {
@@ -673,6 +679,28 @@ int lfba_comm_unique_id(char out[128]) {
   return LFBA_OK;
 }
 
+int lfba_comm_create(const lfba_comm* cm, void** handle) {
+  if (!cm || !handle || cm->nranks < 1) return LFBA_INVALID_ARGUMENT;
+  Nccl& n = Nccl::get();
+  if (!n.ok) {
+    set_error("libnccl.so.2 not found");
+    return LFBA_NCCL_ERROR;
+  }
+  Nccl::UniqueId id;
+  std::memcpy(id.internal, cm->nccl_unique_id, 128);
+  Nccl::comm_t c = nullptr;
+  const int rc = n.CommInitRank(&c, cm->nranks, id, cm->rank);
+  if (rc != 0) {
+    set_error(std::string("ncclCommInitRank: ") + n.GetErrorString(rc));
+    return LFBA_NCCL_ERROR;
+  }
+  *handle = (void*)c;
+  return LFBA_OK;
+}
+void lfba_comm_destroy(void* handle) {
+  if (handle) Nccl::get().CommDestroy((Nccl::comm_t)handle);
+}
+
 int lfba_solver_create(const lfba_problem* pb, const lfba_options* opt, const lfba_comm* comm, lfba_solver** out) {
   if (!pb || !opt || !out) return LFBA_INVALID_ARGUMENT;
   *out = nullptr;
@@ -864,6 +892,7 @@ int lfba_solve(const lfba_problem* pb, const lfba_options* opt_in, double* cam, 
   }
   lfba_comm base;
   std::memset(&base, 0, sizeof(base));
+  base.handle = nullptr;
   base.nranks = G;
   int rc0 = lfba_comm_unique_id(base.nccl_unique_id);
   if (rc0 != LFBA_OK) return rc0;

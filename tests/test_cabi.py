@@ -44,7 +44,7 @@ def test_version_and_reference_defaults(built):
 def test_struct_layouts_match_header(built):
     # sizes the C side was compiled with (guards the ctypes mirrors in lifcal_b200/capi.py)
     assert C.sizeof(capi.Iteration) == 4 * 4 + 9 * 8
-    assert C.sizeof(capi.Comm) == 8 + 128
+    assert C.sizeof(capi.Comm) == 8 + 128 + 8
     assert C.sizeof(capi.ReprojStats) == 6 * 8
     assert capi.Problem.obs_x.offset == 48 and capi.Problem.n_constraints.offset == 96
 

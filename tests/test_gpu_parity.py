@@ -61,7 +61,12 @@ def _assert_solution_parity(gs, gp, os_, op, scene, spread=None):
     assert abs(gs["final_cost"] - os_["final_cost"]) <= REL * os_["final_cost"]
     sp = spread if spread is not None else [np.zeros_like(ocam), np.zeros_like(ovw), np.zeros_like(opt_)]
     live = np.abs(ocam) > 0
-    tol_cam = np.maximum(REL * np.abs(ocam), 4.0 * sp[0])
+    # a camera parameter may also differ by what moves no reprojection by more than 1e-9 px (a near-zero distortion
+    # coefficient has no meaningful RELATIVE accuracy): |dp_j| <= 1e-9 px / rms_i |d r_i / d p_j|
+    jc = ob.evaluate(scene.problem if hasattr(scene, "problem") else scene, ocam, ovw, opt_)["jac_camera"]
+    col_rms = np.sqrt(np.mean(jc.reshape(-1, 17) ** 2, axis=0))
+    tol_px = np.where(col_rms > 0, 1e-9 / np.maximum(col_rms, 1e-300), 0.0)
+    tol_cam = np.maximum(np.maximum(REL * np.abs(ocam), 4.0 * sp[0]), tol_px)
     worst = np.max(np.abs(cam[live] - ocam[live]) / tol_cam[live])
     assert worst <= 1.0, ("camera", worst, cam[:9], ocam[:9])
     assert np.all(cam[~live] == 0)
@@ -163,7 +168,7 @@ def test_edge_cases_unobserved_points_and_frames(gpu):
     pa = sc.problem.subset(keep)
     cam, vw, pt, s = api.solve(pa, sc.camera_init, sc.views_init, sc.points_init)
     spread, (ocam, ovw, opt_, os_) = _oracle_spread(pa, (sc.camera_init, sc.views_init, sc.points_init))
-    _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread)
+    _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), pa, spread)
     untouched = np.arange(80) % 7 == 3
     assert np.array_equal(pt.reshape(-1, 3)[untouched], sc.points_init.reshape(-1, 3)[untouched])
     assert np.array_equal(vw[12:18], sc.views_init[12:18])
