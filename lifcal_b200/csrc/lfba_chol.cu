@@ -11,6 +11,8 @@
 // diagonal tile (recomputed by every CTA of the column: no inter-CTA dependency inside a launch), TRSM.
 // tcgen05 has no FP64 kind and the tiles are tiny, so this is plain DFMA work; the chain of n pivots is the
 // latency that matters, not the flops.
+#include <cstdio>
+
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
 
@@ -266,6 +268,13 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
   }
   __syncthreads();
 
+#ifdef LFBA_CHOL_PROF
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#define CHOL_TICK(i) { const long long tn = clock64(); pc[i] += tn - tlast; tlast = tn; }
+#else
+#define CHOL_TICK(i)
+#endif
   const int tx = tid & 15, ty = tid >> 4;
   for (int k = 0; k < F; ++k) {
     const int s = bslot(k, bw1);
@@ -283,6 +292,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
       }
       if (tid < 6 * nb) pb = border_fetch(fn, tid, plb);
     }
+    CHOL_TICK(0)
     // ---- 6x6 Cholesky of the pivot block: one thread, registers only (the latency chain of the whole solve) ----
     if (tid == 0) {
       double a[21];
@@ -313,11 +323,13 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
 #pragma unroll
         for (int j = 0; j <= i; ++j) A[(s + i) * LDW + s + j] = a[i * (i + 1) / 2 + j];
     }
+    CHOL_TICK(1)
     const int nbf = min(bw, F - 1 - k);
     const int mrows = 6 * nbf + nb;
     for (int i = tid; i < mrows; i += nt)
       lrow[i] = i < 6 * nbf ? bslot(k + 1 + i / 6, bw1) + i % 6 : NBAND + (i - 6 * nbf);
     __syncthreads();
+    CHOL_TICK(2)
     // ---- panel: rows of the frames k+1..k+bw and the border; X = A L^-T ----
     for (int i = tid; i < mrows; i += nt) {
       const int lr = lrow[i];
@@ -349,6 +361,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
       d.S[sky.row(k, i) + (6 * k + j - sky.c0(k))] = A[(s + i) * LDW + s + j];
     }
     __syncthreads();
+    CHOL_TICK(3)
     // ---- trailing update of the window: A[i][j] -= X_i . X_j, i >= j in global order (16 x 16 thread grid) ----
     for (int i = ty; i < mrows; i += 16) {
       const int li = lrow[i];
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
       }
     }
     __syncthreads();
+    CHOL_TICK(4)
     // ---- slide the window: frame k+bw+1 takes the slot of frame k ----
     if (fn < F) {
 #pragma unroll
@@ -371,6 +385,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
       __syncthreads();
     }
   }
+  CHOL_TICK(5)
   // ---- dense Cholesky of the border block (coupled points + camera); the rhs row is not a pivot ----
   for (int c = 0; c < npiv; ++c) {
     __syncthreads();
@@ -398,6 +413,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
   }
   if (tid == 0 && s_fail) st->solve_ok = 0;
   if (s_fail) return;
+  CHOL_TICK(6)
   // ---- backward substitution L^T y = z, z = the factorised rhs row ----
   if (tid == 0) {
     for (int b = npiv - 1; b >= 0; --b) {
@@ -465,6 +481,10 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
     }
     __syncthreads();
   }
+  CHOL_TICK(7)
+#ifdef LFBA_CHOL_PROF
+  if (tid == 0) printf("chol phases (cycles): top/prefetch %lld chol6 %lld lrow+sync %lld panel %lld trailing %lld slide %lld | border+backward %lld\n", pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[7]);
+#endif
   for (int j = tid; j < d.n; j += nt) d.y[j] = ys[j];
 }
 
