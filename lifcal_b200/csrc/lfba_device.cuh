@@ -104,6 +104,11 @@ struct Dev {
   const int32_t* pair_t2;
   int npairs;
   const int32_t* eval_order;  // track processing order of the evaluation kernel (length-sorted)
+  // packed evaluation stream (lfba_setup.cuh, build_stream): rows of 32 entries in the order k_eval_rows consumes them
+  const double2* s_obs;       // [n_rows * 32]
+  const int32_t* s_lid;       // [n_rows * 32], -1 = padding
+  const int32_t* step_base;   // [n_rounds + 1]
+  int n_rounds, n_rows, stream_L;
   // point / frame flags
   const int32_t* pt_coupled;  // [P] index among coupled points or -1
   const int32_t* coupled_pts; // [Pc]

@@ -7,6 +7,7 @@
 // lfba_eval(): calcReprojectionError (src/CameraCalibration.cpp:1026-1103), parity tests, and the
 // "M residual+Jacobian evals/s" metric with the Jacobian written to HBM.
 // Algorithmic HBM bytes per observation: read 28 (double2 + 3 x int32), write 16 + 16*(17 + 6 + 3) = 432.
+// HBM-bound: the outputs are staged per CTA in shared memory and streamed out coalesced (see stream_out).
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
 
@@ -32,40 +33,74 @@ __global__ void k_tables_for(Dev d, int which) {
   if (i < d.F) frame_entry(d.views[which] + 6 * i, d.frames[which] + (size_t)i * kFrameStride);
 }
 
+// Output staging: every thread produces 54 doubles (r 2, J_camera 34, J_view 12, J_point 6) for ITS observation, i.e.
+// at a 272 / 96 / 48 / 16-byte stride in HBM. Written directly that is one 32-byte sector per 8-byte store (measured:
+// 25% of the HBM roofline). The CTA therefore stages its 128 observations in shared memory (row stride padded to an
+// odd number of doubles: conflict-free for the strided writes AND for the linear read-back) and then streams each
+// output array out with fully coalesced 8-byte stores: the 128 rows of a CTA are one contiguous range of each array.
+constexpr int kEvalBlock = 128;
+constexpr int kStrideC = 35, kStrideV = 13, kStrideP = 7, kStrideR = 3;  // padded rows of 34 / 12 / 6 / 2 doubles
+constexpr int kEvalSmemDoubles = kEvalBlock * (kStrideC + kStrideV + kStrideP + kStrideR);
+
+template <int W, int STRIDE>
+__device__ __forceinline__ void stream_out(const double* __restrict__ sm, double* __restrict__ dst, int rows) {
+  // dst[row * W + c] = sm[row * STRIDE + c] for the CTA's `rows` observations, as 16-byte streaming stores: consecutive
+  // threads -> consecutive double2 (512 B per warp instruction). W is even, so a pair never straddles two rows; dst is
+  // 16-byte aligned because a CTA starts at a multiple of 128 observations.
+  static_assert(W % 2 == 0, "row width must be even");
+  const int total2 = rows * (W / 2);
+  double2* __restrict__ dst2 = reinterpret_cast<double2*>(dst);
+  for (int j = threadIdx.x; j < total2; j += kEvalBlock) {
+    const int row = j / (W / 2), c = 2 * (j - row * (W / 2));
+    const double* p = sm + row * STRIDE + c;
+    __stcs(dst2 + j, make_double2(p[0], p[1]));  // written once, never re-read by this kernel
+  }
+}
+
 template <int NC, int NRAD>
-__global__ void __launch_bounds__(128) k_eval_only(Dev d, EvalIn in, EvalOut out, int which) {
+__global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, EvalOut out, int which) {
   __shared__ CamModel cm;
   __shared__ double sred[4 * 6];
+  extern __shared__ double stage[];
+  double* sC = stage;
+  double* sV = sC + kEvalBlock * kStrideC;
+  double* sP = sV + kEvalBlock * kStrideV;
+  double* sR = sP + kEvalBlock * kStrideP;
   if (threadIdx.x == 0) cam_model_init(cm, d.camera[which], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
   __syncthreads();
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t i0 = blockIdx.x * (int64_t)kEvalBlock;
+  const int64_t i = i0 + threadIdx.x;
   double ex2 = 0.0, ey2 = 0.0, mx = 0.0, my = 0.0, inl = 0.0, cost = 0.0;
   if (i < d.N) {
-    const double2 o = in.obs[i];
-    const int p = in.point_idx[i], f = in.frame_idx[i];
+    const double2 o = __ldcs(in.obs + i);
+    const int p = __ldcs(in.point_idx + i), f = __ldcs(in.frame_idx + i);
     const double* fe = d.frames[which] + (size_t)f * kFrameStride;
     const double* X = d.points[which] + 3 * (size_t)p;
-    const double* le = d.lens + (size_t)in.lens_id[i] * kLensStride;
+    const double2* le = reinterpret_cast<const double2*>(d.lens + (size_t)__ldcs(in.lens_id + i) * kLensStride);
     double e[kLensStride];
 #pragma unroll
-    for (int k = 0; k < kLensStride; ++k) e[k] = le[k];
+    for (int k = 0; k < kLensStride / 2; ++k) {
+      const double2 v2 = __ldg(le + k);
+      e[2 * k] = v2.x;
+      e[2 * k + 1] = v2.y;
+    }
     double Pc[3];
     track_point(fe, X, Pc);
     TrackCtx tc;
     track_setup(cm, Pc, tc);
     double r[2], G[6], J[2 * NC];
     obs_eval<NC, NRAD>(cm, tc, e, o.x, o.y, r, G, J);
-    out.residuals[2 * i] = r[0];
-    out.residuals[2 * i + 1] = r[1];
+    sR[threadIdx.x * kStrideR] = r[0];
+    sR[threadIdx.x * kStrideR + 1] = r[1];
     if (out.jac_camera) {
-      double* jc = out.jac_camera + 34 * i;
+      double* jc = sC + threadIdx.x * kStrideC;
 #pragma unroll
       for (int row = 0; row < 2; ++row)
 #pragma unroll
         for (int c = 0; c < 17; ++c) jc[17 * row + c] = c < NC ? J[NC * row + c] : 0.0;
     }
     if (out.jac_view) {
-      double* jv = out.jac_view + 12 * i;
+      double* jv = sV + threadIdx.x * kStrideV;
       double m[9];
       mat3_vec(fe + 9, X, m + 0);
       mat3_vec(fe + 18, X, m + 3);
@@ -80,7 +115,7 @@ __global__ void __launch_bounds__(128) k_eval_only(Dev d, EvalIn in, EvalOut out
         }
     }
     if (out.jac_point) {
-      double* jp = out.jac_point + 6 * i;
+      double* jp = sP + threadIdx.x * kStrideP;
 #pragma unroll
       for (int row = 0; row < 2; ++row)
 #pragma unroll
@@ -111,7 +146,12 @@ __global__ void __launch_bounds__(128) k_eval_only(Dev d, EvalIn in, EvalOut out
     }
     if (lane == 0) sred[warp * 6 + v] = x;
   }
-  __syncthreads();
+  __syncthreads();  // also orders the staging writes before the read-back
+  const int rows = (int)(d.N - i0 < (int64_t)kEvalBlock ? d.N - i0 : (int64_t)kEvalBlock);
+  stream_out<2, kStrideR>(sR, out.residuals + 2 * i0, rows);
+  if (out.jac_camera) stream_out<34, kStrideC>(sC, out.jac_camera + 34 * i0, rows);
+  if (out.jac_view) stream_out<12, kStrideV>(sV, out.jac_view + 12 * i0, rows);
+  if (out.jac_point) stream_out<6, kStrideP>(sP, out.jac_point + 6 * i0, rows);
   if (threadIdx.x < 6 && out.stats) {
     const int v = threadIdx.x;
     double x = sred[v];
@@ -128,15 +168,27 @@ void launch_tables_for(const Dev& d, int which, cudaStream_t s) {
 
 void launch_eval_only(const Dev& d, const EvalIn& in, const EvalOut& out, int which, cudaStream_t s) {
   if (d.N == 0) return;
-  const unsigned grid = (unsigned)((d.N + 127) / 128);
+  const unsigned grid = (unsigned)((d.N + kEvalBlock - 1) / kEvalBlock);
+  const size_t smem = (size_t)kEvalSmemDoubles * sizeof(double);
+  static const bool prepared = [] {
+    const int b = kEvalSmemDoubles * (int)sizeof(double);
+    cudaFuncSetAttribute(k_eval_only<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    cudaFuncSetAttribute(k_eval_only<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    cudaFuncSetAttribute(k_eval_only<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    cudaFuncSetAttribute(k_eval_only<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    cudaFuncSetAttribute(k_eval_only<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    cudaFuncSetAttribute(k_eval_only<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    return true;
+  }();
+  (void)prepared;
   const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
   switch (nrad * 2 + tang) {
-    case 0: k_eval_only<5, 0><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    case 1: k_eval_only<7, 0><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    case 2: k_eval_only<6, 1><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    case 3: k_eval_only<8, 1><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    case 4: k_eval_only<7, 2><<<grid, 128, 0, s>>>(d, in, out, which); break;
-    default: k_eval_only<9, 2><<<grid, 128, 0, s>>>(d, in, out, which); break;
+    case 0: k_eval_only<5, 0><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
+    case 1: k_eval_only<7, 0><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
+    case 2: k_eval_only<6, 1><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
+    case 3: k_eval_only<8, 1><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
+    case 4: k_eval_only<7, 2><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
+    default: k_eval_only<9, 2><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
   }
 }
 

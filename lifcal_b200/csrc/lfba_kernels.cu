@@ -1691,11 +1691,12 @@ static void launch_eval_part(const Dev& d, int L, int grid, cudaStream_t s) {
   }
 }
 // mode 0: direct Jacobian-block sums, one pass; 1: the same in two passes; 2: software-pipelined stream kernel;
-// 3 (default): feature/Gram form
+// 3: feature/Gram form; 4: the same with a cp.async lens prefetch; 5: 9-feature Gram (lfba_gram2.cu);
+// 6 (default): 9-feature Gram over the packed stream with the cooperative lens gather (lfba_rows.cu)
 static int eval_mode() {
   static const int m = [] {
     const char* e = std::getenv("LFBA_EVAL_MODE");
-    return e ? std::atoi(e) : 3;
+    return e ? std::atoi(e) : 6;
   }();
   return m;
 }
@@ -1787,6 +1788,8 @@ static void prepare_eval_nc() {
   cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
 }
 void prepare_eval_kernels() {
+  prepare_gram2_kernels();
+  prepare_rows_kernels();
   prepare_eval_nc<5, 0>();
   prepare_eval_nc<7, 0>();
   prepare_eval_nc<6, 1>();
@@ -1799,6 +1802,14 @@ void launch_tables(const Dev& d, cudaStream_t s) {
   k_tables<<<(n + 127) / 128, 128, 0, s>>>(d);
 }
 int launch_eval(const Dev& d, int L, cudaStream_t s) {
+  if (eval_mode() == 5) {
+    launch_eval_gram2(d, L, s);
+    return 1;
+  }
+  if (eval_mode() == 6) {
+    launch_eval_rows(d, L, s);
+    return 1;
+  }
   int n = 1;
   const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
   LFBA_DISPATCH_MODEL(nrad, tang, (n = launch_eval_nc<NC, NRAD>(d, L, d.grid_eval, s)));

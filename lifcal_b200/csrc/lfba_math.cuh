@@ -504,6 +504,116 @@ LFBA_HD void obs_features(const CamModel& m, const TrackCtx& t, const LensEntry&
   }
 }
 
+// ---- reduced feature set (NC + 0 features) --------------------------------------------------------------------
+// f2 = Ms q is not independent: q = P + (a1 gamma) u with per-TRACK P and a1, so f2 = Px f0 + Py f1 + (a1 gamma) f3.
+// Dropping it leaves NF9 = NC features [f0, f1, f3, f4, ...] and 54 instead of 65 running sums for NC = 9; the
+// sums that involve f2 are rebuilt once per track (gram9_expand) — the same algebra, 22 fewer DFMA per observation.
+template <int NC>
+struct Feat9Dims {
+  static constexpr int NF = NC;
+  static constexpr int NQ = NF * (NF + 1) / 2;
+  static constexpr int NG = NQ + NF;
+};
+
+// residual and the NC features; F[a] = x component, F[NC + a] = y component.
+// New index -> old index (obs_features): 0 -> 0, 1 -> 1, a >= 2 -> a + 1.
+template <int NC, int NRAD, class LensEntry>
+LFBA_HD void obs_features9(const CamModel& m, const TrackCtx& t, const LensEntry& e, double ox, double oy, double r[2],
+                           double* F) {
+  constexpr int NF = NC;
+  constexpr int TAN = (NC - 5 - NRAD) / 2;
+  static_assert(5 + NRAD + 2 * TAN == NC && NRAD >= 0 && NRAD <= 2 && (TAN == 0 || TAN == 1), "NC / NRAD mismatch");
+  const double ux = e[2], uy = e[3];
+  const double cux = ux * m.gamma, cuy = uy * m.gamma;
+  const double qx = t.Px + t.a1 * cux, qy = t.Py + t.a1 * cuy;
+  const double pmx = (qx - cux * m.inv_fL) * m.gB, pmy = (qy - cuy * m.inv_fL) * m.gB;
+  double wx, wy;
+  double M00 = m.isx, M01 = 0.0, M10 = 0.0, M11 = m.isy;
+  double dk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool fwd = m.ml_adjust && m.any_dist;
+  if (m.ml_adjust) {
+    wx = pmx + cux;
+    wy = pmy + cuy;
+    if (m.any_dist) {
+      double dx, dy, A[4];
+      dist_shift_jac(m, wx, wy, dx, dy, A, dk + 0, dk + 2, dk + 4, dk + 6);
+      wx += dx;
+      wy += dy;
+      M00 = m.isx * (1.0 + A[0]);
+      M01 = m.isx * A[1];
+      M10 = m.isy * A[2];
+      M11 = m.isy * (1.0 + A[3]);
+    }
+  } else {
+    wx = pmx + (e[0] - m.crx) * m.sx;
+    wy = pmy + (e[1] - m.cry) * m.sy;
+  }
+  r[0] = (wx * m.isx + m.crx) - ox;
+  r[1] = (wy * m.isy + m.cry) - oy;
+  F[0] = M00;
+  F[NF + 0] = M10;
+  F[1] = M01;
+  F[NF + 1] = M11;
+  F[2] = M00 * ux + M01 * uy;
+  F[NF + 2] = M10 * ux + M11 * uy;
+  {
+    double d3x = t.kl * e[4], d3y = t.kl * e[5];
+    double d4x = t.kl * e[6], d4y = t.kl * e[7];
+    if (!m.ml_adjust) {
+      d3x += -m.dcrx * m.sx;
+      d4y += -m.dcry * m.sy;
+    }
+    F[3] = M00 * d3x + M01 * d3y + m.dcrx;
+    F[NF + 3] = M10 * d3x + M11 * d3y;
+    F[4] = M00 * d4x + M01 * d4y;
+    F[NF + 4] = M10 * d4x + M11 * d4y + m.dcry;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool live = (k == 0 && NRAD > 0) || (k == 1 && NRAD > 1) || (k >= 2 && TAN);
+    if (!live) continue;
+    const int col = 5 + (k < 2 ? k : NRAD + (k - 2));  // compile-time after unrolling
+    const double dx = t.kl * e[8 + 2 * k], dy = t.kl * e[9 + 2 * k];
+    double jx = M00 * dx + M01 * dy, jy = M10 * dx + M11 * dy;
+    if (fwd) {
+      jx += dk[2 * k] * m.isx;
+      jy += dk[2 * k + 1] * m.isy;
+    }
+    F[col] = jx;
+    F[NF + col] = jy;
+  }
+}
+
+// Rebuild the NC+1-feature Gram sums (layout of FeatDims<NC>: Q lower triangle row-major, then h) from the NC-feature
+// sums gn (layout of Feat9Dims<NC>), using f2 = Px f0 + Py f1 + c f3, c = a1 * gamma.
+template <int NC>
+LFBA_HD void gram9_expand(const TrackCtx& t, double c, const double* gn, double* go) {
+  constexpr int NF9 = NC, NQ9 = NF9 * (NF9 + 1) / 2;
+  constexpr int NF = NC + 1, NQ = NF * (NF + 1) / 2;
+  auto Qn = [&](int a, int b) -> double { return a >= b ? gn[a * (a + 1) / 2 + b] : gn[b * (b + 1) / 2 + a]; };
+#pragma unroll
+  for (int a = 0; a < NF; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      double v;
+      if (a == 2 && b == 2) {
+        v = t.Px * (t.Px * Qn(0, 0) + 2.0 * (t.Py * Qn(1, 0) + c * Qn(2, 0))) +
+            t.Py * (t.Py * Qn(1, 1) + 2.0 * c * Qn(2, 1)) + c * c * Qn(2, 2);
+      } else if (a == 2 || b == 2) {
+        const int o = a == 2 ? b : a;            // the other (old) index, != 2
+        const int n = o < 2 ? o : o - 1;         // its new index
+        v = t.Px * Qn(0, n) + t.Py * Qn(1, n) + c * Qn(2, n);
+      } else {
+        v = Qn(a < 2 ? a : a - 1, b < 2 ? b : b - 1);
+      }
+      go[a * (a + 1) / 2 + b] = v;
+    }
+  const double* hn = gn + NQ9;
+#pragma unroll
+  for (int a = 0; a < NF; ++a)
+    go[NQ + a] = a == 2 ? t.Px * hn[0] + t.Py * hn[1] + c * hn[2] : hn[a < 2 ? a : a - 1];
+}
+
 // Track blocks from the Gram sums. Q, h as in FeatDims; outputs: rec = [A(6) b(3) C(3 x NC)], hcc (lower, NC(NC+1)/2), gc.
 // Every output entry is independent; `stride`/`first` let L lanes split the entries (entry index % stride == first).
 template <int NC>

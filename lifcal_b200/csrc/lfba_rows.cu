@@ -1,0 +1,314 @@
+// lfba_rows.cu — k_eval_rows: the fused evaluation pass of the LM loop over the PACKED evaluation stream.
+//
+// What it replaces in the reference: one ceres::Problem::Evaluate over all reprojection blocks
+// (AutoDiffCostFunction<OurCostFunctionBundle,2,17,6,3> + CauchyLoss/Corrector, src/BundleAdjustment/BundleAdjustment.h:
+// 120-222, src/CameraCalibration.cpp:871-913) fused with the Jacobian-block products of SchurEliminator (E^T E, E^T F,
+// F^T F per residual block). The Jacobian never leaves registers.
+//
+// Arithmetic: identical to k_eval_gram2 (lfba_gram2.cu): NC two-component features per observation, weighted Gram
+// (54 running sums for NC = 9), expanded once per track into the track record (A, b, C) and the camera block (Hcc, gc).
+//
+// Memory system — why this kernel exists. ncu on k_eval_gram / k_eval_gram2 showed the L1TEX data pipe at 76% with the FP64
+// pipe at 31%: every observation gathers its 128-byte lens-table entry as 8 x LDG.128, and with one observation per lane
+// each of those warp instructions touches 32 different lines = 32 wavefronts (256 per warp step). Here
+//   * the observations are pre-arranged at set-up in the order the kernel consumes them (lfba_setup.cuh, build_stream):
+//     a warp streams rows of 32 entries, fully coalesced (512 B + 128 B per row), two rows ahead, with cp.async into a
+//     three-slot shared-memory ring;
+//   * the lens entries of the NEXT row are gathered cooperatively with cp.async (LDGSTS): the lens ids are shuffled so
+//     that 8 consecutive lanes fetch the 8 consecutive 16-byte chunks of ONE entry (4 lines per warp instruction instead
+//     of 32) straight into a padded, double-buffered shared-memory tile, from which each lane reads its own entry with
+//     conflict-free LDS.128. About 100 instead of 280 L1TEX wavefronts per warp step, and the dependent chain
+//     lens id -> lens entry is one row ahead of its use.
+// Rounds (32 / L length-adjacent tracks, one per L-lane group) are split evenly by ROW count over the warps of the grid.
+#include <cuda_pipeline.h>
+
+#include "lfba_device.cuh"
+#include "lfba_kernels.h"
+
+namespace lfba {
+
+constexpr int kLensRow = 33;  // double2 per chunk row of the shared lens tile: 32 lanes + 1 pad (bank spread)
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store_rows(double* vals, double* out, double* smem /*[nwarps*NV]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double s = vals[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) smem[warp * NV + v] = s;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += smem[w * NV + v];
+    out[v] = s;
+  }
+  __syncthreads();
+}
+
+// first round whose first row is >= row
+__device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ step_base, int R, int64_t row) {
+  int lo = 0, hi = R;  // answer in [0, R]
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (step_base[mid] < row) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int NC, int NRAD, int L>
+__global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
+  const LmState* st = d.st;
+  if (st->done || st->eval_skip) return;
+  const int cand = 1 - st->cur;
+  constexpr int G = 32 / L;
+  constexpr int NH = NC * (NC + 1) / 2;
+  constexpr int NV = NH + NC + 1;
+  constexpr int NVL = (NV + L - 1) / L;  // camera-block totals a lane owns: entries v with v % L == lane % L
+  constexpr int RS = 9 + 3 * NC;
+  constexpr int NF9 = Feat9Dims<NC>::NF, NQ9 = Feat9Dims<NC>::NQ, NG9 = Feat9Dims<NC>::NG;
+  constexpr int NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
+  typedef GramMap<NC> GM;
+  __shared__ CamModel cm;
+  __shared__ double red[4 * NV];
+  extern __shared__ double dyn[];
+  double* pers = dyn;                                              // [NVL][128]
+  double2* tiles = reinterpret_cast<double2*>(dyn + NVL * 128);    // [4 warps][2][8][kLensRow]
+  double2* ring_o = tiles + 4 * 2 * 8 * kLensRow;                  // [4 warps][3][32] observations of rows s, s+1, s+2
+  int32_t* ring_l = reinterpret_cast<int32_t*>(ring_o + 4 * 3 * 32);  // [4 warps][3][32] their lens ids
+  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+#pragma unroll
+  for (int v = 0; v < NVL; ++v) pers[v * 128 + threadIdx.x] = 0.0;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lig = lane % L, grp = lane / L;
+  double2* tile = tiles + warp * (2 * 8 * kLensRow);
+  double2* my_o = ring_o + warp * (3 * 32) + lane;
+  int32_t* my_l = ring_l + warp * (3 * 32) + lane;
+  const double* __restrict__ frames = d.frames[cand];
+  const double* __restrict__ points = d.points[cand];
+  const double2* __restrict__ lens2 = reinterpret_cast<const double2*>(d.lens);
+  const double2* __restrict__ s_obs = d.s_obs;
+  const int32_t* __restrict__ s_lid = d.s_lid;
+  const int32_t* __restrict__ step_base = d.step_base;
+  double* __restrict__ recs = d.rec[cand];
+  const bool robust = cm.robust != 0;
+  const double loss_c = cm.loss_c, half_b = 0.5 * cm.loss_b;
+  double cost = 0.0;
+
+  // this warp's rounds: an even split of the rows, aligned to round boundaries
+  const int R = d.n_rounds;
+  const int64_t W = (int64_t)gridDim.x * 4, wg = (int64_t)blockIdx.x * 4 + warp;
+  const int r_begin = round_lower_bound(step_base, R, (int64_t)d.n_rows * wg / W);
+  const int r_end = round_lower_bound(step_base, R, (int64_t)d.n_rows * (wg + 1) / W);
+  int row = R > 0 ? step_base[r_begin] : 0;
+  const int row_end = R > 0 ? step_base[r_end] : 0;
+
+  // cooperative gather of the lens entries of one row: 8 consecutive lanes fetch the 8 chunks of one entry
+  const int chunk = lane & 7, lane8 = lane & ~7;
+  auto gather_row = [&](int lid, double2* buf) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int src = lane8 + k;
+      const int lk = __shfl_sync(0xffffffffu, lid, src);
+      if (lk >= 0) __pipeline_memcpy_async(buf + chunk * kLensRow + src, lens2 + (size_t)lk * 8 + chunk, 16);
+    }
+  };
+
+  // Software pipeline, all through cp.async (no register rotation: the compiler turns rotated load targets into moves
+  // right behind the loads, which puts the full memory latency back on the critical path):
+  //   ring slot row % 3 : observation + lens id of the row           (fetched two rows ahead)
+  //   tile half row % 2 : the lens entries of the row's 32 lanes     (gathered one row ahead, needs that row's lens ids)
+  auto fetch_row = [&](int rw) {  // coalesced: 512 B + 128 B per warp
+    if (rw < row_end) {
+      __pipeline_memcpy_async(my_o + (rw % 3) * 32, s_obs + (size_t)rw * 32 + lane, 16);
+      __pipeline_memcpy_async(my_l + (rw % 3) * 32, s_lid + (size_t)rw * 32 + lane, 4);
+    }
+  };
+  fetch_row(row);
+  fetch_row(row + 1);
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncwarp();
+  gather_row(row < row_end ? my_l[(row % 3) * 32] : -1, tile + (row & 1) * (8 * kLensRow));
+  __pipeline_commit();
+
+  for (int r = r_begin; r < r_end; ++r) {
+    const int nsteps = step_base[r + 1] - step_base[r];
+    const int pos = r * G + grp;
+    const bool valid = pos < d.T;
+    const int t = valid ? d.eval_order[pos] : 0;
+    double g[NG9];
+#pragma unroll
+    for (int v = 0; v < NG9; ++v) g[v] = 0.0;
+    double prod = 1.0;
+    TrackCtx tc;
+    {
+      const int p = d.trk_point[t], f = d.trk_frame[t];
+      double Pc[3];
+      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
+      track_setup(cm, Pc, tc);
+    }
+    for (int m = 0; m < nsteps; ++m) {
+      __pipeline_wait_prior(0);  // this lane's copies for rows row (lens) and row + 1 (observation) have landed ...
+      __syncwarp();              // ... and so have everybody else's; nobody still reads what is refilled next
+      gather_row(row + 1 < row_end ? my_l[((row + 1) % 3) * 32] : -1, tile + ((row + 1) & 1) * (8 * kLensRow));
+      fetch_row(row + 2);
+      __pipeline_commit();
+      const int lid_c = my_l[(row % 3) * 32];
+      if (lid_c >= 0) {
+        const double2 o_c = my_o[(row % 3) * 32];
+        const double2* lp = tile + (row & 1) * (8 * kLensRow) + lane;
+        double e[kLensStride];
+#pragma unroll
+        for (int k = 0; k < kLensStride / 2; ++k) {
+          const double2 v2 = lp[k * kLensRow];
+          e[2 * k] = v2.x;
+          e[2 * k + 1] = v2.y;
+        }
+        double rr[2], F[2 * NF9];
+        obs_features9<NC, NRAD>(cm, tc, e, o_c.x, o_c.y, rr, F);
+        const double s = rr[0] * rr[0] + rr[1] * rr[1];
+        double w = 1.0;
+        if (robust) {
+          const double sum = 1.0 + s * loss_c;
+          w = 1.0 / sum;  // rho'
+          prod *= sum;
+          if (prod > 1e200) {  // keep the running product finite whatever the residuals are
+            cost += half_b * log(prod);
+            prod = 1.0;
+          }
+        } else {
+          cost += 0.5 * s;
+        }
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < NF9; ++a) {
+          const double wx = w * F[a], wy = w * F[NF9 + a];  // row a of the weighted features, live for this row only
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            g[q] = fma(wx, F[b], fma(wy, F[NF9 + b], g[q]));
+            ++q;
+          }
+          g[NQ9 + a] = fma(wx, rr[0], fma(wy, rr[1], g[NQ9 + a]));
+        }
+      }
+      ++row;
+    }
+    if (robust) cost += half_b * log(prod);
+    if (L > 1) {
+#pragma unroll
+      for (int v = 0; v < NG9; ++v)
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) g[v] += __shfl_xor_sync(0xffffffffu, g[v], o);
+    }
+    if (valid) {
+      // rebuild the sums that involve f2, then expand into the track record and the camera block; the entries are
+      // split over the L lanes of the group
+      double go[NG];
+      gram9_expand<NC>(tc, tc.a1 * cm.gamma, g, go);
+      const double* h = go + NQ;
+      double* dst = recs + (size_t)t * RS;
+      int v = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+          if ((v % L) == lig) dst[v] = GM::gg(tc, go, i, j);
+          ++v;
+        }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if ((v % L) == lig) dst[v] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
+        ++v;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if ((v % L) == lig) dst[v] = GM::gcam(tc, go, i, c);
+          ++v;
+        }
+      int hh = 0;
+#pragma unroll
+      for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+        for (int c2 = 0; c2 <= c1; ++c2) {
+          if ((hh % L) == lig) pers[(hh / L) * 128 + threadIdx.x] += GM::cc(tc, go, c1, c2);
+          ++hh;
+        }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (((NH + c) % L) == lig) {
+          double gcv;
+          if (c < 3) {
+            double a, b;
+            GM::geo(tc, c, a, b);
+            gcv = a * h[3] + b * h[2];
+          } else {
+            gcv = h[c + 1];
+          }
+          pers[((NH + c) / L) * 128 + threadIdx.x] += gcv;
+        }
+      }
+    }
+  }
+  __pipeline_wait_prior(0);
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV - 1; ++v) acc[v] = (v % L) == lig ? pers[(v / L) * 128 + threadIdx.x] : 0.0;
+  acc[NV - 1] = cost;
+  block_reduce_store_rows<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
+}
+
+template <int NC, int L>
+constexpr int rows_smem_bytes() {
+  return (((NC * (NC + 1) / 2 + NC + 1) + L - 1) / L) * 128 * (int)sizeof(double) + 4 * 2 * 8 * kLensRow * (int)sizeof(double2) +
+         4 * 3 * 32 * ((int)sizeof(double2) + (int)sizeof(int32_t));
+}
+
+template <int NC, int NRAD>
+static void launch_rows_nc(const Dev& d, int L, int grid, cudaStream_t s) {
+  switch (L) {
+    case 1: k_eval_rows<NC, NRAD, 1><<<grid, 128, rows_smem_bytes<NC, 1>(), s>>>(d); break;
+    case 2: k_eval_rows<NC, NRAD, 2><<<grid, 128, rows_smem_bytes<NC, 2>(), s>>>(d); break;
+    case 4: k_eval_rows<NC, NRAD, 4><<<grid, 128, rows_smem_bytes<NC, 4>(), s>>>(d); break;
+    case 8: k_eval_rows<NC, NRAD, 8><<<grid, 128, rows_smem_bytes<NC, 8>(), s>>>(d); break;
+    default: k_eval_rows<NC, NRAD, 16><<<grid, 128, rows_smem_bytes<NC, 16>(), s>>>(d); break;
+  }
+}
+
+template <int NC, int NRAD>
+static void prepare_rows_nc() {
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 1>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 2>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 4>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 8>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 16>());
+}
+
+void prepare_rows_kernels() {
+  prepare_rows_nc<5, 0>();
+  prepare_rows_nc<7, 0>();
+  prepare_rows_nc<6, 1>();
+  prepare_rows_nc<8, 1>();
+  prepare_rows_nc<7, 2>();
+  prepare_rows_nc<9, 2>();
+}
+
+void launch_eval_rows(const Dev& d, int L, cudaStream_t s) {
+  const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
+  switch (nrad * 2 + tang) {
+    case 0: launch_rows_nc<5, 0>(d, L, d.grid_eval, s); break;
+    case 1: launch_rows_nc<7, 0>(d, L, d.grid_eval, s); break;
+    case 2: launch_rows_nc<6, 1>(d, L, d.grid_eval, s); break;
+    case 3: launch_rows_nc<8, 1>(d, L, d.grid_eval, s); break;
+    case 4: launch_rows_nc<7, 2>(d, L, d.grid_eval, s); break;
+    default: launch_rows_nc<9, 2>(d, L, d.grid_eval, s); break;
+  }
+}
+
+}  // namespace lfba

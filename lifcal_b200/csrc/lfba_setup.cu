@@ -466,4 +466,75 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
   if (launches) *launches += nl;
 }
 
+// ---- packed evaluation stream ----------------------------------------------------------------------------------
+namespace {
+__global__ void k_round_steps(const int32_t* eval_order, const int32_t* trk_begin, int32_t* steps, int G, int L, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  if (r == R) {
+    steps[r] = 0;
+    return;
+  }
+  const int t = eval_order[(size_t)r * G];  // tracks are in descending length order: the first is the longest
+  steps[r] = (trk_begin[t + 1] - trk_begin[t] + L - 1) / L;
+}
+__global__ void k_fill_stream(const int32_t* __restrict__ eval_order, const int32_t* __restrict__ trk_begin,
+                              const int32_t* __restrict__ step_base, const double2* __restrict__ obs,
+                              const int32_t* __restrict__ lens_id, double2* __restrict__ s_obs,
+                              int32_t* __restrict__ s_lid, int T, int G, int L, int R, int64_t n_entries) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  const int row = (int)(e >> 5), lane = (int)(e & 31);
+  int lo = 0, hi = R;  // largest round with step_base[round] <= row
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (step_base[mid] <= row) lo = mid; else hi = mid;
+  }
+  const int m = row - step_base[lo];
+  const int pos = lo * G + lane / L;
+  double2 o = make_double2(0.0, 0.0);
+  int lid = -1;
+  if (pos < T) {
+    const int t = eval_order[pos];
+    const int i = trk_begin[t] + lane % L + L * m;
+    if (i < trk_begin[t + 1]) {
+      o = obs[i];
+      lid = lens_id[i];
+    }
+  }
+  s_obs[e] = o;
+  s_lid[e] = lid;
+}
+}  // namespace
+
+void build_stream(ProblemIndex& ix, int L, cudaStream_t s, int64_t* launches) {
+  ix.stream_L = L;
+  ix.n_rounds = 0;
+  ix.n_rows = 0;
+  if (ix.T <= 0) {
+    ix.step_base.alloc(1);
+    ix.step_base.zero(s);
+    return;
+  }
+  const int G = 32 / L;
+  const int R = (ix.T + G - 1) / G;
+  Temp tmp;
+  DevBuf<int32_t> steps((size_t)R + 1);
+  ix.step_base.alloc((size_t)R + 1);
+  k_round_steps<<<grid_for(R + 1), 256, 0, s>>>(ix.eval_order.p, ix.trk_begin.p, steps.p, G, L, R);
+  exclusive_sum(tmp, steps.p, ix.step_base.p, (size_t)R + 1, s);
+  int32_t rows = 0;
+  LFBA_CUDA(cudaMemcpyAsync(&rows, ix.step_base.p + R, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  LFBA_CUDA(cudaStreamSynchronize(s));
+  if (rows < 0) throw CudaError("evaluation stream too long", LFBA_INVALID_ARGUMENT);
+  ix.n_rounds = R;
+  ix.n_rows = rows;
+  const int64_t n_entries = (int64_t)rows * 32;
+  ix.s_obs.alloc((size_t)n_entries);
+  ix.s_lid.alloc((size_t)n_entries);
+  k_fill_stream<<<grid_for(n_entries), 256, 0, s>>>(ix.eval_order.p, ix.trk_begin.p, ix.step_base.p, ix.obs_sorted,
+                                                      ix.lens_id_sorted, ix.s_obs.p, ix.s_lid.p, ix.T, G, L, R, n_entries);
+  if (launches) *launches += 3;
+}
+
 }  // namespace lfba

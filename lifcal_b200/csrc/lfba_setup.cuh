@@ -90,6 +90,13 @@ struct ProblemIndex {
   DevBuf<int32_t> trk_point, trk_frame, trk_begin, pt_trk_begin, frm_begin, frm_trk;
   DevBuf<int32_t> pair_begin, pair_f1, pair_f2, pair_t1, pair_t2;
   DevBuf<int32_t> eval_order;
+  // packed evaluation stream (build_stream): observations re-laid out in the order the fused evaluation kernel consumes
+  // them. A ROUND is 32 / L length-adjacent tracks (one per L-lane group of a warp); its rows are 32 entries each:
+  // entry (row, lane) = observation  lane % L + L * step  of the track of group lane / L, or padding (lens id -1).
+  DevBuf<double2> s_obs;      // [n_rows * 32]
+  DevBuf<int32_t> s_lid;      // [n_rows * 32]
+  DevBuf<int32_t> step_base;  // [n_rounds + 1] first row of each round
+  int n_rounds = 0, n_rows = 0, stream_L = 0;
   DevBuf<double> lens_xy;
   // input-order copies for the eval-only API
   DevBuf<double2> obs_in;
@@ -99,5 +106,6 @@ struct ProblemIndex {
 };
 
 void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64_t* launches);
+void build_stream(ProblemIndex& ix, int L, cudaStream_t s, int64_t* launches);
 
 }  // namespace lfba

@@ -343,17 +343,23 @@ struct Solver {
     part_step.alloc((size_t)d.grid_pts * 8);
     part_pts.zero(stream);
     part_step.zero(stream);
-    // lanes per track: enough (point, frame) groups to fill the machine, at most ~one observation slot wasted
+    // lanes per track (L): the fused evaluation walks ROUNDS of 32 / L length-adjacent tracks per warp. L = 1 has no
+    // cross-lane reduction and no predicated per-track work (measured at cfg4: 4.9 ms vs 7.3 ms for L = 4), so L grows
+    // only while there are too few rounds to give every warp of the grid a few of them.
     {
       const double mean_len = T > 0 ? (double)ix.N / T : 1.0;
-      const int64_t threads = (int64_t)d.grid_eval * 128;
+      d.grid_eval = std::max(1, 2 * sms);
+      const int64_t warps = (int64_t)d.grid_eval * 4;
       int L = 1;
-      while (L < 16 && (int64_t)T * L < threads * 2 && L * 2 <= mean_len) L *= 2;
-      if (L < 4 && mean_len >= 8) L = 4;
+      while (L < 16 && ((int64_t)T * L + 31) / 32 < 2 * warps && L * 2 <= mean_len) L *= 2;
+      if (const char* e = std::getenv("LFBA_LANES")) L = std::max(1, std::min(16, std::atoi(e)));  // experiment
       lanes = L;
-      d.grid_eval = std::max(1, (int)std::min<int64_t>(2 * sms, ((int64_t)T * L + 127) / 128));
+      const int64_t rounds = ((int64_t)T * L + 31) / 32;
+      d.grid_eval = std::max(1, (int)std::min<int64_t>(2 * sms, (rounds + 3) / 4));
     }
     part_eval.alloc((size_t)d.grid_eval * 64);
+    build_stream(ix, lanes, stream, &launches);
+    phase("packed stream");
     {
       const int per_frame = F > 0 ? (T + F - 1) / F : 0;
       frame_splits = std::max(1, std::min(16, std::min((4 * sms) / std::max(1, F), (per_frame + 255) / 256)));
@@ -373,6 +379,9 @@ struct Solver {
     d.trk_begin = ix.trk_begin.p; d.pt_trk_begin = ix.pt_trk_begin.p; d.frm_begin = ix.frm_begin.p;
     d.frm_trk = ix.frm_trk.p; d.pair_begin = ix.pair_begin.p; d.pair_f1 = ix.pair_f1.p; d.pair_f2 = ix.pair_f2.p;
     d.pair_t1 = ix.pair_t1.p; d.pair_t2 = ix.pair_t2.p; d.npairs = ix.npairs; d.eval_order = ix.eval_order.p;
+    d.s_obs = ix.s_obs.p; d.s_lid = ix.s_lid.p; d.step_base = ix.step_base.p;
+    d.n_rounds = ix.n_rounds; d.n_rows = ix.n_rows; d.stream_L = ix.stream_L;
+    if (std::getenv("LFBA_EVAL_ORDER") && std::atoi(std::getenv("LFBA_EVAL_ORDER")) == 0) d.eval_order = nullptr;  // experiment: storage order
     d.pt_coupled = pt_coupled.p; d.coupled_pts = coupled_pts.p; d.pt_active = pt_active.p; d.frm_active = frm_active.p;
     d.c_p1 = c_p1.p; d.c_p2 = c_p2.p; d.c_dist = c_dist.p; d.c_sigma = c_sigma.p;
     for (int c = 0; c < 17; ++c) {
