@@ -1200,6 +1200,169 @@ __global__ void __launch_bounds__(128) k_frame_pose(Dev d) {
   }
 }
 
+// Per frame, ONE pass over the frame's tracks (k_frame_pose + k_frame_cam fused: the track record, the point data and
+// W are read once, W never round-trips through HBM): pose diagonal block, pose gradient, camera-pose block.
+template <int NC>
+__global__ void __launch_bounds__(128) k_frame_all(Dev d) {
+  LmState* st = d.st;
+  if (st->done) return;
+  const int cur = st->cur;
+  const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  constexpr int RS = 9 + 3 * NC;
+  constexpr int NP = 21 + 6 + 6 + 6;  // S_ff (lower 21), reduced gradient, full gradient, diag(F^T F)
+  constexpr int NV = NP + 6 * NC;     // + camera-pose block
+  __shared__ double fe[kFrameStride];
+  __shared__ double red[4 * NV];
+  __shared__ double out[NV];
+  if (threadIdx.x < kFrameStride) fe[threadIdx.x] = d.frames[cur][(size_t)f * kFrameStride + threadIdx.x];
+  __syncthreads();
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  const double* __restrict__ recs = d.rec[cur];
+  const double* __restrict__ points = d.points[cur];
+  for (int idx = d.frm_begin[f] + split * blockDim.x + threadIdx.x; idx < d.frm_begin[f + 1];
+       idx += nsplit * blockDim.x) {
+    const int t = d.frm_trk[idx];
+    const int p = d.trk_point[t];
+    // first the 3x3 part of the record and of the point data (A, b | Hpp^-1, g_p); the camera parts are loaded after
+    // the pose block is done, so that they are not live across it (255 registers: 93 accumulators + one track)
+    const double* rcp = recs + (size_t)t * RS;
+    const double2* pd2 = reinterpret_cast<const double2*>(d.pdata + (size_t)p * kPointStride);
+    double rc[10], pd[10];
+    if (RS % 2 == 0) {  // records are 16-byte aligned: 128-bit loads
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double2 v2 = __ldg(reinterpret_cast<const double2*>(rcp) + k);
+        rc[2 * k] = v2.x;
+        rc[2 * k + 1] = v2.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) rc[k] = __ldg(rcp + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const double2 v2 = __ldg(pd2 + k);
+      pd[2 * k] = v2.x;
+      pd[2 * k + 1] = v2.y;
+    }
+    const double A[6] = {rc[0], rc[1], rc[2], rc[3], rc[4], rc[5]};
+    const double b[3] = {rc[6], rc[7], rc[8]};
+    double m[9];
+    track_M(fe, points + 3 * (size_t)p, m);
+    double AM[18];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double y[3];
+      sym3_vec(A, m + 3 * k, y);
+      AM[0 * 6 + k] = y[0];
+      AM[1 * 6 + k] = y[1];
+      AM[2 * 6 + k] = y[2];
+    }
+    AM[0 * 6 + 3] = A[0]; AM[0 * 6 + 4] = A[1]; AM[0 * 6 + 5] = A[2];
+    AM[1 * 6 + 3] = A[1]; AM[1 * 6 + 4] = A[3]; AM[1 * 6 + 5] = A[4];
+    AM[2 * 6 + 3] = A[2]; AM[2 * 6 + 4] = A[4]; AM[2 * 6 + 5] = A[5];
+    auto Mt = [&](int a, int i) -> double { return a < 3 ? m[3 * a + i] : (a - 3 == i ? 1.0 : 0.0); };
+    const double* R = fe;
+    double AR[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      AR[0 + j] = A[0] * R[j] + A[1] * R[3 + j] + A[2] * R[6 + j];
+      AR[3 + j] = A[1] * R[j] + A[3] * R[3 + j] + A[4] * R[6 + j];
+      AR[6 + j] = A[2] * R[j] + A[4] * R[3 + j] + A[5] * R[6 + j];
+    }
+    double V[18], W[18];
+    const double Hi[6] = {pd[0], pd[1], pd[2], pd[3], pd[4], pd[5]};
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) V[3 * a + j] = Mt(a, 0) * AR[j] + Mt(a, 1) * AR[3 + j] + Mt(a, 2) * AR[6 + j];
+      sym3_vec(Hi, V + 3 * a, W + 3 * a);
+    }
+    double2* vw2 = reinterpret_cast<double2*>(d.vw + (size_t)t * kVWStride);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      vw2[k] = make_double2(V[2 * k], V[2 * k + 1]);
+      vw2[9 + k] = make_double2(W[2 * k], W[2 * k + 1]);
+    }
+    const double gp[3] = {pd[6], pd[7], pd[8]};
+    {
+      int h = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double gva = Mt(a, 0) * b[0] + Mt(a, 1) * b[1] + Mt(a, 2) * b[2];
+#pragma unroll
+        for (int c = 0; c <= a; ++c) {
+          const double hvv = Mt(a, 0) * AM[0 * 6 + c] + Mt(a, 1) * AM[1 * 6 + c] + Mt(a, 2) * AM[2 * 6 + c];
+          acc[h] += hvv - (W[3 * a] * V[3 * c] + W[3 * a + 1] * V[3 * c + 1] + W[3 * a + 2] * V[3 * c + 2]);
+          if (c == a) acc[33 + a] += hvv;
+          ++h;
+        }
+        acc[21 + a] += gva - (W[3 * a] * gp[0] + W[3 * a + 1] * gp[1] + W[3 * a + 2] * gp[2]);
+        acc[27 + a] += gva;
+      }
+    }
+    // camera-pose block: C_t^T M_t - Hcp W_t^T
+    {
+      double cc[3 * NC + 1], hc[3 * NC + 1 + ((3 * NC + 1) & 1)];  // cc[0] = rc[9]; hc = pd[12 ..]
+      cc[0] = rc[9];
+      if (RS % 2 == 0) {
+#pragma unroll
+        for (int k = 5; k < RS / 2; ++k) {
+          const double2 v2 = __ldg(reinterpret_cast<const double2*>(rcp) + k);
+          cc[2 * k - 9] = v2.x;
+          cc[2 * k - 8] = v2.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 10; k < RS; ++k) cc[k - 9] = __ldg(rcp + k);
+      }
+#pragma unroll
+      for (int k = 0; k < (3 * NC + 1) / 2; ++k) {
+        const double2 v2 = __ldg(pd2 + 6 + k);
+        hc[2 * k] = v2.x;
+        hc[2 * k + 1] = v2.y;
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const double c0 = cc[c], c1 = cc[NC + c], c2 = cc[2 * NC + c];
+        const double h0 = hc[3 * c], h1 = hc[3 * c + 1], h2 = hc[3 * c + 2];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const double cm = a < 3 ? (c0 * m[3 * a] + c1 * m[3 * a + 1] + c2 * m[3 * a + 2])
+                                  : (a == 3 ? c0 : (a == 4 ? c1 : c2));
+          acc[NP + 6 * c + a] += cm - (h0 * W[3 * a] + h1 * W[3 * a + 1] + h2 * W[3 * a + 2]);
+        }
+      }
+    }
+  }
+  block_reduce_store<NV>(acc, out, red);
+  if (threadIdx.x < NV) {
+    const int v = threadIdx.x;
+    const double sv = out[v];
+    double* dst = nullptr;
+    if (v < 21) {
+      int a = 0, h = v;
+      while (h > a) { h -= a + 1; ++a; }
+      dst = S_at(d, 6 * f + a, 6 * f + h);
+    } else if (v < 27) {
+      dst = d.g + 6 * f + (v - 21);
+    } else if (v < 33) {
+      dst = d.gfull + 6 * f + (v - 27);
+    } else if (v < NP) {
+      dst = d.hdiag + 6 * f + (v - 33);
+    } else {
+      const int c = (v - NP) / 6, a = (v - NP) % 6;
+      const int r = d.cam_red[c];
+      if (r >= 0) dst = S_at(d, r, 6 * f + a);
+    }
+    if (dst) {
+      if (nsplit == 1) *dst += sv; else atomicAdd(dst, sv);
+    }
+  }
+}
+
 // Per frame: camera-pose block S[cam, f] = sum_t (C_t^T M_t - Hcp W_t^T).
 template <int NC>
 __global__ void __launch_bounds__(128) k_frame_cam(Dev d) {
@@ -1261,13 +1424,16 @@ __global__ void __launch_bounds__(128) k_pairs(Dev d) {
 #pragma unroll
   for (int v = 0; v < 36; ++v) acc[v] = 0.0;
   for (int i = d.pair_begin[warp] + lane; i < d.pair_begin[warp + 1]; i += 32) {
-    const double* W = d.vw + (size_t)d.pair_t1[i] * kVWStride + 18;
-    const double* V = d.vw + (size_t)d.pair_t2[i] * kVWStride;
+    const double2* W = reinterpret_cast<const double2*>(d.vw + (size_t)d.pair_t1[i] * kVWStride + 18);
+    const double2* V = reinterpret_cast<const double2*>(d.vw + (size_t)d.pair_t2[i] * kVWStride);
     double w[18], v[18];
 #pragma unroll
-    for (int k = 0; k < 18; ++k) {
-      w[k] = W[k];
-      v[k] = V[k];
+    for (int k = 0; k < 9; ++k) {  // 144-byte halves of a 288-byte record: 16-byte aligned
+      const double2 a = __ldg(W + k), b = __ldg(V + k);
+      w[2 * k] = a.x;
+      w[2 * k + 1] = a.y;
+      v[2 * k] = b.x;
+      v[2 * k + 1] = b.y;
     }
 #pragma unroll
     for (int a = 0; a < 6; ++a)
@@ -1825,9 +1991,15 @@ int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
   }
   if (d.refine_poses) {
     dim3 grid(d.F, frame_splits);
-    k_frame_pose<<<grid, 128, 0, s>>>(d);
-    LFBA_DISPATCH_NC(d.NC, (k_frame_cam<NC><<<grid, 128, 0, s>>>(d)));
-    launches += 2;
+    static const bool split_frames = std::getenv("LFBA_SPLIT_FRAME_KERNELS") != nullptr;  // A/B: the two-kernel form
+    if (split_frames) {
+      k_frame_pose<<<grid, 128, 0, s>>>(d);
+      LFBA_DISPATCH_NC(d.NC, (k_frame_cam<NC><<<grid, 128, 0, s>>>(d)));
+      launches += 2;
+    } else {
+      LFBA_DISPATCH_NC(d.NC, (k_frame_all<NC><<<grid, 128, 0, s>>>(d)));
+      launches += 1;
+    }
     if (d.refine_points && d.npairs > 0) {
       k_pairs<<<(d.npairs + 3) / 4, 128, 0, s>>>(d);
       ++launches;
