@@ -506,7 +506,12 @@ size_t banded_smem_bytes(const Dev& d, int bw, int nb) {
   return bytes <= (size_t)kBandedSmemMax ? bytes : 0;
 }
 
-int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, int bw, cudaStream_t s) {
+void launch_chol_banded(const Dev& d, int bw, int nb, size_t smem, cudaStream_t s) {
+  k_chol_banded<<<1, 256, smem, s>>>(d, bw, nb);
+}
+
+int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, int bw, cudaStream_t s, PartPlan* plan) {
+  if (part_plan_active(plan)) return launch_part_solve(d, plan, s);
   const int nb = d.n - d.np6 + 1;
   const size_t bsm = banded_smem_bytes(d, bw, nb);
   if (bsm > 0) {

@@ -27,8 +27,14 @@ void launch_eval_gram2(const Dev& d, int lanes_per_track, cudaStream_t s);
 // lfba_rows.cu: fused evaluation over the packed stream, cooperative cp.async lens gather
 void prepare_rows_kernels();
 void launch_eval_rows(const Dev& d, int lanes_per_track, cudaStream_t s);
+// lfba_chol_part.cu: partitioned factorisation of the banded-arrowhead system (P CTAs instead of one chain of F pivots)
+struct PartPlan;
+PartPlan* part_plan_create(const Dev& d, int bandwidth_frames, cudaStream_t s);  // never null; may be inactive
+void part_plan_destroy(PartPlan* p);
+bool part_plan_active(const PartPlan* p);
+int launch_part_solve(const Dev& d, PartPlan* p, cudaStream_t s);
 int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first /*[n_tiles] first nonzero tile col*/,
-                         int bandwidth_frames, cudaStream_t s);
+                         int bandwidth_frames, cudaStream_t s, PartPlan* plan);
 
 // ---- lfba_eval.cu: eval-only kernel (residuals + Jacobians materialised in Ceres' block layout) ----
 struct EvalOut {

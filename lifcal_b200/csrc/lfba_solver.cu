@@ -105,6 +105,7 @@ struct Solver {
   int frame_splits = 1;
   int n_tiles = 0;
   int band_frames = 0;
+  PartPlan* part_plan = nullptr;
   int64_t launches = 0;
   double setup_time = 0;
   int64_t n_obs_global = 0;
@@ -130,6 +131,7 @@ struct Solver {
     if (ev_made)
       for (auto& e : ev) cudaEventDestroy(e);
     if (h_done) cudaFreeHost(h_done);
+    part_plan_destroy(part_plan);
     if (comm && own_comm) Nccl::get().CommDestroy(comm);
     alloc_stream() = stream;  // member buffers are freed (stream-ordered) right after this body
   }
@@ -404,6 +406,7 @@ struct Solver {
     ev_made = true;
     prepare_device_kernels();
     prepare_eval_kernels();
+    part_plan = part_plan_create(d, band_frames, stream);
     LFBA_CUDA(cudaStreamSynchronize(stream));
     phase("buffers");
     poolstat("end");
@@ -504,7 +507,7 @@ struct Solver {
       mark(LFBA_T_ALLREDUCE);
       launch_finalize(d, stream);
       mark(LFBA_T_DAMP);
-      launches += 1 + launch_reduced_solve(d, n_tiles, tile_first.p, band_frames, stream);
+      launches += 1 + launch_reduced_solve(d, n_tiles, tile_first.p, band_frames, stream, part_plan);
       mark(LFBA_T_CHOL);
       launches += launch_steps(d, stream);
       mark(LFBA_T_POINTSTEP);

@@ -147,6 +147,15 @@ def test_model_variants_match_oracle(gpu):
                 _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread)
 
 
+def test_windowed_scene_partitioned_reduced_solve(gpu):
+    # 64 frames, window 4: the reduced system is banded (3 frames) + border, long enough for the partitioned
+    # factorisation (lfba_chol_part.cu: 4 partitions, 3 separators). Same answer as the oracle's dense LLT.
+    sc = capi.make_scene(None, n_points=1500, n_frames=64, window=4, seed=77, order=1)
+    cam, vw, pt, s = api.solve(sc.problem, sc.camera_init, sc.views_init, sc.points_init)
+    spread, (ocam, ovw, opt_, os_) = _oracle_spread(sc.problem, (sc.camera_init, sc.views_init, sc.points_init))
+    _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread)
+
+
 def test_observation_order_does_not_matter(gpu):
     # frame-major (reference order) vs point-major vs shuffled input: same solution
     a = capi.make_scene(None, n_points=150, n_frames=8, window=3, seed=31, order=0)
