@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_gram_pf(Dev d) {
 
 // Sum the CTA partials of k_eval_tracks (fixed order) -> camsum[cand]; sum the step partials of
 // k_point_step (previous round); candidate cost of the distance constraints; assemble eval_scalars.
-__global__ void k_reduce_eval(Dev d) {
+__global__ void __launch_bounds__(1024) k_reduce_eval(Dev d) {
   LmState* st = d.st;
   if (st->done) return;
   const int cand = 1 - st->cur;
@@ -823,19 +823,24 @@ __global__ void k_reduce_eval(Dev d) {
   __shared__ double sh[64];
   __shared__ double shs[8];
   const int v = threadIdx.x;
-  if (v < 64) {
-    double s = 0.0;
-    if (v < NV && !st->eval_skip)
-      for (int b = 0; b < d.grid_eval; ++b) s += d.part_eval[(size_t)b * 64 + v];
-    sh[v] = s;
-    if (v < NV) d.camsum[cand][v] = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 32 warps; a warp sums one value over the CTAs
+  for (int q = warp; q < 64; q += 32) {                        // (lanes stride over the CTAs, then a butterfly: fixed order)
+    double s_ = 0.0;
+    if (q < NV && !st->eval_skip)
+      for (int b = lane; b < d.grid_eval; b += 32) s_ += d.part_eval[(size_t)b * 64 + q];
+    s_ = warp_sum(s_);
+    if (lane == 0) {
+      sh[q] = s_;
+      if (q < NV) d.camsum[cand][q] = s_;
+    }
   }
-  if (v >= 64 && v < 72) {
-    const int k = v - 64;
-    double s = 0.0;
+  if (warp < 8) {
+    const int k = warp;
+    double s_ = 0.0;
     if (d.refine_points && (st->iter == 0 || st->solve_ok))
-      for (int b = 0; b < d.grid_pts; ++b) s += d.part_step[(size_t)b * 8 + k];
-    shs[k] = s;
+      for (int b = lane; b < d.grid_pts; b += 32) s_ += d.part_step[(size_t)b * 8 + k];
+    s_ = warp_sum(s_);
+    if (lane == 0) shs[k] = s_;
   }
   __syncthreads();
   if (v == 0) {
@@ -1550,23 +1555,26 @@ __global__ void k_constraints(Dev d) {
 
 // Camera block: Hcc, gc of the accepted state (from k_eval_tracks) + the Schur terms of k_points; point
 // gradient statistics into the system scalars.
-__global__ void k_add_camera(Dev d) {
+__global__ void __launch_bounds__(1024) k_add_camera(Dev d) {
   LmState* st = d.st;
   if (st->done) return;
   const int NC = d.NC, NH = NC * (NC + 1) / 2;
   const double* cs = d.camsum[st->cur];
   __shared__ double sp[64];
   const int v = threadIdx.x;
-  if (v < 64) {
-    double s = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = warp; q < 64; q += 32) {  // a warp reduces one value over the CTAs of k_points (fixed order)
+    double s_ = 0.0;
     if (d.refine_points) {
-      if (v == 63) {
-        for (int b = 0; b < d.grid_pts; ++b) s = fmax(s, d.part_pts[(size_t)b * 64 + 63]);
+      if (q == 63) {
+        for (int b = lane; b < d.grid_pts; b += 32) s_ = fmax(s_, d.part_pts[(size_t)b * 64 + 63]);
+        s_ = warp_max(s_);
       } else {
-        for (int b = 0; b < d.grid_pts; ++b) s += d.part_pts[(size_t)b * 64 + v];
+        for (int b = lane; b < d.grid_pts; b += 32) s_ += d.part_pts[(size_t)b * 64 + q];
+        s_ = warp_sum(s_);
       }
     }
-    sp[v] = s;
+    if (lane == 0) sp[q] = s_;
   }
   __syncthreads();
   if (v < NH) {
@@ -1593,11 +1601,11 @@ __global__ void k_add_camera(Dev d) {
 // (EvaluateGradientAndJacobian's scaling + gradient norms, FinalizeIterationAndCheckIfMinimizerCanContinue,
 //  LevenbergMarquardtStrategy::ComputeStep's diagonal). One CTA.
 // ================================================================================================
-__global__ void __launch_bounds__(256) k_finalize(Dev d) {
+__global__ void __launch_bounds__(1024) k_finalize(Dev d) {
   LmState* st = d.st;
   if (st->done) return;
   const Options& o = d.opt;
-  __shared__ double sg2[8], sgm[8];
+  __shared__ double sg2[32], sgm[32];
   const bool first = st->first != 0;
   const bool refresh = st->pending_row && st->row.step_is_successful;
   double g2 = 0.0, gm = 0.0;
@@ -1630,7 +1638,7 @@ __global__ void __launch_bounds__(256) k_finalize(Dev d) {
       lfba_iteration& row = st->row;
       if (refresh) {
         double t2 = d.sys_scalars[SS_GNORM2], tm = 0.0;
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
           t2 += sg2[w];
           tm = fmax(tm, sgm[w]);
         }
@@ -1981,7 +1989,7 @@ int launch_eval(const Dev& d, int L, cudaStream_t s) {
   LFBA_DISPATCH_MODEL(nrad, tang, (n = launch_eval_nc<NC, NRAD>(d, L, d.grid_eval, s)));
   return n;
 }
-void launch_reduce_eval(const Dev& d, cudaStream_t s) { k_reduce_eval<<<1, 128, 0, s>>>(d); }
+void launch_reduce_eval(const Dev& d, cudaStream_t s) { k_reduce_eval<<<1, 1024, 0, s>>>(d); }
 void launch_control_accept(const Dev& d, cudaStream_t s) { k_control_accept<<<1, 1, 0, s>>>(d); }
 int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
   int launches = 0;
@@ -2013,10 +2021,10 @@ int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
     k_constraints<<<1, 32, 0, s>>>(d);
     ++launches;
   }
-  k_add_camera<<<1, 64, 0, s>>>(d);
+  k_add_camera<<<1, 1024, 0, s>>>(d);
   return launches + 1;
 }
-void launch_finalize(const Dev& d, cudaStream_t s) { k_finalize<<<1, 256, 0, s>>>(d); }
+void launch_finalize(const Dev& d, cudaStream_t s) { k_finalize<<<1, 1024, 0, s>>>(d); }
 int launch_steps(const Dev& d, cudaStream_t s) {
   int launches = 1;
   if (d.refine_points) {

@@ -124,12 +124,15 @@ struct Solver {
   int* h_done = nullptr;  // pinned
   std::vector<int> h_coupled;
   cudaEvent_t ev[LFBA_NUM_KERNEL_TIMERS + 1];
+  cudaEvent_t ev_round[4];
   bool ev_made = false;
 
   ~Solver() {
     cudaSetDevice(device);
-    if (ev_made)
+    if (ev_made) {
       for (auto& e : ev) cudaEventDestroy(e);
+      for (auto& e : ev_round) cudaEventDestroy(e);
+    }
     if (h_done) cudaFreeHost(h_done);
     part_plan_destroy(part_plan);
     if (comm && own_comm) Nccl::get().CommDestroy(comm);
@@ -403,6 +406,7 @@ struct Solver {
     d.part_eval = part_eval.p; d.part_pts = part_pts.p; d.part_step = part_step.p;
     d.st = st.p; d.log = log.p;
     for (auto& e : ev) LFBA_CUDA(cudaEventCreate(&e));
+    for (auto& e : ev_round) LFBA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ev_made = true;
     prepare_device_kernels();
     prepare_eval_kernels();
@@ -511,8 +515,24 @@ struct Solver {
       mark(LFBA_T_CHOL);
       launches += launch_steps(d, stream);
       mark(LFBA_T_POINTSTEP);
-      LFBA_CUDA(cudaMemcpyAsync(h_done, &st.p->done, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      LFBA_CUDA(cudaStreamSynchronize(stream));
+      // The host runs ONE round ahead of the device: round r + 1 is enqueued before the `done` flag of round r is read,
+      // so the stream never drains between rounds (every kernel early-outs on the device flag once the solve is over;
+      // all ranks see the same flags, so they enqueue the same rounds and the NCCL calls stay matched).
+      const int slot = rounds & 3;
+      LFBA_CUDA(cudaMemcpyAsync(h_done + slot, &st.p->done, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      LFBA_CUDA(cudaEventRecord(ev_round[slot], stream));
+      if (prof || debug) {
+        LFBA_CUDA(cudaStreamSynchronize(stream));
+      } else if (rounds >= 1) {
+        LFBA_CUDA(cudaEventSynchronize(ev_round[(rounds - 1) & 3]));
+        if (h_done[(rounds - 1) & 3]) {
+          ++rounds;
+          break;
+        }
+        continue;
+      } else {
+        continue;
+      }
       if (prof) {
         const int order[] = {LFBA_T_LENS, LFBA_T_EVAL, LFBA_T_CONTROL, LFBA_T_SCHUR, LFBA_T_ALLREDUCE, LFBA_T_DAMP,
                              LFBA_T_CHOL, LFBA_T_POINTSTEP};
@@ -548,7 +568,7 @@ struct Solver {
         std::fprintf(stderr, "[lfba dbg]   |y|max=%.6e y[0..5]=%.4e %.4e %.4e %.4e %.4e %.4e\n", ymax, hy[0], hy[1], hy[2],
                      d.n > 3 ? hy[3] : 0.0, d.n > 4 ? hy[4] : 0.0, d.n > 5 ? hy[5] : 0.0);
       }
-      if (*h_done) {
+      if (h_done[slot]) {
         ++rounds;
         break;
       }
