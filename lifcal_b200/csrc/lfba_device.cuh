@@ -126,6 +126,7 @@ struct Dev {
   double* points[2];   // [3P]
   // tables
   double* lens;        // [NL*16]
+  CamModel* cm_buf;    // camera model of the candidate parameters, written by k_tables (copied into constant memory)
   const double* lens_xy;  // [NL*2] lens centres
   double implicit_tol;           // use the implicit lens derivatives while lens_dev <= this (negative: never)
   unsigned long long* lens_dev;  // bits of the largest relative deviation (implicit vs exact lens derivatives) seen in this run

@@ -39,21 +39,34 @@ __global__ void k_tables_for(Dev d, int which) {
 // odd number of doubles: conflict-free for the strided writes AND for the linear read-back) and then streams each
 // output array out with fully coalesced 8-byte stores: the 128 rows of a CTA are one contiguous range of each array.
 constexpr int kEvalBlock = 128;
-constexpr int kStrideC = 35, kStrideV = 13, kStrideP = 7, kStrideR = 3;  // padded rows of 34 / 12 / 6 / 2 doubles
-constexpr int kEvalSmemDoubles = kEvalBlock * (kStrideC + kStrideV + kStrideP + kStrideR);
+constexpr int kStrideV = 13, kStrideP = 7, kStrideR = 3;  // padded rows of 12 / 6 / 2 doubles
+// the camera block is staged without its 17 - NC structurally zero columns (they are written as zeros on the way out):
+// 2 NC doubles per observation, padded to an odd stride; at least 17 so that a warp's 32 rows hold its 4 KB lens scratch
+template <int NC>
+constexpr int stride_c() { return 2 * NC + 1 < 17 ? 17 : 2 * NC + 1; }
+template <int NC>
+constexpr int eval_smem_doubles() { return kEvalBlock * (stride_c<NC>() + kStrideV + kStrideP + kStrideR); }
 
 template <int W, int STRIDE>
 __device__ __forceinline__ void stream_out(const double* __restrict__ sm, double* __restrict__ dst, int rows) {
-  // dst[row * W + c] = sm[row * STRIDE + c] for the CTA's `rows` observations, as 16-byte streaming stores: consecutive
-  // threads -> consecutive double2 (512 B per warp instruction). W is even, so a pair never straddles two rows; dst is
-  // 16-byte aligned because a CTA starts at a multiple of 128 observations.
-  static_assert(W % 2 == 0, "row width must be even");
-  const int total2 = rows * (W / 2);
-  double2* __restrict__ dst2 = reinterpret_cast<double2*>(dst);
-  for (int j = threadIdx.x; j < total2; j += kEvalBlock) {
-    const int row = j / (W / 2), c = 2 * (j - row * (W / 2));
-    const double* p = sm + row * STRIDE + c;
-    __stcs(dst2 + j, make_double2(p[0], p[1]));  // written once, never re-read by this kernel
+  // dst[row * W + c] = sm[row * STRIDE + c] for the CTA's `rows` observations; consecutive threads -> consecutive doubles:
+  // conflict-free 8-byte shared-memory reads (the rows are padded by one double) and 256 contiguous bytes per warp store.
+  // (16-byte stores were measured no faster: the odd row stride makes their shared-memory side 2-way conflicted.)
+  const int total = rows * W;
+  for (int j = threadIdx.x; j < total; j += kEvalBlock) {
+    const int row = j / W, c = j - row * W;
+    __stcs(dst + j, sm[row * STRIDE + c]);  // streaming store: written once, never re-read by this kernel
+  }
+}
+
+// camera block: Ceres' 2 x 17 row-major layout from the staged 2 x NC live columns
+template <int NC, int STRIDE>
+__device__ __forceinline__ void stream_out_camera(const double* __restrict__ sm, double* __restrict__ dst, int rows) {
+  const int total = rows * 34;
+  for (int j = threadIdx.x; j < total; j += kEvalBlock) {
+    const int row = j / 34, c = j - row * 34;
+    const int rr = c >= 17 ? 1 : 0, cc = c - 17 * rr;
+    __stcs(dst + j, cc < NC ? sm[row * STRIDE + rr * NC + cc] : 0.0);
   }
 }
 
@@ -63,6 +76,7 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
   __shared__ double sred[4 * 6];
   extern __shared__ double stage[];
   double* sC = stage;
+  constexpr int kStrideC = stride_c<NC>();
   double* sV = sC + kEvalBlock * kStrideC;
   double* sP = sV + kEvalBlock * kStrideV;
   double* sR = sP + kEvalBlock * kStrideP;
@@ -71,19 +85,40 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
   const int64_t i0 = blockIdx.x * (int64_t)kEvalBlock;
   const int64_t i = i0 + threadIdx.x;
   double ex2 = 0.0, ey2 = 0.0, mx = 0.0, my = 0.0, inl = 0.0, cost = 0.0;
+  // Cooperative gather of the 128-byte lens-table entries of the warp's 32 observations: 8 consecutive lanes fetch the
+  // 8 consecutive 16-byte chunks of ONE entry (4 lines per warp instruction instead of 32), the chunks are transposed
+  // to their owner through an XOR-swizzled shared-memory scratch (conflict-free both ways). The scratch lives in the
+  // warp's own part of the output staging area, which it only fills afterwards.
+  double ecoop[kLensStride];
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lid = i < d.N ? __ldcs(in.lens_id + i) : -1;
+    double2* scratch = reinterpret_cast<double2*>(sC + warp * 32 * kStrideC);  // 32 entries x 8 chunks
+    const double2* lens2 = reinterpret_cast<const double2*>(d.lens);
+    const int chunk = lane & 7, lane8 = lane & ~7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int src = lane8 + k;
+      const int lk = __shfl_sync(0xffffffffu, lid, src);
+      if (lk >= 0) scratch[src * 8 + (chunk ^ k)] = __ldg(lens2 + (size_t)lk * 8 + chunk);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double2 v2 = scratch[lane * 8 + (c ^ (lane & 7))];
+      ecoop[2 * c] = v2.x;
+      ecoop[2 * c + 1] = v2.y;
+    }
+    __syncwarp();
+  }
   if (i < d.N) {
     const double2 o = __ldcs(in.obs + i);
     const int p = __ldcs(in.point_idx + i), f = __ldcs(in.frame_idx + i);
     const double* fe = d.frames[which] + (size_t)f * kFrameStride;
     const double* X = d.points[which] + 3 * (size_t)p;
-    const double2* le = reinterpret_cast<const double2*>(d.lens + (size_t)__ldcs(in.lens_id + i) * kLensStride);
     double e[kLensStride];
 #pragma unroll
-    for (int k = 0; k < kLensStride / 2; ++k) {
-      const double2 v2 = __ldg(le + k);
-      e[2 * k] = v2.x;
-      e[2 * k + 1] = v2.y;
-    }
+    for (int k = 0; k < kLensStride; ++k) e[k] = ecoop[k];
     double Pc[3];
     track_point(fe, X, Pc);
     TrackCtx tc;
@@ -95,9 +130,7 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
     if (out.jac_camera) {
       double* jc = sC + threadIdx.x * kStrideC;
 #pragma unroll
-      for (int row = 0; row < 2; ++row)
-#pragma unroll
-        for (int c = 0; c < 17; ++c) jc[17 * row + c] = c < NC ? J[NC * row + c] : 0.0;
+      for (int k = 0; k < 2 * NC; ++k) jc[k] = J[k];
     }
     if (out.jac_view) {
       double* jv = sV + threadIdx.x * kStrideV;
@@ -149,7 +182,7 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
   __syncthreads();  // also orders the staging writes before the read-back
   const int rows = (int)(d.N - i0 < (int64_t)kEvalBlock ? d.N - i0 : (int64_t)kEvalBlock);
   stream_out<2, kStrideR>(sR, out.residuals + 2 * i0, rows);
-  if (out.jac_camera) stream_out<34, kStrideC>(sC, out.jac_camera + 34 * i0, rows);
+  if (out.jac_camera) stream_out_camera<NC, kStrideC>(sC, out.jac_camera + 34 * i0, rows);
   if (out.jac_view) stream_out<12, kStrideV>(sV, out.jac_view + 12 * i0, rows);
   if (out.jac_point) stream_out<6, kStrideP>(sP, out.jac_point + 6 * i0, rows);
   if (threadIdx.x < 6 && out.stats) {
@@ -169,26 +202,24 @@ void launch_tables_for(const Dev& d, int which, cudaStream_t s) {
 void launch_eval_only(const Dev& d, const EvalIn& in, const EvalOut& out, int which, cudaStream_t s) {
   if (d.N == 0) return;
   const unsigned grid = (unsigned)((d.N + kEvalBlock - 1) / kEvalBlock);
-  const size_t smem = (size_t)kEvalSmemDoubles * sizeof(double);
   static const bool prepared = [] {
-    const int b = kEvalSmemDoubles * (int)sizeof(double);
-    cudaFuncSetAttribute(k_eval_only<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    cudaFuncSetAttribute(k_eval_only<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    cudaFuncSetAttribute(k_eval_only<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    cudaFuncSetAttribute(k_eval_only<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    cudaFuncSetAttribute(k_eval_only<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    cudaFuncSetAttribute(k_eval_only<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    cudaFuncSetAttribute(k_eval_only<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<5>() * (int)sizeof(double));
+    cudaFuncSetAttribute(k_eval_only<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
+    cudaFuncSetAttribute(k_eval_only<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<6>() * (int)sizeof(double));
+    cudaFuncSetAttribute(k_eval_only<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<8>() * (int)sizeof(double));
+    cudaFuncSetAttribute(k_eval_only<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
+    cudaFuncSetAttribute(k_eval_only<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<9>() * (int)sizeof(double));
     return true;
   }();
   (void)prepared;
   const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
   switch (nrad * 2 + tang) {
-    case 0: k_eval_only<5, 0><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
-    case 1: k_eval_only<7, 0><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
-    case 2: k_eval_only<6, 1><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
-    case 3: k_eval_only<8, 1><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
-    case 4: k_eval_only<7, 2><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
-    default: k_eval_only<9, 2><<<grid, kEvalBlock, smem, s>>>(d, in, out, which); break;
+    case 0: k_eval_only<5, 0><<<grid, kEvalBlock, eval_smem_doubles<5>() * sizeof(double), s>>>(d, in, out, which); break;
+    case 1: k_eval_only<7, 0><<<grid, kEvalBlock, eval_smem_doubles<7>() * sizeof(double), s>>>(d, in, out, which); break;
+    case 2: k_eval_only<6, 1><<<grid, kEvalBlock, eval_smem_doubles<6>() * sizeof(double), s>>>(d, in, out, which); break;
+    case 3: k_eval_only<8, 1><<<grid, kEvalBlock, eval_smem_doubles<8>() * sizeof(double), s>>>(d, in, out, which); break;
+    case 4: k_eval_only<7, 2><<<grid, kEvalBlock, eval_smem_doubles<7>() * sizeof(double), s>>>(d, in, out, which); break;
+    default: k_eval_only<9, 2><<<grid, kEvalBlock, eval_smem_doubles<9>() * sizeof(double), s>>>(d, in, out, which); break;
   }
 }
 

@@ -78,7 +78,10 @@ __global__ void k_tables(Dev d) {
   if (st->done || st->eval_skip) return;
   const int cand = 1 - st->cur;
   __shared__ CamModel cm;
-  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+  if (threadIdx.x == 0) {
+    cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
+    if (blockIdx.x == 0 && d.cm_buf) *d.cm_buf = cm;  // -> __constant__ memory of the evaluation kernel (launch_eval)
+  }
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < d.NL) {

@@ -27,6 +27,13 @@
 
 namespace lfba {
 
+// Camera model of the candidate parameters in CONSTANT memory: k_tables computes it on the device, launch_eval_rows copies
+// it here device-to-device on the solver's stream right before the kernel. Every use becomes a constant-bank operand of
+// the FP64 instruction itself instead of a shared-memory load with ~30 cycles of exposed latency (two warps per
+// scheduler cannot hide those) and the registers that cached the hot fields are free again.
+// One evaluation per device at a time (one solver stream): concurrent solvers on the SAME device would share it.
+__constant__ CamModel c_cam;
+
 constexpr int kLensRow = 33;  // double2 per chunk row of the shared lens tile: 32 lanes + 1 pad (bank spread)
 
 template <int NV>
@@ -71,14 +78,13 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   constexpr int NF9 = Feat9Dims<NC>::NF, NQ9 = Feat9Dims<NC>::NQ, NG9 = Feat9Dims<NC>::NG;
   constexpr int NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
   typedef GramMap<NC> GM;
-  __shared__ CamModel cm;
+  const CamModel& cm = c_cam;
   __shared__ double red[4 * NV];
   extern __shared__ double dyn[];
   double* pers = dyn;                                              // [NVL][128]
   double2* tiles = reinterpret_cast<double2*>(dyn + NVL * 128);    // [4 warps][2][8][kLensRow]
   double2* ring_o = tiles + 4 * 2 * 8 * kLensRow;                  // [4 warps][3][32] observations of rows s, s+1, s+2
   int32_t* ring_l = reinterpret_cast<int32_t*>(ring_o + 4 * 3 * 32);  // [4 warps][3][32] their lens ids
-  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
 #pragma unroll
   for (int v = 0; v < NVL; ++v) pers[v * 128 + threadIdx.x] = 0.0;
   __syncthreads();
@@ -155,20 +161,26 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
     for (int m = 0; m < nsteps; ++m) {
       __pipeline_wait_prior(0);  // this lane's copies for rows row (lens) and row + 1 (observation) have landed ...
       __syncwarp();              // ... and so have everybody else's; nobody still reads what is refilled next
-      gather_row(row + 1 < row_end ? my_l[((row + 1) % 3) * 32] : -1, tile + ((row + 1) & 1) * (8 * kLensRow));
-      fetch_row(row + 2);
-      __pipeline_commit();
+      // Read everything this step needs from shared memory BEFORE queueing the next copies: the load/store unit is in
+      // order, an LDS issued behind the ten LDGSTS below would wait for all of them (measured: 10% of the kernel on
+      // the first use of lid_c).
       const int lid_c = my_l[(row % 3) * 32];
-      if (lid_c >= 0) {
-        const double2 o_c = my_o[(row % 3) * 32];
+      const int lid_next = row + 1 < row_end ? my_l[((row + 1) % 3) * 32] : -1;
+      const double2 o_c = my_o[(row % 3) * 32];
+      double e[kLensStride];
+      {
         const double2* lp = tile + (row & 1) * (8 * kLensRow) + lane;
-        double e[kLensStride];
 #pragma unroll
         for (int k = 0; k < kLensStride / 2; ++k) {
           const double2 v2 = lp[k * kLensRow];
           e[2 * k] = v2.x;
           e[2 * k + 1] = v2.y;
         }
+      }
+      gather_row(lid_next, tile + ((row + 1) & 1) * (8 * kLensRow));
+      fetch_row(row + 2);
+      __pipeline_commit();
+      if (lid_c >= 0) {
         double rr[2], F[2 * NF9];
         obs_features9<NC, NRAD>(cm, tc, e, o_c.x, o_c.y, rr, F);
         const double s = rr[0] * rr[0] + rr[1] * rr[1];
@@ -300,6 +312,7 @@ void prepare_rows_kernels() {
 }
 
 void launch_eval_rows(const Dev& d, int L, cudaStream_t s) {
+  cudaMemcpyToSymbolAsync(c_cam, d.cm_buf, sizeof(CamModel), 0, cudaMemcpyDeviceToDevice, s);
   const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
   switch (nrad * 2 + tang) {
     case 0: launch_rows_nc<5, 0>(d, L, d.grid_eval, s); break;

@@ -118,6 +118,7 @@ struct Solver {
   DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one NCCL all-reduce)
   DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step;
   DevBuf<unsigned long long> lens_dev;
+  DevBuf<CamModel> cm_buf;
   DevBuf<LmState> st;
   DevBuf<lfba_iteration> log;
   size_t S_len = 0, red_len = 0;
@@ -339,6 +340,8 @@ struct Solver {
     log.alloc(kMaxLog);
     lens_dev.alloc(1);
     lens_dev.zero(stream);
+    cm_buf.alloc(1);
+    cm_buf.zero(stream);
 
     // ---- launch geometry ----
     const int sms = prop.multiProcessorCount;
@@ -397,7 +400,7 @@ struct Solver {
       d.camera[b] = camera[b].p; d.views[b] = views[b].p; d.points[b] = points[b].p;
       d.frames[b] = frames[b].p; d.rec[b] = rec[b].p; d.camsum[b] = camsum[b].p;
     }
-    d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.lens_dev = lens_dev.p;
+    d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.lens_dev = lens_dev.p; d.cm_buf = cm_buf.p;
     // measured on B200: the implicit form (fewer gathered bytes, ~75 more FP64 ops) is slower than the table: opt-in only
     d.implicit_tol = std::getenv("LFBA_IMPLICIT_TOL") ? std::atof(std::getenv("LFBA_IMPLICIT_TOL")) : -1.0; d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p;
     d.S = redbuf.p; d.row_off = row_off.p; d.row_c0 = row_c0.p;
