@@ -34,8 +34,8 @@ if ROOT not in sys.path:
 
 # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the ncu --set full
 # capture of the same build (profiles/README.md); None where no capture exists for that workload
-NCU_TRAFFIC = {}
-FP64_INST_PER_OBS = 330.0
+NCU_TRAFFIC = {"cfg4": 3.99e9}  # 2.87 GB read + 1.12 GB written per launch (r01_prof_cfg4_v4.ncu-rep)
+FP64_INST_PER_OBS = 263.0  # ncu source counters of k_eval_rows<9,2,1> (profiles/README.md): loop + per-track part / N
 METRIC = "lm_residual_jacobian_evals_per_s"
 UNIT = "M evals/s"
 WORKLOADS = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4}
@@ -305,7 +305,7 @@ def main():
                 "achieved": alg_bytes / (eval_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_bytes / (eval_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.workload),
                 "peak_source": peak_src, "ms_per_launch": eval_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "this kernel is FP64-pipe bound by design (30 B/observation of HBM traffic against ~330 FP64 "
+                "note": "this kernel is FP64-pipe bound by design (30 B/observation of HBM traffic against 263 FP64 "
                         "instructions): its fraction of the HBM roof is small on purpose; see fp64 for the pipe "
                         "utilisation and roofline_eval_only for the HBM-bound kernel that materialises the Jacobian"}
     extra = {}

@@ -1,6 +1,7 @@
 // lfba_setup.cu — device-side indexing of the observations (see lfba_setup.cuh).
 #include "lfba_setup.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -478,20 +479,23 @@ __global__ void k_round_steps(const int32_t* eval_order, const int32_t* trk_begi
   const int t = eval_order[(size_t)r * G];  // tracks are in descending length order: the first is the longest
   steps[r] = (trk_begin[t + 1] - trk_begin[t] + L - 1) / L;
 }
+// round of every row: thread r marks the rows [step_base[r], step_base[r + 1]) (a handful each)
+__global__ void k_row_rounds(const int32_t* __restrict__ step_base, int32_t* __restrict__ row_round, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  for (int row = step_base[r]; row < step_base[r + 1]; ++row) row_round[row] = r;
+}
 __global__ void k_fill_stream(const int32_t* __restrict__ eval_order, const int32_t* __restrict__ trk_begin,
-                              const int32_t* __restrict__ step_base, const double2* __restrict__ obs,
-                              const int32_t* __restrict__ lens_id, double2* __restrict__ s_obs,
-                              int32_t* __restrict__ s_lid, int T, int G, int L, int R, int64_t n_entries) {
+                              const int32_t* __restrict__ step_base, const int32_t* __restrict__ row_round,
+                              const double2* __restrict__ obs, const int32_t* __restrict__ lens_id,
+                              double2* __restrict__ s_obs, int32_t* __restrict__ s_lid, int T, int G, int L,
+                              int64_t n_entries) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n_entries) return;
   const int row = (int)(e >> 5), lane = (int)(e & 31);
-  int lo = 0, hi = R;  // largest round with step_base[round] <= row
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (step_base[mid] <= row) lo = mid; else hi = mid;
-  }
-  const int m = row - step_base[lo];
-  const int pos = lo * G + lane / L;
+  const int r = row_round[row];
+  const int m = row - step_base[r];
+  const int pos = r * G + lane / L;
   double2 o = make_double2(0.0, 0.0);
   int lid = -1;
   if (pos < T) {
@@ -532,9 +536,12 @@ void build_stream(ProblemIndex& ix, int L, cudaStream_t s, int64_t* launches) {
   const int64_t n_entries = (int64_t)rows * 32;
   ix.s_obs.alloc((size_t)n_entries);
   ix.s_lid.alloc((size_t)n_entries);
-  k_fill_stream<<<grid_for(n_entries), 256, 0, s>>>(ix.eval_order.p, ix.trk_begin.p, ix.step_base.p, ix.obs_sorted,
-                                                      ix.lens_id_sorted, ix.s_obs.p, ix.s_lid.p, ix.T, G, L, R, n_entries);
-  if (launches) *launches += 3;
+  DevBuf<int32_t> row_round((size_t)std::max(1, rows));
+  k_row_rounds<<<grid_for(R), 256, 0, s>>>(ix.step_base.p, row_round.p, R);
+  k_fill_stream<<<grid_for(n_entries), 256, 0, s>>>(ix.eval_order.p, ix.trk_begin.p, ix.step_base.p, row_round.p,
+                                                      ix.obs_sorted, ix.lens_id_sorted, ix.s_obs.p, ix.s_lid.p, ix.T, G, L,
+                                                      n_entries);
+  if (launches) *launches += 4;
 }
 
 }  // namespace lfba
