@@ -22,6 +22,37 @@
 
 namespace lfba {
 
+#if defined(__CUDACC__)
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256). A lane that reads or writes ITS OWN record (track record,
+// point data) touches one 32-byte sector per instruction instead of half or a quarter of it: fewer L1 wavefronts on the
+// read side, no partially filled sectors towards L2 on the write side. The address must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const double* p, double* out) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(out[0]), "=d"(out[1]), "=d"(out[2]), "=d"(out[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// N doubles of a record at p: 256-bit loads when the caller guarantees 32-byte alignment of p and N % 4 == 0 (ALIGN32),
+// else 128-bit (N even, 16-byte aligned), else scalar
+template <int N, bool ALIGN32>
+__device__ __forceinline__ void load_record(const double* __restrict__ p, double* out) {
+  if (ALIGN32 && N % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k) ldg256(p + 4 * k, out + 4 * k);
+  } else if (N % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      const double2 v2 = __ldg(reinterpret_cast<const double2*>(p) + k);
+      out[2 * k] = v2.x;
+      out[2 * k + 1] = v2.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = __ldg(p + k);
+  }
+}
+#endif
+
 constexpr int kPointStride = 40;  // pdata: Hinv(6) gp(3) dmp(3) Hcp(3*NC<=27) pad
 constexpr int kVWStride = 36;     // vw: V(18: 6x3 row-major) W(18)
 constexpr int kMaxLog = 1024;

@@ -1004,7 +1004,9 @@ __global__ void __launch_bounds__(128) k_points(Dev d) {
 #pragma unroll
     for (int k = 0; k < 3 * NC; ++k) Hcp[k] = 0.0;
     for (int t = d.pt_trk_begin[p]; t < d.pt_trk_begin[p + 1]; ++t) {
-      const double* rc = recs + (size_t)t * RS;
+      // a lane reads ITS track record (288 B for NC = 9): wide loads cut the L1 wavefronts of this strided access
+      double rc[RS + 3];
+      load_record<RS, RS % 4 == 0>(recs + (size_t)t * RS, rc);
       const double* R = frames + (size_t)d.trk_frame[t] * kFrameStride;
       const double A[6] = {rc[0], rc[1], rc[2], rc[3], rc[4], rc[5]};
       double AR[9];
@@ -1713,7 +1715,8 @@ __global__ void __launch_bounds__(128) k_point_step(Dev d) {
   const double* __restrict__ y = d.y;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.P; p += gridDim.x * blockDim.x) {
     if (!d.pt_active[p] || d.pt_coupled[p] >= 0) continue;
-    const double* pd = d.pdata + (size_t)p * kPointStride;
+    double pd[kPointStride];
+    load_record<kPointStride, true>(d.pdata + (size_t)p * kPointStride, pd);  // 320-byte records, 32-byte aligned
     double h[3] = {0, 0, 0};
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -1725,7 +1728,16 @@ __global__ void __launch_bounds__(128) k_point_step(Dev d) {
     }
     if (d.refine_poses) {
       for (int t = d.pt_trk_begin[p]; t < d.pt_trk_begin[p + 1]; ++t) {
-        const double* V = d.vw + (size_t)t * kVWStride;
+        double V[18];
+        {
+          const double2* V2 = reinterpret_cast<const double2*>(d.vw + (size_t)t * kVWStride);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            const double2 v2 = __ldg(V2 + k);
+            V[2 * k] = v2.x;
+            V[2 * k + 1] = v2.y;
+          }
+        }
         const double* yf = y + 6 * d.trk_frame[t];
 #pragma unroll
         for (int a = 0; a < 6; ++a) {

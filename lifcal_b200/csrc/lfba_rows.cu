@@ -224,26 +224,51 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
       gram9_expand<NC>(tc, tc.a1 * cm.gamma, g, go);
       const double* h = go + NQ;
       double* dst = recs + (size_t)t * RS;
-      int v = 0;
+      if (L == 1 && RS % 2 == 0) {
+        // one lane owns the whole record: 256-bit (or 128-bit) stores instead of 8-byte ones, which reached L2 as 4.6 GB of
+        // partially filled sectors for 1.15 GB of records (ncu l1tex__m_l1tex2xbar_write_bytes); measured -10% kernel time
+        double rec_[RS];
+        int v = 0;
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = i; j < 3; ++j) {
-          if ((v % L) == lig) dst[v] = GM::gg(tc, go, i, j);
+          for (int j = i; j < 3; ++j) rec_[v++] = GM::gg(tc, go, i, j);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rec_[v++] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) rec_[v++] = GM::gcam(tc, go, i, c);
+        if (RS % 4 == 0) {  // records are 32-byte aligned: one full sector per store
+#pragma unroll
+          for (int k = 0; k < RS / 4; ++k) stg256(dst + 4 * k, rec_[4 * k], rec_[4 * k + 1], rec_[4 * k + 2], rec_[4 * k + 3]);
+        } else {
+          double2* dst2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+          for (int k = 0; k < RS / 2; ++k) dst2[k] = make_double2(rec_[2 * k], rec_[2 * k + 1]);
+        }
+      } else {
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = i; j < 3; ++j) {
+            if ((v % L) == lig) dst[v] = GM::gg(tc, go, i, j);
+            ++v;
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if ((v % L) == lig) dst[v] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
           ++v;
         }
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if ((v % L) == lig) dst[v] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
-        ++v;
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if ((v % L) == lig) dst[v] = GM::gcam(tc, go, i, c);
+            ++v;
+          }
       }
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          if ((v % L) == lig) dst[v] = GM::gcam(tc, go, i, c);
-          ++v;
-        }
       int hh = 0;
 #pragma unroll
       for (int c1 = 0; c1 < NC; ++c1)
