@@ -34,6 +34,12 @@ namespace lfba {
 // One evaluation per device at a time (one solver stream): concurrent solvers on the SAME device would share it.
 __constant__ CamModel c_cam;
 
+// 16-byte cp.async that ALLOCATES IN L1 (the __pipeline_memcpy_async form is .cg = L2 only): the evaluation order keeps
+// tracks of the same image neighbourhood together, so most lens-table lines a warp gathers were fetched a moment ago.
+__device__ __forceinline__ void cp_async_ca16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
 constexpr int kLensRow = 33;  // double2 per chunk row of the shared lens tile: 32 lanes + 1 pad (bank spread)
 
 template <int NV>
@@ -73,7 +79,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   constexpr int G = 32 / L;
   constexpr int NH = NC * (NC + 1) / 2;
   constexpr int NV = NH + NC + 1;
-  constexpr int NVL = (NV + L - 1) / L;  // camera-block totals a lane owns: entries v with v % L == lane % L
+  constexpr int NVL = L == 1 ? 0 : (NV + L - 1) / L;  // L > 1: camera-block totals a lane owns (entries v with v % L == lane % L)
   constexpr int RS = 9 + 3 * NC;
   constexpr int NF9 = Feat9Dims<NC>::NF, NQ9 = Feat9Dims<NC>::NQ, NG9 = Feat9Dims<NC>::NG;
   constexpr int NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   const bool robust = cm.robust != 0;
   const double loss_c = cm.loss_c, half_b = 0.5 * cm.loss_b;
   double cost = 0.0;
+  double camacc[2] = {0.0, 0.0};  // L == 1: this lane's two entries of the camera block (see the end of a round)
 
   // this warp's rounds: an even split of the rows, aligned to round boundaries
   const int R = d.n_rounds;
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
     for (int k = 0; k < 8; ++k) {
       const int src = lane8 + k;
       const int lk = __shfl_sync(0xffffffffu, lid, src);
-      if (lk >= 0) __pipeline_memcpy_async(buf + chunk * kLensRow + src, lens2 + (size_t)lk * 8 + chunk, 16);
+      if (lk >= 0) cp_async_ca16(buf + chunk * kLensRow + src, lens2 + (size_t)lk * 8 + chunk);
     }
   };
 
@@ -217,6 +224,11 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
 #pragma unroll
         for (int o = L / 2; o > 0; o >>= 1) g[v] += __shfl_xor_sync(0xffffffffu, g[v], o);
     }
+    double cv[L == 1 ? NV - 1 : 1];  // L == 1: camera-block contribution of this lane's track (zero for an idle lane)
+    if constexpr (L == 1) {
+#pragma unroll
+      for (int v = 0; v < NV - 1; ++v) cv[v] = 0.0;
+    }
     if (valid) {
       // rebuild the sums that involve f2, then expand into the track record and the camera block; the entries are
       // split over the L lanes of the group
@@ -269,41 +281,101 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
             ++v;
           }
       }
-      int hh = 0;
+      if constexpr (L > 1) {
+        int hh = 0;
 #pragma unroll
-      for (int c1 = 0; c1 < NC; ++c1)
+        for (int c1 = 0; c1 < NC; ++c1)
 #pragma unroll
-        for (int c2 = 0; c2 <= c1; ++c2) {
-          if ((hh % L) == lig) pers[(hh / L) * 128 + threadIdx.x] += GM::cc(tc, go, c1, c2);
-          ++hh;
+          for (int c2 = 0; c2 <= c1; ++c2) {
+            if ((hh % L) == lig) pers[(hh / L) * 128 + threadIdx.x] += GM::cc(tc, go, c1, c2);
+            ++hh;
+          }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (((NH + c) % L) == lig) {
+            double gcv;
+            if (c < 3) {
+              double a, b;
+              GM::geo(tc, c, a, b);
+              gcv = a * h[3] + b * h[2];
+            } else {
+              gcv = h[c + 1];
+            }
+            pers[((NH + c) / L) * 128 + threadIdx.x] += gcv;
+          }
         }
+      } else {
+        int hh = 0;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        if (((NH + c) % L) == lig) {
-          double gcv;
+        for (int c1 = 0; c1 < NC; ++c1)
+#pragma unroll
+          for (int c2 = 0; c2 <= c1; ++c2) cv[hh++] = GM::cc(tc, go, c1, c2);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
           if (c < 3) {
             double a, b;
             GM::geo(tc, c, a, b);
-            gcv = a * h[3] + b * h[2];
+            cv[NH + c] = a * h[3] + b * h[2];
           } else {
-            gcv = h[c + 1];
+            cv[NH + c] = h[c + 1];
           }
-          pers[((NH + c) / L) * 128 + threadIdx.x] += gcv;
         }
+      }
+    }
+    if constexpr (L == 1) {
+      // Camera block (Hcc, gc): the 32 tracks of the round are summed by a reduce-scatter butterfly over the warp, in two
+      // chunks of 32 values; lane l ends up with entries brev5(l) and 32 + brev5(l), which it keeps in two registers for
+      // the whole kernel. (This replaced a 66 KB per-thread shared-memory accumulator: the freed space is L1 for the
+      // lens gather.) Fixed order: deterministic.
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (32 * ch + i < NV - 1) ? cv[32 * ch + i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int half = 16 >> k;
+          const bool up = (lane >> k) & 1;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << k);
+          }
+        }
+        camacc[ch] += v[0];
       }
     }
   }
   __pipeline_wait_prior(0);
-  double acc[NV];
+  if constexpr (L == 1) {
+    __shared__ double wsum[4][64];
+    __shared__ double wcost[4];
+    const int br = ((lane & 1) << 4) | ((lane & 2) << 2) | (lane & 4) | ((lane & 8) >> 2) | ((lane & 16) >> 4);
+    wsum[warp][br] = camacc[0];
+    wsum[warp][32 + br] = camacc[1];
+    double c = cost;
 #pragma unroll
-  for (int v = 0; v < NV - 1; ++v) acc[v] = (v % L) == lig ? pers[(v / L) * 128 + threadIdx.x] : 0.0;
-  acc[NV - 1] = cost;
-  block_reduce_store_rows<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) wcost[warp] = c;
+    __syncthreads();
+    for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+      double s_ = 0.0;
+      for (int w = 0; w < 4; ++w) s_ += v < NV - 1 ? wsum[w][v] : wcost[w];
+      d.part_eval[(size_t)blockIdx.x * 64 + v] = s_;
+    }
+  } else {
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV - 1; ++v) acc[v] = (v % L) == lig ? pers[(v / L) * 128 + threadIdx.x] : 0.0;
+    acc[NV - 1] = cost;
+    block_reduce_store_rows<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
+  }
 }
 
 template <int NC, int L>
 constexpr int rows_smem_bytes() {
-  return (((NC * (NC + 1) / 2 + NC + 1) + L - 1) / L) * 128 * (int)sizeof(double) + 4 * 2 * 8 * kLensRow * (int)sizeof(double2) +
+  return (L == 1 ? 0 : ((NC * (NC + 1) / 2 + NC + 1) + L - 1) / L) * 128 * (int)sizeof(double) + 4 * 2 * 8 * kLensRow * (int)sizeof(double2) +
          4 * 3 * 32 * ((int)sizeof(double2) + (int)sizeof(int32_t));
 }
 

@@ -135,9 +135,22 @@ __global__ void k_iota(int32_t* a, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = i;
 }
-__global__ void k_track_len(const int32_t* trk_begin, int32_t* len, int T) {
+// Sort key of the evaluation order: track length (so that the tracks of a warp round have the same number of steps),
+// then the image cell of the track's first micro lens (64 x 64 px cells, row-major): tracks that are neighbours in the
+// order gather largely the SAME lens-table entries, which the L1-allocating cp.async of k_eval_rows turns into hits.
+__global__ void k_track_len(const int32_t* trk_begin, const int32_t* __restrict__ lens_id, const double* __restrict__ lens_xy,
+                            int32_t* len, int T) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < T) len[t] = trk_begin[t + 1] - trk_begin[t];
+  if (t >= T) return;
+  const int b = trk_begin[t], n = trk_begin[t + 1] - b;
+  int cell = 0;
+  if (n > 0 && lens_id && lens_xy) {
+    const int l = lens_id[b];
+    const int cx = min(63, max(0, (int)(lens_xy[2 * l] * (1.0 / 64.0))));
+    const int cy = min(63, max(0, (int)(lens_xy[2 * l + 1] * (1.0 / 64.0))));
+    cell = cy * 64 + ((cy & 1) ? 63 - cx : cx);  // boustrophedon: the end of a cell row is next to the start of the next
+  }
+  len[t] = (min(n, (1 << 19) - 1) << 12) | cell;
 }
 __global__ void k_pair_counts(const int32_t* pt_trk_begin, int32_t* cnt, int P) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,7 +422,7 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
     DevBuf<int32_t> iota(T), keys_out(T), len(T);
     k_iota<<<grid_for(T), 256, 0, s>>>(iota.p, T);
     sort_pairs(tmp, ix.trk_frame.p, keys_out.p, iota.p, ix.frm_trk.p, (size_t)T, s, bits_for((uint64_t)(F > 0 ? F - 1 : 0)));
-    k_track_len<<<grid_for(T), 256, 0, s>>>(ix.trk_begin.p, len.p, T);
+    k_track_len<<<grid_for(T), 256, 0, s>>>(ix.trk_begin.p, ix.lens_id_sorted, ix.lens_xy.p, len.p, T);
     sort_pairs(tmp, len.p, keys_out.p, iota.p, ix.eval_order.p, (size_t)T, s, 32, true);
     nl += 6;
   }
