@@ -1239,8 +1239,11 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
     // the pose block is done, so that they are not live across it (255 registers: 93 accumulators + one track)
     const double* rcp = recs + (size_t)t * RS;
     const double2* pd2 = reinterpret_cast<const double2*>(d.pdata + (size_t)p * kPointStride);
-    double rc[10], pd[10];
-    if (RS % 2 == 0) {  // records are 16-byte aligned: 128-bit loads
+    double rc[12], pd[12];
+    if (RS % 4 == 0) {  // records are 32-byte aligned: 256-bit loads (one sector per instruction and lane)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ldg256(rcp + 4 * k, rc + 4 * k);
+    } else if (RS % 2 == 0) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const double2 v2 = __ldg(reinterpret_cast<const double2*>(rcp) + k);
@@ -1252,11 +1255,7 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
       for (int k = 0; k < 10; ++k) rc[k] = __ldg(rcp + k);
     }
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const double2 v2 = __ldg(pd2 + k);
-      pd[2 * k] = v2.x;
-      pd[2 * k + 1] = v2.y;
-    }
+    for (int k = 0; k < 3; ++k) ldg256(d.pdata + (size_t)p * kPointStride + 4 * k, pd + 4 * k);  // 320-byte records
     const double A[6] = {rc[0], rc[1], rc[2], rc[3], rc[4], rc[5]};
     const double b[3] = {rc[6], rc[7], rc[8]};
     double m[9];
@@ -1290,11 +1289,16 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
       for (int j = 0; j < 3; ++j) V[3 * a + j] = Mt(a, 0) * AR[j] + Mt(a, 1) * AR[3 + j] + Mt(a, 2) * AR[6 + j];
       sym3_vec(Hi, V + 3 * a, W + 3 * a);
     }
-    double2* vw2 = reinterpret_cast<double2*>(d.vw + (size_t)t * kVWStride);
+    {  // V | W: 288 bytes, 32-byte aligned
+      double* vwp = d.vw + (size_t)t * kVWStride;
+      double vwv[36];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      vw2[k] = make_double2(V[2 * k], V[2 * k + 1]);
-      vw2[9 + k] = make_double2(W[2 * k], W[2 * k + 1]);
+      for (int k = 0; k < 18; ++k) {
+        vwv[k] = V[k];
+        vwv[18 + k] = W[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) stg256(vwp + 4 * k, vwv[4 * k], vwv[4 * k + 1], vwv[4 * k + 2], vwv[4 * k + 3]);
     }
     const double gp[3] = {pd[6], pd[7], pd[8]};
     {
@@ -1317,7 +1321,15 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
     {
       double cc[3 * NC + 1], hc[3 * NC + 1 + ((3 * NC + 1) & 1)];  // cc[0] = rc[9]; hc = pd[12 ..]
       cc[0] = rc[9];
-      if (RS % 2 == 0) {
+      if (RS % 4 == 0) {
+        cc[1] = rc[10];
+        cc[2] = rc[11];
+        double tmp[RS - 12 + 4];
+#pragma unroll
+        for (int k = 3; k < RS / 4; ++k) ldg256(rcp + 4 * k, tmp + 4 * (k - 3));
+#pragma unroll
+        for (int k = 12; k < RS; ++k) cc[k - 9] = tmp[k - 12];
+      } else if (RS % 2 == 0) {
 #pragma unroll
         for (int k = 5; k < RS / 2; ++k) {
           const double2 v2 = __ldg(reinterpret_cast<const double2*>(rcp) + k);
@@ -1328,11 +1340,12 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
 #pragma unroll
         for (int k = 10; k < RS; ++k) cc[k - 9] = __ldg(rcp + k);
       }
+      {  // Hcp = pd[12 ..]: 7 x 256 bit
+        double tmp[28];
 #pragma unroll
-      for (int k = 0; k < (3 * NC + 1) / 2; ++k) {
-        const double2 v2 = __ldg(pd2 + 6 + k);
-        hc[2 * k] = v2.x;
-        hc[2 * k + 1] = v2.y;
+        for (int k = 0; k < 7; ++k) ldg256(d.pdata + (size_t)p * kPointStride + 12 + 4 * k, tmp + 4 * k);
+#pragma unroll
+        for (int k = 0; k < 3 * NC + 1; ++k) hc[k] = tmp[k];
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
@@ -1434,17 +1447,23 @@ __global__ void __launch_bounds__(128) k_pairs(Dev d) {
 #pragma unroll
   for (int v = 0; v < 36; ++v) acc[v] = 0.0;
   for (int i = d.pair_begin[warp] + lane; i < d.pair_begin[warp + 1]; i += 32) {
-    const double2* W = reinterpret_cast<const double2*>(d.vw + (size_t)d.pair_t1[i] * kVWStride + 18);
-    const double2* V = reinterpret_cast<const double2*>(d.vw + (size_t)d.pair_t2[i] * kVWStride);
+    // V = first 144 bytes of a 288-byte record (32-byte aligned), W = the second half (16 mod 32): 256-bit loads where
+    // the alignment allows, one 128-bit load at the odd end
+    const double* Vp = d.vw + (size_t)d.pair_t2[i] * kVWStride;
+    const double* Wp = d.vw + (size_t)d.pair_t1[i] * kVWStride + 18;
     double w[18], v[18];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {  // 144-byte halves of a 288-byte record: 16-byte aligned
-      const double2 a = __ldg(W + k), b = __ldg(V + k);
-      w[2 * k] = a.x;
-      w[2 * k + 1] = a.y;
-      v[2 * k] = b.x;
-      v[2 * k + 1] = b.y;
+    for (int k = 0; k < 4; ++k) ldg256(Vp + 4 * k, v + 4 * k);
+    {
+      const double2 t2 = __ldg(reinterpret_cast<const double2*>(Vp + 16));
+      v[16] = t2.x;
+      v[17] = t2.y;
+      const double2 t3 = __ldg(reinterpret_cast<const double2*>(Wp));
+      w[0] = t3.x;
+      w[1] = t3.y;
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ldg256(Wp + 2 + 4 * k, w + 2 + 4 * k);
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
