@@ -34,8 +34,8 @@ if ROOT not in sys.path:
 
 # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the ncu --set full
 # capture of the same build (profiles/README.md); None where no capture exists for that workload
-NCU_TRAFFIC = {"cfg4": 3.99e9}  # 2.87 GB read + 1.12 GB written per launch (r01_prof_cfg4_v4.ncu-rep)
-FP64_INST_PER_OBS = 263.0  # ncu source counters of k_eval_rows<9,2,1> (profiles/README.md): loop + per-track part / N
+NCU_TRAFFIC = {"cfg4": 4.397e9}  # 3.262 GB read + 1.135 GB written per launch (profiles/r01_ncu_k_eval_rows_cfg4.txt)
+FP64_INST_PER_OBS = 262.4  # ncu source counters of k_eval_rows<9,2,1> (profiles/README.md): loop + per-track part / N
 METRIC = "lm_residual_jacobian_evals_per_s"
 UNIT = "M evals/s"
 WORKLOADS = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4}
@@ -318,6 +318,7 @@ def main():
                                            "achieved": mat_bytes / (mat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                            "frac": mat_bytes / (mat_ms * 1e-3) / 1e9 / peak, "ms_per_launch": mat_ms,
                                            "algorithmic_bytes_per_launch": mat_bytes,
+                                           "traffic": 5.1557e10 if args.workload == "cfg4" else None,  # ncu: 3.17 GB read + 48.39 GB written
                                            "m_evals_per_s": n_local / (mat_ms * 1e-3) / 1e6}
             fp64 = api.measure_fp64_peak(local_rank)
             # FP64 instructions per observation of the fused kernel, from the ncu source counters of the same build
