@@ -168,6 +168,7 @@ struct Dev {
   double* pdata;
   double* pscale;      // [3P] Jacobi scale of the point columns
   double* vw;
+  double* frame_part;  // [F * frame_splits * (39 + 6 NC)] partial sums of k_frame_all when frames are split over CTAs
   // reduced system
   double* S;           // skyline storage
   const int64_t* row_off;  // [n+2]

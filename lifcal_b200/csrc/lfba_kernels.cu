@@ -1212,6 +1212,29 @@ __global__ void __launch_bounds__(128) k_frame_pose(Dev d) {
 
 // Per frame, ONE pass over the frame's tracks (k_frame_pose + k_frame_cam fused: the track record, the point data and
 // W are read once, W never round-trips through HBM): pose diagonal block, pose gradient, camera-pose block.
+// entry v of k_frame_all's per-frame sums -> its place in the reduced system
+template <int NC>
+__device__ __forceinline__ void frame_all_scatter(const Dev& d, int f, int v, double sv) {
+  constexpr int NP = 21 + 6 + 6 + 6;
+  double* dst = nullptr;
+  if (v < 21) {
+    int a = 0, h = v;
+    while (h > a) { h -= a + 1; ++a; }
+    dst = S_at(d, 6 * f + a, 6 * f + h);
+  } else if (v < 27) {
+    dst = d.g + 6 * f + (v - 21);
+  } else if (v < 33) {
+    dst = d.gfull + 6 * f + (v - 27);
+  } else if (v < NP) {
+    dst = d.hdiag + 6 * f + (v - 33);
+  } else {
+    const int c = (v - NP) / 6, a = (v - NP) % 6;
+    const int r = d.cam_red[c];
+    if (r >= 0) dst = S_at(d, r, 6 * f + a);
+  }
+  if (dst) *dst += sv;
+}
+
 template <int NC>
 __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
   LmState* st = d.st;
@@ -1362,28 +1385,23 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
   }
   block_reduce_store<NV>(acc, out, red);
   if (threadIdx.x < NV) {
-    const int v = threadIdx.x;
-    const double sv = out[v];
-    double* dst = nullptr;
-    if (v < 21) {
-      int a = 0, h = v;
-      while (h > a) { h -= a + 1; ++a; }
-      dst = S_at(d, 6 * f + a, 6 * f + h);
-    } else if (v < 27) {
-      dst = d.g + 6 * f + (v - 21);
-    } else if (v < 33) {
-      dst = d.gfull + 6 * f + (v - 27);
-    } else if (v < NP) {
-      dst = d.hdiag + 6 * f + (v - 33);
-    } else {
-      const int c = (v - NP) / 6, a = (v - NP) % 6;
-      const int r = d.cam_red[c];
-      if (r >= 0) dst = S_at(d, r, 6 * f + a);
-    }
-    if (dst) {
-      if (nsplit == 1) *dst += sv; else atomicAdd(dst, sv);
-    }
+    if (nsplit == 1) frame_all_scatter<NC>(d, f, threadIdx.x, out[threadIdx.x]);
+    else d.frame_part[((size_t)f * nsplit + split) * NV + threadIdx.x] = out[threadIdx.x];  // summed by k_frame_finish
   }
+}
+
+// Second stage when a frame is split over several CTAs (few active frames per rank: multi-GPU shards): the partial sums
+// are added in split order — no atomics, the same bits every run.
+template <int NC>
+__global__ void __launch_bounds__(128) k_frame_finish(Dev d, int nsplit) {
+  LmState* st = d.st;
+  if (st->done) return;
+  constexpr int NV = 21 + 6 + 6 + 6 + 6 * NC;
+  const int f = blockIdx.x, v = threadIdx.x;
+  if (v >= NV) return;
+  double sv = 0.0;
+  for (int sp = 0; sp < nsplit; ++sp) sv += d.frame_part[((size_t)f * nsplit + sp) * NV + v];
+  frame_all_scatter<NC>(d, f, v, sv);
 }
 
 // Per frame: camera-pose block S[cam, f] = sum_t (C_t^T M_t - Hcp W_t^T).
@@ -1438,15 +1456,16 @@ __global__ void __launch_bounds__(128) k_frame_cam(Dev d) {
 }
 
 // Per co-visible frame pair (f1 > f2), one warp: S[f1, f2] = -sum_p W_{p,f1} V_{p,f2}^T.
-__global__ void __launch_bounds__(128) k_pairs(Dev d) {
+__global__ void __launch_bounds__(256) k_pairs(Dev d) {
   LmState* st = d.st;
   if (st->done) return;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= d.npairs) return;
+  // one CTA per pair, 1..8 warps (the launcher picks the width so that a rank with few pairs still fills the machine)
+  const int pair = blockIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ double sred[8][36];
   double acc[36];
 #pragma unroll
   for (int v = 0; v < 36; ++v) acc[v] = 0.0;
-  for (int i = d.pair_begin[warp] + lane; i < d.pair_begin[warp + 1]; i += 32) {
+  for (int i = d.pair_begin[pair] + threadIdx.x; i < d.pair_begin[pair + 1]; i += blockDim.x) {
     // V = first 144 bytes of a 288-byte record (32-byte aligned), W = the second half (16 mod 32): 256-bit loads where
     // the alignment allows, one 128-bit load at the odd end
     const double* Vp = d.vw + (size_t)d.pair_t2[i] * kVWStride;
@@ -1470,11 +1489,17 @@ __global__ void __launch_bounds__(128) k_pairs(Dev d) {
       for (int b = 0; b < 6; ++b)
         acc[6 * a + b] += w[3 * a] * v[3 * b] + w[3 * a + 1] * v[3 * b + 1] + w[3 * a + 2] * v[3 * b + 2];
   }
-  const int f1 = d.pair_f1[warp], f2 = d.pair_f2[warp];
+  const int f1 = d.pair_f1[pair], f2 = d.pair_f2[pair];
 #pragma unroll
   for (int v = 0; v < 36; ++v) {
     const double s = warp_sum(acc[v]);
-    if (lane == (v & 31)) *S_at(d, 6 * f1 + v / 6, 6 * f2 + v % 6) -= s;
+    if (lane == 0) sred[wrp][v] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += sred[w][threadIdx.x];  // fixed order
+    *S_at(d, 6 * f1 + threadIdx.x / 6, 6 * f2 + threadIdx.x % 6) -= s;
   }
 }
 
@@ -2041,9 +2066,15 @@ int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
     } else {
       LFBA_DISPATCH_NC(d.NC, (k_frame_all<NC><<<grid, 128, 0, s>>>(d)));
       launches += 1;
+      if (frame_splits > 1) {
+        LFBA_DISPATCH_NC(d.NC, (k_frame_finish<NC><<<d.F, 128, 0, s>>>(d, frame_splits)));
+        launches += 1;
+      }
     }
     if (d.refine_points && d.npairs > 0) {
-      k_pairs<<<(d.npairs + 3) / 4, 128, 0, s>>>(d);
+      int wpp = 1;  // warps per pair: enough CTAs x warps to cover the SMs a few times
+      while (wpp < 8 && (long long)d.npairs * wpp < 4096) wpp *= 2;
+      k_pairs<<<d.npairs, 32 * wpp, 0, s>>>(d);
       ++launches;
     }
   }

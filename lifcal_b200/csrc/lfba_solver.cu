@@ -116,7 +116,7 @@ struct Solver {
   DevBuf<double> camera0, views0, points0;  // parameters given by the caller: every run() starts from them
   DevBuf<double> camera[2], views[2], points[2], lens, frames[2], rec[2], camsum[2], pdata, pscale, vw;
   DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one NCCL all-reduce)
-  DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step;
+  DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step, frame_part;
   DevBuf<unsigned long long> lens_dev;
   DevBuf<CamModel> cm_buf;
   DevBuf<LmState> st;
@@ -369,8 +369,15 @@ struct Solver {
     build_stream(ix, lanes, stream, &launches);
     phase("packed stream");
     {
-      const int per_frame = F > 0 ? (T + F - 1) / F : 0;
-      frame_splits = std::max(1, std::min(16, std::min((4 * sms) / std::max(1, F), (per_frame + 255) / 256)));
+      // frames that have tracks ON THIS RANK: a shard of a multi-GPU solve touches F / nranks of them, and one CTA per
+      // frame would leave most SMs idle — split the frames' track lists over several CTAs then
+      int f_local = 0;
+      for (int f = 0; f < F; ++f) f_local += ix.h_frame_count[f] > 0 ? 1 : 0;
+      f_local = std::max(1, f_local);
+      const int per_frame = (T + f_local - 1) / f_local;
+      frame_splits = std::max(1, std::min(16, std::min((4 * sms) / f_local, (per_frame + 255) / 256)));
+      if (const char* e = std::getenv("LFBA_FRAME_SPLITS")) frame_splits = std::max(1, std::min(16, std::atoi(e)));  // test hook
+      frame_part.alloc((size_t)std::max(1, F) * frame_splits * (39 + 6 * kMaxNC));
     }
 
     // ---- Dev ----
@@ -406,7 +413,7 @@ struct Solver {
     d.S = redbuf.p; d.row_off = row_off.p; d.row_c0 = row_c0.p;
     d.g = redbuf.p + S_len; d.gfull = d.g + n; d.hdiag = d.gfull + n; d.sys_scalars = d.hdiag + n;
     d.rscale = rscale.p; d.rdamp = rdamp.p; d.y = y.p; d.eval_scalars = eval_scalars.p;
-    d.part_eval = part_eval.p; d.part_pts = part_pts.p; d.part_step = part_step.p;
+    d.part_eval = part_eval.p; d.part_pts = part_pts.p; d.part_step = part_step.p; d.frame_part = frame_part.p;
     d.st = st.p; d.log = log.p;
     for (auto& e : ev) LFBA_CUDA(cudaEventCreate(&e));
     for (auto& e : ev_round) LFBA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
