@@ -159,8 +159,6 @@ struct Dev {
   double* lens;        // [NL*16]
   CamModel* cm_buf;    // camera model of the candidate parameters, written by k_tables (copied into constant memory)
   const double* lens_xy;  // [NL*2] lens centres
-  double implicit_tol;           // use the implicit lens derivatives while lens_dev <= this (negative: never)
-  unsigned long long* lens_dev;  // bits of the largest relative deviation (implicit vs exact lens derivatives) seen in this run
   double* frames[2];   // [F*40]
   // per-track / per-point work arrays
   double* rec[2];

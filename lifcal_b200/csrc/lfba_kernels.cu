@@ -6,14 +6,14 @@
 //
 // Round structure (all on one stream, no host decisions; the host only polls LmState::done):
 //   E  k_tables            per-lens undistortion table + per-frame rotation table at the CANDIDATE parameters
-//      k_eval_tracks       fused residual + analytic Jacobian + robust weighting + per-track normal-equation
-//                          blocks in the camera frame (A = G^T G, b = G^T r, C = G^T Jc) + camera block
-//                          (Hcc, gc) + cost.  The Jacobian never leaves registers.
+//      k_eval_rows         (lfba_rows.cu) fused residual + analytic Jacobian + robust weighting + per-track
+//                          normal-equation blocks in the camera frame (A = G^T G, b = G^T r, C = G^T Jc) + camera
+//                          block (Hcc, gc) + cost.  The Jacobian never leaves registers.
 //      k_reduce_eval       deterministic reduction of the per-CTA partials; candidate scalars
 //   C1 k_control_accept    step tests, rho, accept/reject (buffer flip), radius update   [device-resident LM]
 //   B  k_points            per point: Hpp, g_p, Hcp; damping; 3x3 inverse; camera-camera Schur term
-//      k_frame_pose        per frame: pose diagonal block, pose gradient (Schur-corrected), V and W=V Hpp^-1
-//      k_frame_cam         per frame: camera-pose block (Schur-corrected)
+//      k_frame_all         per frame: pose diagonal block, pose gradient, camera-pose block (Schur-corrected), V and
+//                          W = V Hpp^-1 (+ k_frame_finish when a frame's tracks are split over several CTAs)
 //      k_pairs             per co-visible frame pair: -sum_p W_{p,f1} V_{p,f2}^T
 //      k_coupled, k_constraints, k_add_camera
 //   C2 k_finalize          Jacobi scaling (iteration 0), gradient norms, iteration row, termination tests,
@@ -23,7 +23,6 @@
 //      k_reduced_step      candidate camera/poses/coupled points (manifold + bounds), reduced-part scalars
 // Scatter into the reduced system is gather-by-destination (per frame, per frame pair): no atomics on the hot
 // blocks and a fixed summation order.
-#include <cuda_pipeline.h>
 #include <stdlib.h>
 #include <cstdlib>
 #include <float.h>
@@ -87,16 +86,6 @@ __global__ void k_tables(Dev d) {
   if (i < d.NL) {
     double e[kLensStride];
     lens_entry(cm, d.lens_xy[2 * i], d.lens_xy[2 * i + 1], e);
-    {  // how far is the implicit-function derivative from the exact ten-step recurrence? (see lens_implicit_derivs)
-      double im[12], num = 0.0, den = 0.0;
-      lens_implicit_derivs(cm, e[2], e[3], im);
-      for (int k = 0; k < 12; ++k) {
-        num = fmax(num, fabs(im[k] - e[4 + k]));
-        den = fmax(den, fabs(e[4 + k]));
-      }
-      const double dev = den > 0.0 ? num / den : 0.0;
-      if (dev > 0.0) atomicMax(d.lens_dev, (unsigned long long)__double_as_longlong(dev));
-    }
     double2* dst = reinterpret_cast<double2*>(d.lens + (size_t)i * kLensStride);
 #pragma unroll
     for (int k = 0; k < kLensStride / 2; ++k) dst[k] = make_double2(e[2 * k], e[2 * k + 1]);
@@ -110,713 +99,9 @@ __global__ void k_tables(Dev d) {
   }
 }
 
-// Fused residual + analytic Jacobian + per-track normal-equation blocks.
-// L lanes cooperate on one track (point, frame): lane j takes observations j, j+L, ... of the track; the
-// track sums (A 6, b 3, C 3xNC) are combined with xor-shuffles inside the L-lane group; the camera block
-// (Hcc, gc) and the cost stay in per-thread accumulators for the whole kernel and are reduced once per CTA.
-// Algorithmic HBM traffic: 20 B per observation (double2 + int32) + REC*8 B per track written.
-// PART selects which accumulators a launch keeps (the evaluation itself is identical):
-//   0  everything in one pass: track records (A, b, C) + camera block (Hcc, gc) + cost      [255 registers, 8 warps/SM]
-//   1  track records + gc + cost                                                             } two passes, each at
-//   2  Hcc only                                                                              } roughly half the registers
-// The split recomputes the residual/Jacobian (about 150 FP64 ops) but doubles the resident warps and removes the
-// register spills; which variant is faster is a measured choice, not a semantic one.
-template <int NC, int NRAD, int L, int PART>
-__global__ void __launch_bounds__(128, PART == 0 ? 2 : 3) k_eval_tracks(Dev d) {
-  const LmState* st = d.st;
-  if (st->done || st->eval_skip) return;
-  const int cand = 1 - st->cur;
-  constexpr int NH = NC * (NC + 1) / 2;
-  constexpr int NV = NH + NC + 1;
-  constexpr int RS = 9 + 3 * NC;
-  constexpr bool kRec = PART != 2, kHcc = PART != 1;
-  constexpr int NA = PART == 0 ? NV : (PART == 1 ? NC + 1 : NH);  // per-thread accumulators of this launch
-  constexpr int AOFF = PART == 1 ? NH : 0;                         // their offset inside the NV-vector
-  __shared__ CamModel cm;
-  __shared__ double red[4 * NA];
-  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
-  __syncthreads();
+// The fused evaluation kernel itself is k_eval_rows (lfba_rows.cu).
 
-  double acc[NA];
-#pragma unroll
-  for (int v = 0; v < NA; ++v) acc[v] = 0.0;
-  // views into acc
-  double* hcc = acc;                          // PART 0/2
-  double* gcv = acc + (PART == 0 ? NH : 0);   // PART 0/1: gc[NC], cost
-
-  const int lig = threadIdx.x % L;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int ngroups = (gridDim.x * blockDim.x) / L;
-  const int iters = (d.T + ngroups - 1) / ngroups;
-  const double* __restrict__ frames = d.frames[cand];
-  const double* __restrict__ points = d.points[cand];
-  double* __restrict__ recs = d.rec[cand];
-  const bool robust = cm.robust != 0;
-
-  for (int it = 0; it < iters; ++it) {
-    const int slot = group + it * ngroups;
-    const bool valid = slot < d.T;
-    const int t = valid ? (d.eval_order ? d.eval_order[slot] : slot) : 0;
-    double tr[kRec ? RS : 1];
-    if (kRec) {
-#pragma unroll
-      for (int v = 0; v < RS; ++v) tr[v] = 0.0;
-    }
-    if (valid) {
-      const int p = d.trk_point[t], f = d.trk_frame[t];
-      const int ob = d.trk_begin[t], oe = d.trk_begin[t + 1];
-      double Pc[3];
-      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
-      TrackCtx tc;
-      track_setup(cm, Pc, tc);
-      for (int i = ob + lig; i < oe; i += L) {
-        const double2 o = d.obs[i];
-        const double2* lp = reinterpret_cast<const double2*>(d.lens + (size_t)d.lens_id[i] * kLensStride);
-        double e[kLensStride];
-#pragma unroll
-        for (int k = 0; k < kLensStride / 2; ++k) {
-          const double2 v2 = __ldg(lp + k);
-          e[2 * k] = v2.x;
-          e[2 * k + 1] = v2.y;
-        }
-        double r[2], G[6], J[2 * NC];
-        obs_eval<NC, NRAD>(cm, tc, e, o.x, o.y, r, G, J);
-        const double s = r[0] * r[0] + r[1] * r[1];
-        if (robust) {
-          double rho;
-          const double sw = robust_scale(cm, s, rho);
-          if (kRec) gcv[NC] += 0.5 * rho;
-          r[0] *= sw;
-          r[1] *= sw;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) G[k] *= sw;
-#pragma unroll
-          for (int k = 0; k < 2 * NC; ++k) J[k] *= sw;
-        } else {
-          if (kRec) gcv[NC] += 0.5 * s;
-        }
-        if (kRec) {
-          // track blocks (explicit fma chains: 2 DFMA per entry instead of DMUL + DFMA + DADD)
-          tr[0] = fma(G[0], G[0], fma(G[3], G[3], tr[0]));
-          tr[1] = fma(G[0], G[1], fma(G[3], G[4], tr[1]));
-          tr[2] = fma(G[0], G[2], fma(G[3], G[5], tr[2]));
-          tr[3] = fma(G[1], G[1], fma(G[4], G[4], tr[3]));
-          tr[4] = fma(G[1], G[2], fma(G[4], G[5], tr[4]));
-          tr[5] = fma(G[2], G[2], fma(G[5], G[5], tr[5]));
-#pragma unroll
-          for (int k = 0; k < 3; ++k) tr[6 + k] = fma(G[k], r[0], fma(G[3 + k], r[1], tr[6 + k]));
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-              tr[9 + k * NC + c] = fma(G[k], J[c], fma(G[3 + k], J[NC + c], tr[9 + k * NC + c]));
-#pragma unroll
-          for (int c = 0; c < NC; ++c) gcv[c] = fma(J[c], r[0], fma(J[NC + c], r[1], gcv[c]));
-        }
-        if (kHcc) {
-          int h = 0;
-#pragma unroll
-          for (int c1 = 0; c1 < NC; ++c1)
-#pragma unroll
-            for (int c2 = 0; c2 <= c1; ++c2) {
-              hcc[h] = fma(J[c1], J[c2], fma(J[NC + c1], J[NC + c2], hcc[h]));
-              ++h;
-            }
-        }
-      }
-    }
-    if (kRec) {
-      if (L > 1) {
-#pragma unroll
-        for (int v = 0; v < RS; ++v)
-#pragma unroll
-          for (int o = L / 2; o > 0; o >>= 1) tr[v] += __shfl_xor_sync(0xffffffffu, tr[v], o);
-      }
-      if (valid) {
-        double* dst = recs + (size_t)t * RS;
-#pragma unroll
-        for (int v = 0; v < RS; ++v)
-          if ((v % L) == lig) dst[v] = tr[v];
-      }
-    }
-  }
-  block_reduce_store<NA>(acc, d.part_eval + (size_t)blockIdx.x * 64 + AOFF, red);
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_eval_stream: the same fused evaluation as k_eval_tracks, organised as a software-pipelined stream.
-//   * every L-lane group owns a CONTIGUOUS range of tracks (tracks are stored sorted by (point, frame), and a
-//     track's observations are contiguous), so each group walks one contiguous slice of the observation arrays;
-//   * groups are decoupled (no warp-wide lock step): the only cross-lane traffic is the xor-shuffle reduction of the
-//     36 track sums inside the group when ITS track ends;
-//   * the observation (double2) and lens id of the item two steps ahead are prefetched into registers, the 128-byte
-//     lens-table entry of the item one step ahead is prefetched with cp.async (LDGSTS) into a per-thread,
-//     bank-conflict-free shared-memory slot, so the dependent load lens_id -> lens entry is off the critical path.
-// The kernel is FP64-issue bound by design; with 255 registers per thread only 8 warps fit on an SM, so latency has
-// to be hidden by this explicit pipeline rather than by occupancy.
-// ------------------------------------------------------------------------------------------------
-struct LensSlot {
-  const double2* base;  // &slot[0][tid]; element k2 lives 128 double2 further
-  __device__ __forceinline__ double operator[](int k) const {
-    const double2 v = base[(k >> 1) * 128];
-    return (k & 1) ? v.y : v.x;
-  }
-};
-
-template <int NC, int NRAD, int L>
-__global__ void __launch_bounds__(128) k_eval_stream(Dev d) {
-  const LmState* st = d.st;
-  if (st->done || st->eval_skip) return;
-  const int cand = 1 - st->cur;
-  constexpr int NH = NC * (NC + 1) / 2;
-  constexpr int NV = NH + NC + 1;
-  constexpr int RS = 9 + 3 * NC;
-  __shared__ CamModel cm;
-  __shared__ double red[4 * NV];
-  __shared__ double2 lens_s[2 * 8 * 128];  // [slot][k2][thread]
-  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
-  __syncthreads();
-
-  double acc[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-
-  const int lig = threadIdx.x % L;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int ngroups = (gridDim.x * blockDim.x) / L;
-  const int per = (d.T + ngroups - 1) / ngroups;
-  const int t_begin = min(d.T, group * per), t_end = min(d.T, t_begin + per);
-  const double* __restrict__ frames = d.frames[cand];
-  const double* __restrict__ points = d.points[cand];
-  double* __restrict__ recs = d.rec[cand];
-  const bool robust = cm.robust != 0;
-  const unsigned gmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << ((threadIdx.x & 31) / L * L));
-
-  if (t_begin < t_end) {
-    const int i_end = d.trk_begin[t_end];  // end of this group's observation slice
-    // step bases: b0 = current, b1 = next, b2 = next-next. A step never crosses a track end.
-    int t = t_begin;
-    int te = d.trk_begin[t + 1];           // end of the current track
-    int t1 = t, te1 = te;                   // track of b1
-    int t2 = t, te2 = te;                   // track of b2
-    int b0 = d.trk_begin[t];
-    auto next_base = [&](int b, int& tt, int& tte) -> int {
-      int nb = b + L;
-      if (nb >= tte) {
-        nb = tte;
-        if (tte < i_end) {
-          ++tt;
-          tte = d.trk_begin[tt + 1];
-        }
-      }
-      return nb;
-    };
-    int b1 = next_base(b0, t1, te1);
-    t2 = t1;
-    te2 = te1;
-    int b2 = next_base(b1, t2, te2);
-    // pipeline registers
-    double2 o0 = make_double2(0.0, 0.0), o1 = o0, o2 = o0;
-    int l1 = 0, l2 = 0;
-    bool v0 = b0 + lig < te, v1 = (b1 < i_end) && (b1 + lig < te1), v2 = (b2 < i_end) && (b2 + lig < te2);
-    int slot = 0;
-    double2* myslot = lens_s + threadIdx.x;
-    auto issue_lens = [&](int lid, int sl) {
-      const double2* src = reinterpret_cast<const double2*>(d.lens + (size_t)lid * kLensStride);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) __pipeline_memcpy_async(myslot + (sl * 8 + k) * 128, src + k, 16);
-    };
-    if (v0) {
-      o0 = d.obs[b0 + lig];
-      issue_lens(d.lens_id[b0 + lig], 0);
-    }
-    __pipeline_commit();
-    if (v1) {
-      o1 = d.obs[b1 + lig];
-      l1 = d.lens_id[b1 + lig];
-    }
-    // track state
-    double tr[RS];
-    TrackCtx tc;
-    bool fresh = true;  // b0 is the first step of a track
-    while (b0 < i_end) {
-      // ---- prefetch: lens entry of the next step (cp.async), observation + lens id of the step after ----
-      if (v1) issue_lens(l1, slot ^ 1);
-      __pipeline_commit();
-      if (v2) {
-        o2 = d.obs[b2 + lig];
-        l2 = d.lens_id[b2 + lig];
-      }
-      if (fresh) {
-        const int p = d.trk_point[t], f = d.trk_frame[t];
-        double Pc[3];
-        track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
-        track_setup(cm, Pc, tc);
-#pragma unroll
-        for (int v = 0; v < RS; ++v) tr[v] = 0.0;
-        fresh = false;
-      }
-      __pipeline_wait_prior(1);  // the current step's lens entry has landed
-      if (v0) {
-        LensSlot e{myslot + slot * 8 * 128};
-        double r[2], G[6], J[2 * NC];
-        obs_eval<NC, NRAD>(cm, tc, e, o0.x, o0.y, r, G, J);
-        const double s = r[0] * r[0] + r[1] * r[1];
-        if (robust) {
-          double rho;
-          const double sw = robust_scale(cm, s, rho);
-          acc[NH + NC] += 0.5 * rho;
-          r[0] *= sw;
-          r[1] *= sw;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) G[k] *= sw;
-#pragma unroll
-          for (int k = 0; k < 2 * NC; ++k) J[k] *= sw;
-        } else {
-          acc[NH + NC] += 0.5 * s;
-        }
-        tr[0] = fma(G[0], G[0], fma(G[3], G[3], tr[0]));
-        tr[1] = fma(G[0], G[1], fma(G[3], G[4], tr[1]));
-        tr[2] = fma(G[0], G[2], fma(G[3], G[5], tr[2]));
-        tr[3] = fma(G[1], G[1], fma(G[4], G[4], tr[3]));
-        tr[4] = fma(G[1], G[2], fma(G[4], G[5], tr[4]));
-        tr[5] = fma(G[2], G[2], fma(G[5], G[5], tr[5]));
-#pragma unroll
-        for (int k = 0; k < 3; ++k) tr[6 + k] = fma(G[k], r[0], fma(G[3 + k], r[1], tr[6 + k]));
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-          for (int c = 0; c < NC; ++c) tr[9 + k * NC + c] = fma(G[k], J[c], fma(G[3 + k], J[NC + c], tr[9 + k * NC + c]));
-        int h = 0;
-#pragma unroll
-        for (int c1 = 0; c1 < NC; ++c1)
-#pragma unroll
-          for (int c2 = 0; c2 <= c1; ++c2) {
-            acc[h] = fma(J[c1], J[c2], fma(J[NC + c1], J[NC + c2], acc[h]));
-            ++h;
-          }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) acc[NH + c] = fma(J[c], r[0], fma(J[NC + c], r[1], acc[NH + c]));
-      }
-      // ---- end of the track: combine the L lanes, write the record ----
-      if (b1 >= te) {  // the next step starts another track (or the slice is finished)
-        if (L > 1) {
-#pragma unroll
-          for (int v = 0; v < RS; ++v)
-#pragma unroll
-            for (int o = L / 2; o > 0; o >>= 1) tr[v] += __shfl_xor_sync(gmask, tr[v], o);
-        }
-        double* dst = recs + (size_t)t * RS;
-#pragma unroll
-        for (int v = 0; v < RS; ++v)
-          if ((v % L) == lig) dst[v] = tr[v];
-        t = t1;
-        te = te1;
-        fresh = true;
-      }
-      // ---- rotate the pipeline ----
-      b0 = b1;
-      v0 = v1;
-      o0 = o1;
-      slot ^= 1;
-      b1 = b2;
-      t1 = t2;
-      te1 = te2;
-      v1 = v2;
-      o1 = o2;
-      l1 = l2;
-      b2 = next_base(b1, t2, te2);
-      v2 = (b2 < i_end) && (b2 + lig < te2);
-    }
-    __pipeline_wait_prior(0);
-  }
-  block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// k_eval_gram: fused evaluation in FEATURE form (lfba_math.cuh, obs_features / GramMap).
-// Per observation the thread accumulates the Gram matrix of NC+1 two-component features (65 running sums for NC = 9)
-// instead of 91 Jacobian-block sums; when a track ends its L lanes combine the Gram sums with xor-shuffles and
-// expand them — once per track, split over the L lanes — into the track record (A, b, C) and the camera block
-// (Hcc, gc), whose running totals live in a per-thread column of shared memory because they are touched once per
-// track, not once per observation. Result: ~35% fewer FP64 instructions per observation and no register spills.
-// ------------------------------------------------------------------------------------------------
-template <int NC, int NRAD, int L, bool IMPLICIT>
-__global__ void __launch_bounds__(128, 2) k_eval_gram(Dev d) {
-  const LmState* st = d.st;
-  if (st->done || st->eval_skip) return;
-  // two instantiations are launched back to back; exactly one of them does the work (device-side decision)
-  if ((__longlong_as_double((long long)*d.lens_dev) <= d.implicit_tol) != IMPLICIT) return;
-  const int cand = 1 - st->cur;
-  constexpr int NH = NC * (NC + 1) / 2;
-  constexpr int NV = NH + NC + 1;
-  constexpr int RS = 9 + 3 * NC;
-  constexpr int NF = FeatDims<NC>::NF, NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
-  typedef GramMap<NC> GM;
-  __shared__ CamModel cm;
-  __shared__ double red[4 * NV];
-  extern __shared__ double pers[];  // [NV][128]: per-thread camera-block totals
-  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
-#pragma unroll
-  for (int v = 0; v < NV; ++v) pers[v * 128 + threadIdx.x] = 0.0;
-  __syncthreads();
-
-  const int lig = threadIdx.x % L;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int ngroups = (gridDim.x * blockDim.x) / L;
-  const int iters = (d.T + ngroups - 1) / ngroups;
-  const double* __restrict__ frames = d.frames[cand];
-  const double* __restrict__ points = d.points[cand];
-  double* __restrict__ recs = d.rec[cand];
-  const bool robust = cm.robust != 0;
-  double cost = 0.0;
-
-  for (int it = 0; it < iters; ++it) {
-    const int slot = group + it * ngroups;
-    const bool valid = slot < d.T;
-    const int t = valid ? (d.eval_order ? d.eval_order[slot] : slot) : 0;
-    double g[NG];
-#pragma unroll
-    for (int v = 0; v < NG; ++v) g[v] = 0.0;
-    TrackCtx tc;
-    if (valid) {
-      const int p = d.trk_point[t], f = d.trk_frame[t];
-      const int ob = d.trk_begin[t], oe = d.trk_begin[t + 1];
-      double Pc[3];
-      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
-      track_setup(cm, Pc, tc);
-      for (int i = ob + lig; i < oe; i += L) {
-        const double2 o = d.obs[i];
-        const double2* lp = reinterpret_cast<const double2*>(d.lens + (size_t)d.lens_id[i] * kLensStride);
-        double e[kLensStride];
-        if (IMPLICIT) {
-          // one 32-byte sector per observation: (mx, my, ux, uy); the derivatives are recomputed from u
-          const double2 v0 = __ldg(lp), v1 = __ldg(lp + 1);
-          e[0] = v0.x;
-          e[1] = v0.y;
-          e[2] = v1.x;
-          e[3] = v1.y;
-          lens_implicit_derivs(cm, e[2], e[3], e + 4);
-        } else {
-#pragma unroll
-          for (int k = 0; k < kLensStride / 2; ++k) {
-            const double2 v2 = __ldg(lp + k);
-            e[2 * k] = v2.x;
-            e[2 * k + 1] = v2.y;
-          }
-        }
-        double r[2], F[2 * NF];
-        obs_features<NC, NRAD>(cm, tc, e, o.x, o.y, r, F);
-        const double s = r[0] * r[0] + r[1] * r[1];
-        if (robust) {
-          double rho;
-          const double sw = robust_scale(cm, s, rho);
-          cost += 0.5 * rho;
-          r[0] *= sw;
-          r[1] *= sw;
-#pragma unroll
-          for (int k = 0; k < 2 * NF; ++k) F[k] *= sw;
-        } else {
-          cost += 0.5 * s;
-        }
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < NF; ++a)
-#pragma unroll
-          for (int b = 0; b <= a; ++b) {
-            g[q] = fma(F[a], F[b], fma(F[NF + a], F[NF + b], g[q]));
-            ++q;
-          }
-#pragma unroll
-        for (int a = 0; a < NF; ++a) g[NQ + a] = fma(F[a], r[0], fma(F[NF + a], r[1], g[NQ + a]));
-      }
-    }
-    if (L > 1) {
-#pragma unroll
-      for (int v = 0; v < NG; ++v)
-#pragma unroll
-        for (int o = L / 2; o > 0; o >>= 1) g[v] += __shfl_xor_sync(0xffffffffu, g[v], o);
-    }
-    if (valid) {
-      // expand the Gram sums into the track record and the camera block; entries are split over the L lanes
-      const double* h = g + NQ;
-      double* dst = recs + (size_t)t * RS;
-      int v = 0;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = i; j < 3; ++j) {
-          if ((v % L) == lig) dst[v] = GM::gg(tc, g, i, j);
-          ++v;
-        }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if ((v % L) == lig) dst[v] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
-        ++v;
-      }
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          if ((v % L) == lig) dst[v] = GM::gcam(tc, g, i, c);
-          ++v;
-        }
-      int hh = 0;
-#pragma unroll
-      for (int c1 = 0; c1 < NC; ++c1)
-#pragma unroll
-        for (int c2 = 0; c2 <= c1; ++c2) {
-          if ((hh % L) == lig) pers[hh * 128 + threadIdx.x] += GM::cc(tc, g, c1, c2);
-          ++hh;
-        }
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        if (((NH + c) % L) == lig) {
-          double gcv;
-          if (c < 3) {
-            double a, b;
-            GM::geo(tc, c, a, b);
-            gcv = a * h[3] + b * h[2];
-          } else {
-            gcv = h[c + 1];
-          }
-          pers[(NH + c) * 128 + threadIdx.x] += gcv;
-        }
-      }
-    }
-  }
-  double acc[NV];
-#pragma unroll
-  for (int v = 0; v < NV - 1; ++v) acc[v] = pers[v * 128 + threadIdx.x];
-  acc[NV - 1] = cost;
-  block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
-}
-
-
-// k_eval_gram with the lens-entry gather software-pipelined (cp.async into per-thread shared-memory slots, observation
-// and lens id prefetched two steps ahead): the dependent load lens_id -> lens entry leaves the critical path.
-template <int NC, int NRAD, int L>
-__global__ void __launch_bounds__(128, 2) k_eval_gram_pf(Dev d) {
-  const LmState* st = d.st;
-  if (st->done || st->eval_skip) return;
-  const int cand = 1 - st->cur;
-  constexpr int NH = NC * (NC + 1) / 2;
-  constexpr int NV = NH + NC + 1;
-  constexpr int RS = 9 + 3 * NC;
-  constexpr int NF = FeatDims<NC>::NF, NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
-  typedef GramMap<NC> GM;
-  __shared__ CamModel cm;
-  __shared__ double red[4 * NV];
-  extern __shared__ double pers[];  // [NV][128]: per-thread camera-block totals, then [2][8][128] double2 lens slots
-  double2* lens_s = reinterpret_cast<double2*>(pers + NV * 128);
-  if (threadIdx.x == 0) cam_model_init(cm, d.camera[cand], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
-#pragma unroll
-  for (int v = 0; v < NV; ++v) pers[v * 128 + threadIdx.x] = 0.0;
-  __syncthreads();
-
-  const int lig = threadIdx.x % L;
-  const int group = (blockIdx.x * blockDim.x + threadIdx.x) / L;
-  const int ngroups = (gridDim.x * blockDim.x) / L;
-  const int iters = (d.T + ngroups - 1) / ngroups;
-  const double* __restrict__ frames = d.frames[cand];
-  const double* __restrict__ points = d.points[cand];
-  double* __restrict__ recs = d.rec[cand];
-  const bool robust = cm.robust != 0;
-  double cost = 0.0;
-
-  // ---- software pipeline over the lane's observation steps (see k_eval_stream for the idea; here the groups of a
-  //      warp stay in lock step per track round, so there is no extra divergence) ----
-  double2* myslot = lens_s + threadIdx.x;
-  auto issue_lens = [&](int lid, int sl) {
-    const double2* src = reinterpret_cast<const double2*>(d.lens + (size_t)lid * kLensStride);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) __pipeline_memcpy_async(myslot + (sl * 8 + k) * 128, src + k, 16);
-  };
-  auto load_track = [&](int slot, int& tt, int& b, int& e2, bool& ok) {
-    ok = slot < d.T;
-    tt = ok ? (d.eval_order ? d.eval_order[slot] : slot) : 0;
-    b = ok ? d.trk_begin[tt] : 0;
-    e2 = ok ? d.trk_begin[tt + 1] : 0;
-  };
-  int t, ob, oe, nt, nob, noe;
-  bool valid, nvalid;
-  load_track(group, t, ob, oe, valid);
-  load_track(group + ngroups, nt, nob, noe, nvalid);
-  // pipeline registers: current (c), next (n), next-next (nn)
-  double2 o_c = make_double2(0.0, 0.0), o_n = o_c, o_nn = o_c;
-  int lid_n = 0, lid_nn = 0;
-  bool v_c = false, v_n = false, have_n = true, v_nn = false, have_nn = true;
-  int sl = 0;
-  {  // prologue: step (0,0) current, step +1 as next
-    const int i0 = ob + lig;
-    v_c = valid && i0 < oe;
-    if (v_c) {
-      o_c = d.obs[i0];
-      issue_lens(d.lens_id[i0], 0);
-    }
-    __pipeline_commit();
-    const int ns0 = valid ? (oe - ob + L - 1) / L : 0;
-    int i1;
-    if (1 < ns0) { i1 = ob + lig + L; v_n = i1 < oe; }
-    else { i1 = nob + lig; v_n = nvalid && i1 < noe; }
-    if (v_n) {
-      o_n = d.obs[i1];
-      lid_n = d.lens_id[i1];
-    }
-  }
-
-  for (int it = 0; it < iters; ++it) {
-    double g[NG];
-#pragma unroll
-    for (int v = 0; v < NG; ++v) g[v] = 0.0;
-    TrackCtx tc;
-    const int nsteps = valid ? (oe - ob + L - 1) / L : 0;
-    const int nsteps_next = nvalid ? (noe - nob + L - 1) / L : 0;
-    if (valid) {
-      const int p = d.trk_point[t], f = d.trk_frame[t];
-      double Pc[3];
-      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
-      track_setup(cm, Pc, tc);
-    }
-    for (int m = 0; m < nsteps; ++m) {
-      // next step's lens entry: cp.async into the other slot (its lens id was loaded one step ago)
-      if (v_n && !have_n) {  // rare: the look-ahead could not see this item (track of <= L observations)
-        const bool same = m + 1 < nsteps;
-        const int i1 = same ? ob + lig + L * (m + 1) : nob + lig;
-        v_n = same ? (i1 < oe) : (nvalid && i1 < noe);
-        have_n = true;
-        if (v_n) {
-          o_n = d.obs[i1];
-          lid_n = d.lens_id[i1];
-        }
-      }
-      if (v_n) issue_lens(lid_n, sl ^ 1);
-      __pipeline_commit();
-      // observation + lens id two steps ahead
-      {
-        int i2 = 0;
-        have_nn = true;
-        if (m + 2 < nsteps) { i2 = ob + lig + L * (m + 2); v_nn = i2 < oe; }
-        else if (m + 1 < nsteps) { i2 = nob + lig; v_nn = nvalid && i2 < noe; }
-        else if (nsteps_next > 1) { i2 = nob + lig + L; v_nn = nvalid && i2 < noe; }
-        else { v_nn = true; have_nn = false; }  // belongs to the round after next: fetched when it becomes "next"
-        if (v_nn && have_nn) {
-          o_nn = d.obs[i2];
-          lid_nn = d.lens_id[i2];
-        }
-      }
-      __pipeline_wait_prior(1);
-      if (v_c) {
-        LensSlot e{myslot + sl * 8 * 128};
-        double r[2], F[2 * NF];
-        obs_features<NC, NRAD>(cm, tc, e, o_c.x, o_c.y, r, F);
-        const double s = r[0] * r[0] + r[1] * r[1];
-        if (robust) {
-          double rho;
-          const double sw = robust_scale(cm, s, rho);
-          cost += 0.5 * rho;
-          r[0] *= sw;
-          r[1] *= sw;
-#pragma unroll
-          for (int k = 0; k < 2 * NF; ++k) F[k] *= sw;
-        } else {
-          cost += 0.5 * s;
-        }
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < NF; ++a)
-#pragma unroll
-          for (int b = 0; b <= a; ++b) {
-            g[q] = fma(F[a], F[b], fma(F[NF + a], F[NF + b], g[q]));
-            ++q;
-          }
-#pragma unroll
-        for (int a = 0; a < NF; ++a) g[NQ + a] = fma(F[a], r[0], fma(F[NF + a], r[1], g[NQ + a]));
-      }
-      // rotate
-      o_c = o_n;
-      v_c = v_n;
-      sl ^= 1;
-      o_n = o_nn;
-      lid_n = lid_nn;
-      v_n = v_nn;
-      have_n = have_nn;
-    }
-    if (L > 1) {
-#pragma unroll
-      for (int v = 0; v < NG; ++v)
-#pragma unroll
-        for (int o = L / 2; o > 0; o >>= 1) g[v] += __shfl_xor_sync(0xffffffffu, g[v], o);
-    }
-    if (valid) {
-      // expand the Gram sums into the track record and the camera block; entries are split over the L lanes
-      const double* h = g + NQ;
-      double* dst = recs + (size_t)t * RS;
-      int v = 0;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = i; j < 3; ++j) {
-          if ((v % L) == lig) dst[v] = GM::gg(tc, g, i, j);
-          ++v;
-        }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if ((v % L) == lig) dst[v] = (i == 2 ? -tc.g1 : tc.g1) * h[i];
-        ++v;
-      }
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          if ((v % L) == lig) dst[v] = GM::gcam(tc, g, i, c);
-          ++v;
-        }
-      int hh = 0;
-#pragma unroll
-      for (int c1 = 0; c1 < NC; ++c1)
-#pragma unroll
-        for (int c2 = 0; c2 <= c1; ++c2) {
-          if ((hh % L) == lig) pers[hh * 128 + threadIdx.x] += GM::cc(tc, g, c1, c2);
-          ++hh;
-        }
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        if (((NH + c) % L) == lig) {
-          double gcv;
-          if (c < 3) {
-            double a, b;
-            GM::geo(tc, c, a, b);
-            gcv = a * h[3] + b * h[2];
-          } else {
-            gcv = h[c + 1];
-          }
-          pers[(NH + c) * 128 + threadIdx.x] += gcv;
-        }
-      }
-    }
-    // next round: the prefetched track becomes current; fetch the one after
-    t = nt;
-    ob = nob;
-    oe = noe;
-    valid = nvalid;
-    load_track(group + (it + 2) * ngroups, nt, nob, noe, nvalid);
-    if (!valid) {  // an invalid round has no steps: the "next" item of the dead round must not leak into a live one
-      v_c = false;
-      v_n = false;
-    }
-  }
-  __pipeline_wait_prior(0);
-  double acc[NV];
-#pragma unroll
-  for (int v = 0; v < NV - 1; ++v) acc[v] = pers[v * 128 + threadIdx.x];
-  acc[NV - 1] = cost;
-  block_reduce_store<NV>(acc, d.part_eval + (size_t)blockIdx.x * 64, red);
-}
-
-
-// Sum the CTA partials of k_eval_tracks (fixed order) -> camsum[cand]; sum the step partials of
+// Sum the CTA partials of k_eval_rows (fixed order) -> camsum[cand]; sum the step partials of
 // k_point_step (previous round); candidate cost of the distance constraints; assemble eval_scalars.
 __global__ void __launch_bounds__(1024) k_reduce_eval(Dev d) {
   LmState* st = d.st;
@@ -1090,128 +375,6 @@ __device__ __forceinline__ void track_M(const double* fe, const double* X, doubl
   mat3_vec(fe + 27, X, m + 6);
 }
 
-// Per frame (one CTA per (frame, split)): pose diagonal block, pose gradient, both Schur-corrected with the
-// track's own point; writes V = Hvp (6x3) and W = V Hpp^-1 for k_pairs / k_frame_cam / k_point_step.
-__global__ void __launch_bounds__(128) k_frame_pose(Dev d) {
-  LmState* st = d.st;
-  if (st->done) return;
-  const int cur = st->cur;
-  const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
-  const int RS = rec_stride(d.NC);
-  constexpr int NV = 21 + 6 + 6 + 6;  // S_ff (lower 21), reduced gradient, full gradient, diag(F^T F)
-  __shared__ double fe[kFrameStride];
-  __shared__ double red[4 * NV];
-  __shared__ double out[NV];
-  if (threadIdx.x < kFrameStride) fe[threadIdx.x] = d.frames[cur][(size_t)f * kFrameStride + threadIdx.x];
-  __syncthreads();
-  double acc[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-  const double* __restrict__ recs = d.rec[cur];
-  const double* __restrict__ points = d.points[cur];
-  for (int idx = d.frm_begin[f] + split * blockDim.x + threadIdx.x; idx < d.frm_begin[f + 1];
-       idx += nsplit * blockDim.x) {
-    const int t = d.frm_trk[idx];
-    const int p = d.trk_point[t];
-    const double* rc = recs + (size_t)t * RS;
-    const double* pd = d.pdata + (size_t)p * kPointStride;
-    const double A[6] = {rc[0], rc[1], rc[2], rc[3], rc[4], rc[5]};
-    const double b[3] = {rc[6], rc[7], rc[8]};
-    double m[9];
-    track_M(fe, points + 3 * (size_t)p, m);
-    // AM (3x6): columns 0..2 = A m_k, columns 3..5 = A
-    double AM[18];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double y[3];
-      sym3_vec(A, m + 3 * k, y);
-      AM[0 * 6 + k] = y[0];
-      AM[1 * 6 + k] = y[1];
-      AM[2 * 6 + k] = y[2];
-    }
-    AM[0 * 6 + 3] = A[0]; AM[0 * 6 + 4] = A[1]; AM[0 * 6 + 5] = A[2];
-    AM[1 * 6 + 3] = A[1]; AM[1 * 6 + 4] = A[3]; AM[1 * 6 + 5] = A[4];
-    AM[2 * 6 + 3] = A[2]; AM[2 * 6 + 4] = A[4]; AM[2 * 6 + 5] = A[5];
-    // M^T as rows: Mt[a][i], a<3: m[3a+i]; a>=3: delta(a-3,i)
-    auto Mt = [&](int a, int i) -> double { return a < 3 ? m[3 * a + i] : (a - 3 == i ? 1.0 : 0.0); };
-    double Hvv[21], gv[6];
-    {
-      int h = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-#pragma unroll
-        for (int c = 0; c <= a; ++c) {
-          Hvv[h++] = Mt(a, 0) * AM[0 * 6 + c] + Mt(a, 1) * AM[1 * 6 + c] + Mt(a, 2) * AM[2 * 6 + c];
-        }
-        gv[a] = Mt(a, 0) * b[0] + Mt(a, 1) * b[1] + Mt(a, 2) * b[2];
-      }
-    }
-    // V = M^T (A R) (6x3), W = V Hi
-    const double* R = fe;
-    double AR[9];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      AR[0 + j] = A[0] * R[j] + A[1] * R[3 + j] + A[2] * R[6 + j];
-      AR[3 + j] = A[1] * R[j] + A[3] * R[3 + j] + A[4] * R[6 + j];
-      AR[6 + j] = A[2] * R[j] + A[4] * R[3 + j] + A[5] * R[6 + j];
-    }
-    double V[18], W[18];
-    const double Hi[6] = {pd[0], pd[1], pd[2], pd[3], pd[4], pd[5]};
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) V[3 * a + j] = Mt(a, 0) * AR[j] + Mt(a, 1) * AR[3 + j] + Mt(a, 2) * AR[6 + j];
-      sym3_vec(Hi, V + 3 * a, W + 3 * a);
-    }
-    double* vw = d.vw + (size_t)t * kVWStride;
-#pragma unroll
-    for (int k = 0; k < 18; ++k) {
-      vw[k] = V[k];
-      vw[18 + k] = W[k];
-    }
-    const double gp[3] = {pd[6], pd[7], pd[8]};
-    {
-      int h = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-#pragma unroll
-        for (int c = 0; c <= a; ++c) {
-          acc[h] += Hvv[h] - (W[3 * a] * V[3 * c] + W[3 * a + 1] * V[3 * c + 1] + W[3 * a + 2] * V[3 * c + 2]);
-          ++h;
-        }
-        acc[21 + a] += gv[a] - (W[3 * a] * gp[0] + W[3 * a + 1] * gp[1] + W[3 * a + 2] * gp[2]);
-        acc[27 + a] += gv[a];
-      }
-      acc[33] += Hvv[0];
-      acc[34] += Hvv[2];
-      acc[35] += Hvv[5];
-      acc[36] += Hvv[9];
-      acc[37] += Hvv[14];
-      acc[38] += Hvv[20];
-    }
-  }
-  block_reduce_store<NV>(acc, out, red);
-  if (threadIdx.x < NV) {
-    const int v = threadIdx.x;
-    const double s = out[v];
-    double* dst;
-    if (v < 21) {
-      int a = 0, h = v;
-      while (h > a) { h -= a + 1; ++a; }
-      dst = S_at(d, 6 * f + a, 6 * f + h);
-    } else if (v < 27) {
-      dst = d.g + 6 * f + (v - 21);
-    } else if (v < 33) {
-      dst = d.gfull + 6 * f + (v - 27);
-    } else {
-      dst = d.hdiag + 6 * f + (v - 33);
-    }
-    if (nsplit == 1) *dst += s; else atomicAdd(dst, s);
-  }
-}
-
-// Per frame, ONE pass over the frame's tracks (k_frame_pose + k_frame_cam fused: the track record, the point data and
-// W are read once, W never round-trips through HBM): pose diagonal block, pose gradient, camera-pose block.
 // entry v of k_frame_all's per-frame sums -> its place in the reduced system
 template <int NC>
 __device__ __forceinline__ void frame_all_scatter(const Dev& d, int f, int v, double sv) {
@@ -1404,57 +567,6 @@ __global__ void __launch_bounds__(128) k_frame_finish(Dev d, int nsplit) {
   frame_all_scatter<NC>(d, f, v, sv);
 }
 
-// Per frame: camera-pose block S[cam, f] = sum_t (C_t^T M_t - Hcp W_t^T).
-template <int NC>
-__global__ void __launch_bounds__(128) k_frame_cam(Dev d) {
-  LmState* st = d.st;
-  if (st->done) return;
-  const int cur = st->cur;
-  const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
-  constexpr int RS = 9 + 3 * NC;
-  constexpr int NV = 6 * NC;
-  __shared__ double fe[kFrameStride];
-  __shared__ double red[4 * NV];
-  __shared__ double out[NV];
-  if (threadIdx.x < kFrameStride) fe[threadIdx.x] = d.frames[cur][(size_t)f * kFrameStride + threadIdx.x];
-  __syncthreads();
-  double acc[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-  const double* __restrict__ recs = d.rec[cur];
-  const double* __restrict__ points = d.points[cur];
-  for (int idx = d.frm_begin[f] + split * blockDim.x + threadIdx.x; idx < d.frm_begin[f + 1];
-       idx += nsplit * blockDim.x) {
-    const int t = d.frm_trk[idx];
-    const int p = d.trk_point[t];
-    const double* rc = recs + (size_t)t * RS;
-    const double* pd = d.pdata + (size_t)p * kPointStride;
-    const double* W = d.vw + (size_t)t * kVWStride + 18;
-    double m[9];
-    track_M(fe, points + 3 * (size_t)p, m);
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const double c0 = rc[9 + c], c1 = rc[9 + NC + c], c2 = rc[9 + 2 * NC + c];
-      const double h0 = pd[12 + 3 * c], h1 = pd[13 + 3 * c], h2 = pd[14 + 3 * c];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        const double cm = a < 3 ? (c0 * m[3 * a] + c1 * m[3 * a + 1] + c2 * m[3 * a + 2])
-                                : (a == 3 ? c0 : (a == 4 ? c1 : c2));
-        acc[6 * c + a] += cm - (h0 * W[3 * a] + h1 * W[3 * a + 1] + h2 * W[3 * a + 2]);
-      }
-    }
-  }
-  block_reduce_store<NV>(acc, out, red);
-  if (threadIdx.x < NV) {
-    const int c = threadIdx.x / 6, a = threadIdx.x % 6;
-    const int r = d.cam_red[c];
-    if (r >= 0) {
-      double* dst = S_at(d, r, 6 * f + a);
-      if (nsplit == 1) *dst += out[threadIdx.x]; else atomicAdd(dst, out[threadIdx.x]);
-    }
-  }
-}
-
 // Per co-visible frame pair (f1 > f2), one warp: S[f1, f2] = -sum_p W_{p,f1} V_{p,f2}^T.
 __global__ void __launch_bounds__(256) k_pairs(Dev d) {
   LmState* st = d.st;
@@ -1602,7 +714,7 @@ __global__ void k_constraints(Dev d) {
   }
 }
 
-// Camera block: Hcc, gc of the accepted state (from k_eval_tracks) + the Schur terms of k_points; point
+// Camera block: Hcc, gc of the accepted state (from k_eval_rows) + the Schur terms of k_points; point
 // gradient statistics into the system scalars.
 __global__ void __launch_bounds__(1024) k_add_camera(Dev d) {
   LmState* st = d.st;
@@ -1913,83 +1025,6 @@ __global__ void __launch_bounds__(128) k_init_norms(Dev d) {
 // ================================================================================================
 // launchers
 // ================================================================================================
-template <int NC, int NRAD, int PART>
-static void launch_eval_part(const Dev& d, int L, int grid, cudaStream_t s) {
-  switch (L) {
-    case 1: k_eval_tracks<NC, NRAD, 1, PART><<<grid, 128, 0, s>>>(d); break;
-    case 2: k_eval_tracks<NC, NRAD, 2, PART><<<grid, 128, 0, s>>>(d); break;
-    case 4: k_eval_tracks<NC, NRAD, 4, PART><<<grid, 128, 0, s>>>(d); break;
-    case 8: k_eval_tracks<NC, NRAD, 8, PART><<<grid, 128, 0, s>>>(d); break;
-    default: k_eval_tracks<NC, NRAD, 16, PART><<<grid, 128, 0, s>>>(d); break;
-  }
-}
-// mode 0: direct Jacobian-block sums, one pass; 1: the same in two passes; 2: software-pipelined stream kernel;
-// 3: feature/Gram form; 4: the same with a cp.async lens prefetch; 5: 9-feature Gram (lfba_gram2.cu);
-// 6 (default): 9-feature Gram over the packed stream with the cooperative lens gather (lfba_rows.cu)
-static int eval_mode() {
-  static const int m = [] {
-    const char* e = std::getenv("LFBA_EVAL_MODE");
-    return e ? std::atoi(e) : 6;
-  }();
-  return m;
-}
-template <int NC, int NRAD>
-static int launch_eval_nc(const Dev& d, int L, int grid, cudaStream_t s) {
-  const int mode = eval_mode();
-  if (mode == 2) {
-    switch (L) {
-      case 1: k_eval_stream<NC, NRAD, 1><<<grid, 128, 0, s>>>(d); break;
-      case 2: k_eval_stream<NC, NRAD, 2><<<grid, 128, 0, s>>>(d); break;
-      case 4: k_eval_stream<NC, NRAD, 4><<<grid, 128, 0, s>>>(d); break;
-      case 8: k_eval_stream<NC, NRAD, 8><<<grid, 128, 0, s>>>(d); break;
-      default: k_eval_stream<NC, NRAD, 16><<<grid, 128, 0, s>>>(d); break;
-    }
-    return 1;
-  }
-  if (mode == 0) {
-    launch_eval_part<NC, NRAD, 0>(d, L, grid, s);
-    return 1;
-  }
-  if (mode == 3) {
-    constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
-    const size_t smem = (size_t)NV * 128 * sizeof(double);
-    switch (L) {
-      case 1: k_eval_gram<NC, NRAD, 1, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 1, false><<<grid, 128, smem, s>>>(d); break;
-      case 2: k_eval_gram<NC, NRAD, 2, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 2, false><<<grid, 128, smem, s>>>(d); break;
-      case 4: k_eval_gram<NC, NRAD, 4, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 4, false><<<grid, 128, smem, s>>>(d); break;
-      case 8: k_eval_gram<NC, NRAD, 8, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 8, false><<<grid, 128, smem, s>>>(d); break;
-      default: k_eval_gram<NC, NRAD, 16, true><<<grid, 128, smem, s>>>(d); k_eval_gram<NC, NRAD, 16, false><<<grid, 128, smem, s>>>(d); break;
-    }
-    return 2;
-  }
-  if (mode == 4) {
-    constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
-    const size_t smem = (size_t)NV * 128 * sizeof(double) + 2 * 8 * 128 * sizeof(double2);
-    switch (L) {
-      case 1: k_eval_gram_pf<NC, NRAD, 1><<<grid, 128, smem, s>>>(d); break;
-      case 2: k_eval_gram_pf<NC, NRAD, 2><<<grid, 128, smem, s>>>(d); break;
-      case 4: k_eval_gram_pf<NC, NRAD, 4><<<grid, 128, smem, s>>>(d); break;
-      case 8: k_eval_gram_pf<NC, NRAD, 8><<<grid, 128, smem, s>>>(d); break;
-      default: k_eval_gram_pf<NC, NRAD, 16><<<grid, 128, smem, s>>>(d); break;
-    }
-    return 1;
-  }
-  launch_eval_part<NC, NRAD, 1>(d, L, grid, s);
-  launch_eval_part<NC, NRAD, 2>(d, L, grid, s);
-  return 2;
-}
-
-// (nRadial, tangential) -> compile-time <NC, NRAD>
-#define LFBA_DISPATCH_MODEL(NRADV, TANV, CALL)                                         \
-  switch ((NRADV) * 2 + ((TANV) ? 1 : 0)) {                                            \
-    case 0: { constexpr int NC = 5, NRAD = 0; CALL; } break;                           \
-    case 1: { constexpr int NC = 7, NRAD = 0; CALL; } break;                           \
-    case 2: { constexpr int NC = 6, NRAD = 1; CALL; } break;                           \
-    case 3: { constexpr int NC = 8, NRAD = 1; CALL; } break;                           \
-    case 4: { constexpr int NC = 7, NRAD = 2; CALL; } break;                           \
-    default: { constexpr int NC = 9, NRAD = 2; CALL; } break;                          \
-  }
-
 #define LFBA_DISPATCH_NC(NCV, CALL)   \
   switch (NCV) {                      \
     case 5: { constexpr int NC = 5; CALL; } break; \
@@ -1999,54 +1034,14 @@ static int launch_eval_nc(const Dev& d, int L, int grid, cudaStream_t s) {
     default: { constexpr int NC = 9; CALL; } break; \
   }
 
-template <int NC, int NRAD>
-static void prepare_eval_nc() {
-  constexpr int NV = NC * (NC + 1) / 2 + NC + 1;
-  const int smem = NV * 128 * (int)sizeof(double);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_eval_gram<NC, NRAD, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int smem2 = smem + 2 * 8 * 128 * (int)sizeof(double2);
-  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-  cudaFuncSetAttribute(k_eval_gram_pf<NC, NRAD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-}
-void prepare_eval_kernels() {
-  prepare_gram2_kernels();
-  prepare_rows_kernels();
-  prepare_eval_nc<5, 0>();
-  prepare_eval_nc<7, 0>();
-  prepare_eval_nc<6, 1>();
-  prepare_eval_nc<8, 1>();
-  prepare_eval_nc<7, 2>();
-  prepare_eval_nc<9, 2>();
-}
+void prepare_eval_kernels() { prepare_rows_kernels(); }
 void launch_tables(const Dev& d, cudaStream_t s) {
   const int n = d.NL > d.F ? d.NL : d.F;
   k_tables<<<(n + 127) / 128, 128, 0, s>>>(d);
 }
 int launch_eval(const Dev& d, int L, cudaStream_t s) {
-  if (eval_mode() == 5) {
-    launch_eval_gram2(d, L, s);
-    return 1;
-  }
-  if (eval_mode() == 6) {
-    launch_eval_rows(d, L, s);
-    return 1;
-  }
-  int n = 1;
-  const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
-  LFBA_DISPATCH_MODEL(nrad, tang, (n = launch_eval_nc<NC, NRAD>(d, L, d.grid_eval, s)));
-  return n;
+  launch_eval_rows(d, L, s);
+  return 1;
 }
 void launch_reduce_eval(const Dev& d, cudaStream_t s) { k_reduce_eval<<<1, 1024, 0, s>>>(d); }
 void launch_control_accept(const Dev& d, cudaStream_t s) { k_control_accept<<<1, 1, 0, s>>>(d); }
@@ -2058,18 +1053,11 @@ int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
   }
   if (d.refine_poses) {
     dim3 grid(d.F, frame_splits);
-    static const bool split_frames = std::getenv("LFBA_SPLIT_FRAME_KERNELS") != nullptr;  // A/B: the two-kernel form
-    if (split_frames) {
-      k_frame_pose<<<grid, 128, 0, s>>>(d);
-      LFBA_DISPATCH_NC(d.NC, (k_frame_cam<NC><<<grid, 128, 0, s>>>(d)));
-      launches += 2;
-    } else {
-      LFBA_DISPATCH_NC(d.NC, (k_frame_all<NC><<<grid, 128, 0, s>>>(d)));
+    LFBA_DISPATCH_NC(d.NC, (k_frame_all<NC><<<grid, 128, 0, s>>>(d)));
+    launches += 1;
+    if (frame_splits > 1) {
+      LFBA_DISPATCH_NC(d.NC, (k_frame_finish<NC><<<d.F, 128, 0, s>>>(d, frame_splits)));
       launches += 1;
-      if (frame_splits > 1) {
-        LFBA_DISPATCH_NC(d.NC, (k_frame_finish<NC><<<d.F, 128, 0, s>>>(d, frame_splits)));
-        launches += 1;
-      }
     }
     if (d.refine_points && d.npairs > 0) {
       int wpp = 1;  // warps per pair: enough CTAs x warps to cover the SMs a few times

@@ -21,9 +21,6 @@ int launch_steps(const Dev& d, cudaStream_t s);
 // forward-substituted), then the backward substitution into d.y. Returns the number of kernels launched.
 void prepare_device_kernels();
 void prepare_eval_kernels();
-// lfba_gram2.cu: fused evaluation, 9-feature Gram form with L1-prefetched lens gather
-void prepare_gram2_kernels();
-void launch_eval_gram2(const Dev& d, int lanes_per_track, cudaStream_t s);
 // lfba_rows.cu: fused evaluation over the packed stream, cooperative cp.async lens gather
 void prepare_rows_kernels();
 void launch_eval_rows(const Dev& d, int lanes_per_track, cudaStream_t s);

@@ -117,7 +117,6 @@ struct Solver {
   DevBuf<double> camera[2], views[2], points[2], lens, frames[2], rec[2], camsum[2], pdata, pscale, vw;
   DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one NCCL all-reduce)
   DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step, frame_part;
-  DevBuf<unsigned long long> lens_dev;
   DevBuf<CamModel> cm_buf;
   DevBuf<LmState> st;
   DevBuf<lfba_iteration> log;
@@ -338,8 +337,6 @@ struct Solver {
     vw.alloc((size_t)std::max(1, T) * kVWStride);
     st.alloc(1);
     log.alloc(kMaxLog);
-    lens_dev.alloc(1);
-    lens_dev.zero(stream);
     cm_buf.alloc(1);
     cm_buf.zero(stream);
 
@@ -396,7 +393,6 @@ struct Solver {
     d.pair_t1 = ix.pair_t1.p; d.pair_t2 = ix.pair_t2.p; d.npairs = ix.npairs; d.eval_order = ix.eval_order.p;
     d.s_obs = ix.s_obs.p; d.s_lid = ix.s_lid.p; d.step_base = ix.step_base.p;
     d.n_rounds = ix.n_rounds; d.n_rows = ix.n_rows; d.stream_L = ix.stream_L;
-    if (std::getenv("LFBA_EVAL_ORDER") && std::atoi(std::getenv("LFBA_EVAL_ORDER")) == 0) d.eval_order = nullptr;  // experiment: storage order
     d.pt_coupled = pt_coupled.p; d.coupled_pts = coupled_pts.p; d.pt_active = pt_active.p; d.frm_active = frm_active.p;
     d.c_p1 = c_p1.p; d.c_p2 = c_p2.p; d.c_dist = c_dist.p; d.c_sigma = c_sigma.p;
     for (int c = 0; c < 17; ++c) {
@@ -407,9 +403,8 @@ struct Solver {
       d.camera[b] = camera[b].p; d.views[b] = views[b].p; d.points[b] = points[b].p;
       d.frames[b] = frames[b].p; d.rec[b] = rec[b].p; d.camsum[b] = camsum[b].p;
     }
-    d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.lens_dev = lens_dev.p; d.cm_buf = cm_buf.p;
-    // measured on B200: the implicit form (fewer gathered bytes, ~75 more FP64 ops) is slower than the table: opt-in only
-    d.implicit_tol = std::getenv("LFBA_IMPLICIT_TOL") ? std::atof(std::getenv("LFBA_IMPLICIT_TOL")) : -1.0; d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p;
+    d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.cm_buf = cm_buf.p;
+    d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p;
     d.S = redbuf.p; d.row_off = row_off.p; d.row_c0 = row_c0.p;
     d.g = redbuf.p + S_len; d.gfull = d.g + n; d.hdiag = d.gfull + n; d.sys_scalars = d.hdiag + n;
     d.rscale = rscale.p; d.rdamp = rdamp.p; d.y = y.p; d.eval_scalars = eval_scalars.p;
@@ -478,7 +473,6 @@ struct Solver {
     init.decrease_factor = 2.0;
     if (!camera0.p) throw CudaError("lfba_solver_run before lfba_solver_set_parameters", LFBA_INVALID_ARGUMENT);
     reset_parameters();  // every run starts from the parameters last given by the caller
-    lens_dev.zero(stream);
     LFBA_CUDA(cudaMemcpyAsync(st.p, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
     if (calib_type == LFBA_RECALIBRATION) {
       // IterationZero of a bounds-constrained problem projects the start point into the box
@@ -570,11 +564,6 @@ struct Solver {
                      hs.x_cost, hs.radius, hs.mcc_red, hs.step2_red, hs.norm2_red, hp[0], hp[1], hp[2]);
         double ymax = 0;
         for (int j = 0; j < d.n; ++j) ymax = std::max(ymax, std::fabs(hy[j]));
-        unsigned long long hdev = 0;
-        LFBA_CUDA(cudaMemcpy(&hdev, lens_dev.p, 8, cudaMemcpyDeviceToHost));
-        double ddev;
-        std::memcpy(&ddev, &hdev, 8);
-        std::fprintf(stderr, "[lfba dbg]   lens implicit-vs-exact deviation = %.3e\n", ddev);
         std::fprintf(stderr, "[lfba dbg]   |y|max=%.6e y[0..5]=%.4e %.4e %.4e %.4e %.4e %.4e\n", ymax, hy[0], hy[1], hy[2],
                      d.n > 3 ? hy[3] : 0.0, d.n > 4 ? hy[4] : 0.0, d.n > 5 ? hy[5] : 0.0);
       }
