@@ -14,9 +14,12 @@
 using namespace lfba;
 
 static double g_feature_worst = 0.0;
+static double g_feature9_worst = 0.0;  // the form k_eval_rows uses: NC features, weighted Gram, gram9_expand
 static double g_cancel_sum[3] = {0,0,0}, g_cancel_n[3] = {0,0,0}, g_cancel_max[3] = {0,0,0};
 extern "C" void harness_cancel(double* out) { for (int c = 0; c < 3; ++c) { out[2*c] = g_cancel_sum[c] / (g_cancel_n[c] + 1e-300); out[2*c+1] = g_cancel_max[c]; } }
 extern "C" double harness_feature_worst(void) { return g_feature_worst; }
+extern "C" double harness_feature9_worst(void) { return g_feature9_worst; }
+extern "C" void harness_feature_reset(void) { g_feature_worst = 0.0; g_feature9_worst = 0.0; }
 
 template <int NC, int NRAD>
 static void eval_all(const lfba_problem* pb, const CamModel& m, const double* views, const double* points,
@@ -56,6 +59,39 @@ static void eval_all(const lfba_problem* pb, const CamModel& m, const double* vi
         for (int b = 0; b < 3; ++b) chk(GramMap<NC>::gg(t, g, a, b), G[a] * G[b] + G[3 + a] * G[3 + b]);
       }
       if (worst > g_feature_worst) g_feature_worst = worst;
+      {  // what the fused kernel does: NC features (f2 dropped), Gram weighted as (w f_a).f_b, rebuilt by gram9_expand
+        constexpr int NF9 = Feat9Dims<NC>::NF, NQ9 = Feat9Dims<NC>::NQ;
+        double r9[2], F9[2 * NF9], g9[NQ9 + NF9], go[NQ + NF];
+        obs_features9<NC, NRAD>(m, t, le, pb->obs_x[i], pb->obs_y[i], r9, F9);
+        const double s9 = r9[0] * r9[0] + r9[1] * r9[1];
+        const double w = 1.0 / (1.0 + s9 * m.loss_c);  // rho' of the Cauchy loss
+        int q9 = 0;
+        for (int a = 0; a < NF9; ++a) {
+          const double wx = w * F9[a], wy = w * F9[NF9 + a];
+          for (int b = 0; b <= a; ++b) g9[q9++] = wx * F9[b] + wy * F9[NF9 + b];
+          g9[NQ9 + a] = wx * r9[0] + wy * r9[1];
+        }
+        gram9_expand<NC>(t, t.a1 * m.gamma, g9, go);
+        double worst9 = 0.0;
+        auto chk9 = [&](double a, double b, double scale) {
+          if (scale > 0 && fabs(a - b) / scale > worst9) worst9 = fabs(a - b) / scale;
+        };
+        if (r9[0] != r[0] || r9[1] != r[1]) worst9 = 1.0;
+        // compare against w * (Jacobian block products); scale = product of the column norms (Cauchy-Schwarz bound)
+        auto nrm = [&](const double* v, int i0, int i1) { return sqrt(v[i0] * v[i0] + v[i1] * v[i1]); };
+        for (int c1 = 0; c1 < NC; ++c1)
+          for (int c2 = 0; c2 <= c1; ++c2)
+            chk9(GramMap<NC>::cc(t, go, c1, c2), w * (J[c1] * J[c2] + J[NC + c1] * J[NC + c2]),
+                 w * nrm(J, c1, NC + c1) * nrm(J, c2, NC + c2));
+        for (int a = 0; a < 3; ++a) {
+          for (int c = 0; c < NC; ++c)
+            chk9(GramMap<NC>::gcam(t, go, a, c), w * (G[a] * J[c] + G[3 + a] * J[NC + c]), w * nrm(G, a, 3 + a) * nrm(J, c, NC + c));
+          for (int b = 0; b < 3; ++b)
+            chk9(GramMap<NC>::gg(t, go, a, b), w * (G[a] * G[b] + G[3 + a] * G[3 + b]), w * nrm(G, a, 3 + a) * nrm(G, b, 3 + b));
+          chk9((a == 2 ? -t.g1 : t.g1) * go[NQ + a], w * (G[a] * r[0] + G[3 + a] * r[1]), w * nrm(G, a, 3 + a) * sqrt(s9));
+        }
+        if (worst9 > g_feature9_worst) g_feature9_worst = worst9;
+      }
       for (int c = 0; c < 3; ++c) {
         double a, b;
         GramMap<NC>::geo(t, c, a, b);

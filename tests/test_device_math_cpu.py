@@ -88,6 +88,24 @@ def test_analytic_jacobian_matches_oracle_autodiff_random(harness):
         assert _colrel(jp, o["jac_point"]) < 1e-12
 
 
+def test_feature_gram_forms_reproduce_jacobian_products(harness):
+    """The fused kernel never forms the Jacobian: it accumulates the weighted Gram matrix of NC two-component features
+    and expands it per track (obs_features9 + gram9_expand + GramMap). On single observations that expansion must
+    equal w * (Jacobian block products) up to rounding — for every model-flag combination, random poses/points."""
+    harness.harness_feature_worst.restype = C.c_double
+    harness.harness_feature9_worst.restype = C.c_double
+    harness.harness_feature_reset()
+    rng = np.random.default_rng(7)
+    for mc in helpers.all_model_configs():
+        cfg = mc | capi.CFG_REFINE_POSES | capi.CFG_REFINE_POINTS
+        b = helpers.random_blocks(rng, cfg, 200, signs=True)
+        n = 200
+        pa = capi.ProblemArrays(cfg, 0, b["spx"], b["spy"], b["scale"], n, n, b["obs"][:, 0], b["obs"][:, 1],
+                                b["ml"][:, 0], b["ml"][:, 1], np.arange(n), np.arange(n))
+        _eval(harness, pa, b["cams"][0], b["views"].ravel(), b["points"].ravel())
+    assert harness.harness_feature9_worst() < 1e-9, harness.harness_feature9_worst()
+
+
 def test_spd3_inverse_and_distance(harness):
     rng = np.random.default_rng(0)
     for _ in range(100):
