@@ -70,3 +70,23 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 for b in banned:
                     assert b not in src, f"{f} references {b}"
+
+
+def test_bench_reference_arm_prints_contract_line(built):
+    """`bench.py --impl reference` (the CPU oracle on the host cores) prints ONE JSON line with the contract keys; it
+    needs no GPU. cfg1 = BASELINE.json configs[0], the reference's own CPU-runnable case."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                        "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "lm_residual_jacobian_evals_per_s" and d["unit"] == "M evals/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "M evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
