@@ -23,6 +23,7 @@ CASES = {1e5: (900, 40), 1e6: (9000, 100), 1e7: (90000, 300), 1e8: (900000, 1000
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-obs", type=float, default=1e8)
+    ap.add_argument("--min-obs", type=float, default=0.0)
     args = ap.parse_args()
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     import torch
@@ -33,7 +34,7 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", lr))
         comm = api.Communicator(rank, world, bench.broadcast_unique_id(api.comm_unique_id() if rank == 0 else None))
     for target, (npts, nfr) in CASES.items():
-        if target > args.max_obs:
+        if target > args.max_obs or target < args.min_obs:
             continue
         for robust in (1, 0):
             for nrad in (0, 1, 2):
