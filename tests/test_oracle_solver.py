@@ -99,3 +99,47 @@ def test_scene_generator_is_deterministic_and_shardable(built):
     # float32 round trip of observations and lens centres (src/CameraCalibration.cpp:748-762)
     assert np.array_equal(a.problem.obs_x, a.problem.obs_x.astype(np.float32).astype(np.float64))
     assert np.array_equal(a.problem.ml_x, a.problem.ml_x.astype(np.float32).astype(np.float64))
+
+
+def test_oracle_minimum_agrees_with_an_independent_solver(built):
+    """Ceres is not available here, so the LM loop of the oracle is 'parity unpinned'. An independent check that it at
+    least lands in the right place: scipy's trust-region least squares on the SAME residuals/Jacobians (non-robust
+    cost, so that both minimise 0.5 sum r^2) must reach the same minimum cost. This does not pin Ceres' iteration
+    semantics (those are covered by the invariants above), only the fixed point."""
+    from scipy.optimize import least_squares
+    cfg = 2 | capi.CFG_TANGENTIAL | capi.CFG_MLADJ | capi.CFG_REFINE_POSES | capi.CFG_REFINE_POINTS  # no robust loss
+    sc = capi.make_scene(None, n_points=40, n_frames=4, seed=123, config=cfg)
+    pa = sc.problem
+    F, P, n = pa.n_frames, pa.n_points, pa.n_obs
+    live = 9
+
+    def unpack(x):
+        cam = sc.camera_init.copy()
+        cam[:live] = x[:live]
+        return cam, x[live:live + 6 * F].copy(), x[live + 6 * F:].copy()
+
+    def fun(x):
+        cam, vw, pt = unpack(x)
+        return ob.evaluate(pa, cam, vw, pt, jacobians=False)["residuals"].ravel()
+
+    def jac(x):
+        cam, vw, pt = unpack(x)
+        e = ob.evaluate(pa, cam, vw, pt)
+        J = np.zeros((2 * n, live + 6 * F + 3 * P))
+        rows = np.arange(2 * n).reshape(n, 2)
+        J[:, :live] = e["jac_camera"].reshape(2 * n, 17)[:, :live]
+        for i in range(n):
+            f, p = pa.frame_idx[i], pa.point_idx[i]
+            J[rows[i], live + 6 * f:live + 6 * f + 6] = e["jac_view"][i]
+            J[rows[i], live + 6 * F + 3 * p:live + 6 * F + 3 * p + 3] = e["jac_point"][i]
+        return J
+
+    x0 = np.concatenate([sc.camera_init[:live], sc.views_init, sc.points_init])
+    ref = least_squares(fun, x0, jac=jac, method="trf", x_scale="jac", ftol=1e-14, xtol=1e-14, gtol=1e-14, max_nfev=200)
+    o = ob.default_options(function_tolerance=1e-13, parameter_tolerance=1e-13, max_num_iterations=200)
+    _, _, _, s = ob.solve(pa, sc.camera_init, sc.views_init, sc.points_init, options=o, threads=2)
+    assert ref.cost > 0
+    assert abs(s["final_cost"] - ref.cost) <= 1e-6 * ref.cost, (s["final_cost"], ref.cost)
+    # with the reference's own tolerances (ftol 1e-6) the oracle stops slightly above that minimum, never below it
+    _, _, _, s2 = ob.solve(pa, sc.camera_init, sc.views_init, sc.points_init, threads=2)
+    assert ref.cost * (1 - 1e-9) <= s2["final_cost"] <= ref.cost * (1 + 1e-3)
