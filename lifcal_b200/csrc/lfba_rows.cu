@@ -5,10 +5,13 @@
 // 120-222, src/CameraCalibration.cpp:871-913) fused with the Jacobian-block products of SchurEliminator (E^T E, E^T F,
 // F^T F per residual block). The Jacobian never leaves registers.
 //
-// Arithmetic: identical to k_eval_gram2 (lfba_gram2.cu): NC two-component features per observation, weighted Gram
-// (54 running sums for NC = 9), expanded once per track into the track record (A, b, C) and the camera block (Hcc, gc).
+// Arithmetic: NC two-component FEATURES per observation (lfba_math.cuh, obs_features9: every Jacobian column of an
+// observation is a per-track combination of them), weighted Gram matrix (54 running sums for NC = 9; Cauchy weight
+// w = rho' applied as (w f_a).f_b, no square roots; cost = one log of the running product per lane and track), expanded
+// once per track into the track record (A, b, C) and the camera block (Hcc, gc) — tests/test_device_math_cpu.py pins that
+// expansion against the Jacobian block products.
 //
-// Memory system — why this kernel exists. ncu on k_eval_gram / k_eval_gram2 showed the L1TEX data pipe at 76% with the FP64
+// Memory system — why the kernel looks like this. ncu on its predecessors (one gather per lane) showed the L1TEX data pipe at 76% with the FP64
 // pipe at 31%: every observation gathers its 128-byte lens-table entry as 8 x LDG.128, and with one observation per lane
 // each of those warp instructions touches 32 different lines = 32 wavefronts (256 per warp step). Here
 //   * the observations are pre-arranged at set-up in the order the kernel consumes them (lfba_setup.cuh, build_stream):
