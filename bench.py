@@ -173,7 +173,13 @@ def run_cpu_baseline(workload: str, small: bool, steps: int = 1, warmup: int = 0
     from oracle import binding as ob
     spec, desc = cpu_sample_spec(workload, small)
     sc = capi.Scene(spec)
-    threads = ob.max_threads()
+    # all host cores this process may use — torchrun exports OMP_NUM_THREADS=1, which would silently make the reference
+    # arm single-threaded at N > 1
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    threads = max(ob.max_threads(), ncores)
     times, evals, iters = [], 0, 0
     for k in range(warmup + steps):
         t0 = time.perf_counter()
