@@ -36,6 +36,7 @@ def lib():
                                   C.c_double, C.c_int, C.c_void_p]
         L.oracle_solve.argtypes = [C.POINTER(capi.Problem), C.POINTER(capi.Options), c_double_p, c_double_p,
                                    c_double_p, C.POINTER(capi.Summary), C.c_int, C.c_double, C.c_void_p]
+        L.oracle_solve_streaming.argtypes = L.oracle_solve.argtypes
         L.oracle_time_eval.argtypes = [C.POINTER(capi.Problem), c_double_p, c_double_p, c_double_p, C.c_int,
                                        C.c_int, c_double_p]
         L.oracle_max_threads.restype = C.c_int
@@ -122,8 +123,9 @@ def evaluate(pa: capi.ProblemArrays, camera, views, points, jacobians=True, thre
 
 
 def solve(pa: capi.ProblemArrays, camera, views, points, options=None, threads=0, max_seconds=0.0,
-          use_ref=False):
-    """Returns (camera, views, points, summary_dict); inputs are not modified."""
+          use_ref=False, streaming=False):
+    """Returns (camera, views, points, summary_dict); inputs are not modified. streaming=True: Jacobian-free
+    block-recompute mode (oracle_solve_streaming) for scenes whose stored Jacobian would not fit the host."""
     L = lib()
     cam = np.array(camera, np.float64, copy=True)
     vw = np.array(views, np.float64, copy=True)
@@ -132,10 +134,12 @@ def solve(pa: capi.ProblemArrays, camera, views, points, options=None, threads=0
     s, rows = capi.new_summary(max(8, o.max_num_iterations + 8))
     p = pa.as_struct()
     fn = ref_block_fn_ptr() if use_ref else None
-    rc = L.oracle_solve(C.byref(p), C.byref(o), capi._dp(cam), capi._dp(vw), capi._dp(pt), C.byref(s), threads,
-                        max_seconds, fn)
+    entry = L.oracle_solve_streaming if streaming else L.oracle_solve
+    rc = entry(C.byref(p), C.byref(o), capi._dp(cam), capi._dp(vw), capi._dp(pt), C.byref(s), threads,
+               max_seconds, fn)
     d = capi.summary_to_dict(s, rows)
     d["status"] = rc
+    d["block_passes"] = d.pop("num_lenses") if streaming else 0
     return cam, vw, pt, d
 
 

@@ -257,17 +257,200 @@ struct Evaluator {
   oracle_block_fn fn;
   // Jacobian storage (Ceres block layout, 416 B per observation with all three blocks)
   std::vector<double> Jc, Jv, Jp, Jk;  // Jk: constraints, [K][2][3] (point1 | point2)
-  std::vector<double> r;               // 2N + K
+  std::vector<double> r;               // 2N + K   (streaming: K, the constraint residuals only)
   int64_t num_jac_evals = 0, num_cost_evals = 0;
+  int64_t num_block_recomputes = 0;    // streaming: passes over all reprojection blocks (autodiff re-evaluations)
+
+  // ---- streaming ("Jacobian-free", block-recompute) mode --------------------------------------------------------
+  // Ceres stores the block-sparse Jacobian (416 B per observation: 41.6 GB at the 1M x 1000 scene). In streaming mode
+  // nothing O(N) is stored: the evaluator keeps the linearisation point and the column scale, and the corrected,
+  // scaled block rows of ONE point's observations are recomputed into a thread-local chunk wherever the stored
+  // Jacobian would be read (evaluation, Schur elimination, back-substitution / model cost change). Same arithmetic
+  // per block; only the summation order of the camera / pose sums differs (by points instead of by input index).
+  bool streaming = false;
+  std::vector<double> lin_camera, lin_views, lin_points;  // point at which the Jacobian is defined
+  std::vector<double> col_scale;                          // Jacobi scale applied on recompute (tangent layout)
+  std::vector<double> cn2;                                // squared column norms of the corrected, unscaled Jacobian
+  struct Chunk {
+    std::vector<double> jc, jv, jp, r;
+    int64_t b0 = 0;
+  };
+  struct Rows {
+    const double *jc, *jv, *jp, *r;
+  };
 
   Evaluator(const Program& prog, double a, int nt, oracle_block_fn f) : g(prog), loss_a(a), nthreads(nt), fn(f) {}
 
   void alloc_jacobian() {
+    if (streaming && !g.has_points) streaming = false;  // nothing to chunk by: the stored form is small anyway
+    Jk.resize((size_t)g.K * 6);
+    if (streaming) {
+      r.resize((size_t)g.K);
+      col_scale.assign((size_t)g.n_t, 1.0);
+      return;
+    }
     Jc.resize((size_t)g.N * 34);
     if (g.has_views) Jv.resize((size_t)g.N * 12);
     if (g.has_points) Jp.resize((size_t)g.N * 6);
-    Jk.resize((size_t)g.K * 6);
     r.resize((size_t)g.N * 2 + g.K);
+  }
+  double& rk(int k) { return streaming ? r[(size_t)k] : r[(size_t)2 * g.N + k]; }
+  double rk(int k) const { return streaming ? r[(size_t)k] : r[(size_t)2 * g.N + k]; }
+
+  // corrected (and, if `scaled`, column-scaled) block rows of every observation of point p at the linearisation
+  // point; returns the point's share of the cost
+  double fill_chunk(int p, bool scaled, Chunk& ch) const {
+    const int64_t b0 = g.pt_begin[p], b1 = g.pt_begin[p + 1];
+    const size_t m = (size_t)(b1 - b0);
+    ch.b0 = b0;
+    if (ch.jc.size() < m * 34) {
+      ch.jc.resize(m * 34);
+      ch.jv.resize(m * 12);
+      ch.jp.resize(m * 6);
+      ch.r.resize(m * 2);
+    }
+    double cost = 0.0;
+    for (int64_t e = b0; e < b1; ++e) {
+      const int64_t i = g.pt_obs[e];
+      const size_t k = (size_t)(e - b0);
+      double* jc = &ch.jc[k * 34];
+      double* jv = g.has_views ? &ch.jv[k * 12] : nullptr;
+      double* jp = g.has_points ? &ch.jp[k * 6] : nullptr;
+      double rr[2];
+      block_autodiff(g, i, lin_camera.data(), lin_views.data(), lin_points.data(), rr, jc, jv, jp, fn);
+      const double s = rr[0] * rr[0] + rr[1] * rr[1];
+      if (g.cfg.robust) {
+        double rho[3];
+        cauchy(loss_a, s, rho);
+        cost += 0.5 * rho[0];
+        const double sq = std::sqrt(rho[1]);
+        if (s == 0.0 || rho[2] <= 0.0) {
+          for (int j = 0; j < 34; ++j) jc[j] *= sq;
+          if (jv)
+            for (int j = 0; j < 12; ++j) jv[j] *= sq;
+          if (jp)
+            for (int j = 0; j < 6; ++j) jp[j] *= sq;
+          rr[0] *= sq;
+          rr[1] *= sq;
+        }
+      } else {
+        cost += 0.5 * s;
+      }
+      ch.r[2 * k] = rr[0];
+      ch.r[2 * k + 1] = rr[1];
+      if (scaled) {
+        const double* sc = col_scale.data();
+        for (int j = 0; j < g.n_cam_t; ++j) {
+          const int c = g.cam_cols[j];
+          jc[c] *= sc[j];
+          jc[17 + c] *= sc[j];
+        }
+        if (jv) {
+          const int o = g.off_view(g.view_slot[g.fidx[i]]);
+          for (int j = 0; j < 6; ++j) {
+            jv[j] *= sc[(size_t)o + j];
+            jv[6 + j] *= sc[(size_t)o + j];
+          }
+        }
+        if (jp) {
+          const int o = g.off_point(g.point_slot[g.pidx[i]]);
+          for (int j = 0; j < 3; ++j) {
+            jp[j] *= sc[(size_t)o + j];
+            jp[3 + j] *= sc[(size_t)o + j];
+          }
+        }
+      }
+    }
+    return cost;
+  }
+  // block rows of the e-th observation in point order (e indexes pt_obs)
+  inline Rows rows(int64_t e, const Chunk* ch) const {
+    if (!streaming) {
+      const size_t i = (size_t)g.pt_obs[e];
+      return Rows{&Jc[i * 34], g.has_views ? &Jv[i * 12] : nullptr, g.has_points ? &Jp[i * 6] : nullptr, &r[2 * i]};
+    }
+    const size_t k = (size_t)(e - ch->b0);
+    return Rows{&ch->jc[k * 34], g.has_views ? &ch->jv[k * 12] : nullptr, g.has_points ? &ch->jp[k * 6] : nullptr,
+                &ch->r[2 * k]};
+  }
+
+  // streaming evaluate: cost, tangent gradient and cn2 in one pass over the points
+  double evaluate_streaming(const double* camera, const double* views, const double* points, std::vector<double>& grad) {
+    lin_camera.assign(camera, camera + 17);
+    lin_views.assign(views, views + (size_t)6 * g.F);
+    lin_points.assign(points, points + (size_t)3 * g.P);
+    ++num_block_recomputes;
+    const int nv = (int)g.active_frames.size();
+    const int ncv = g.n_cam_t + 6 * nv;
+    const int ne = (int)g.active_points.size();
+    std::vector<std::vector<double>> gth((size_t)nthreads, std::vector<double>((size_t)2 * ncv, 0.0));
+    grad.assign((size_t)g.n_t, 0.0);
+    cn2.assign((size_t)g.n_t, 0.0);
+    double cost = 0.0;
+#pragma omp parallel num_threads(nthreads)
+    {
+      std::vector<double>& gl = gth[(size_t)omp_get_thread_num()];
+      double* nl = gl.data() + ncv;
+      Chunk ch;
+      double lcost = 0.0;
+#pragma omp for schedule(static)
+      for (int s = 0; s < ne; ++s) {
+        const int p = g.active_points[s];
+        lcost += fill_chunk(p, false, ch);
+        double gp[3] = {0, 0, 0}, np_[3] = {0, 0, 0};
+        for (int64_t e = g.pt_begin[p]; e < g.pt_begin[p + 1]; ++e) {
+          const Rows w = rows(e, &ch);
+          for (int j = 0; j < g.n_cam_t; ++j) {
+            const int c = g.cam_cols[j];
+            gl[j] += w.jc[c] * w.r[0] + w.jc[17 + c] * w.r[1];
+            nl[j] += w.jc[c] * w.jc[c] + w.jc[17 + c] * w.jc[17 + c];
+          }
+          if (w.jv) {
+            const int o = g.off_view(g.view_slot[g.fidx[g.pt_obs[e]]]);
+            for (int j = 0; j < 6; ++j) {
+              gl[o + j] += w.jv[j] * w.r[0] + w.jv[6 + j] * w.r[1];
+              nl[o + j] += w.jv[j] * w.jv[j] + w.jv[6 + j] * w.jv[6 + j];
+            }
+          }
+          for (int j = 0; j < 3; ++j) {
+            gp[j] += w.jp[j] * w.r[0] + w.jp[3 + j] * w.r[1];
+            np_[j] += w.jp[j] * w.jp[j] + w.jp[3 + j] * w.jp[3 + j];
+          }
+        }
+        for (int j = 0; j < 3; ++j) {
+          grad[(size_t)g.off_point(s) + j] = gp[j];
+          cn2[(size_t)g.off_point(s) + j] = np_[j];
+        }
+      }
+#pragma omp atomic
+      cost += lcost;
+    }
+    for (int t = 0; t < nthreads; ++t)
+      for (int j = 0; j < ncv; ++j) {
+        grad[j] += gth[t][j];
+        cn2[j] += gth[t][(size_t)ncv + j];
+      }
+    for (int k = 0; k < g.K; ++k) {
+      typedef Dual<6> D;
+      D p1[3], p2[3], res;
+      for (int j = 0; j < 3; ++j) {
+        p1[j] = D(points[3 * g.c1[k] + j], j);
+        p2[j] = D(points[3 * g.c2[k] + j], 3 + j);
+      }
+      distance_residual<D>(g.cdist[k], g.csigma[k], p1, p2, &res);
+      for (int j = 0; j < 6; ++j) Jk[(size_t)6 * k + j] = res.v[j];
+      rk(k) = res.a;
+      cost += 0.5 * res.a * res.a;
+      const int o1 = g.off_point(g.point_slot[g.c1[k]]), o2 = g.off_point(g.point_slot[g.c2[k]]);
+      for (int j = 0; j < 3; ++j) {
+        grad[(size_t)o1 + j] += res.v[j] * res.a;
+        grad[(size_t)o2 + j] += res.v[3 + j] * res.a;
+        cn2[(size_t)o1 + j] += res.v[j] * res.v[j];
+        cn2[(size_t)o2 + j] += res.v[3 + j] * res.v[3 + j];
+      }
+    }
+    std::fill(col_scale.begin(), col_scale.end(), 1.0);  // a fresh evaluation is unscaled until scale_columns()
+    return cost;
   }
 
   double cost_only(const double* camera, const double* views, const double* points) {
@@ -297,6 +480,7 @@ struct Evaluator {
   // Fills r, J (corrected, NOT yet column-scaled) and the tangent gradient.
   double evaluate(const double* camera, const double* views, const double* points, std::vector<double>& grad) {
     ++num_jac_evals;
+    if (streaming) return evaluate_streaming(camera, views, points, grad);
     double cost = 0.0;
     const int nv = (int)g.active_frames.size();
     const int ncv = g.n_cam_t + 6 * nv;  // camera + views part of the gradient is accumulated per thread
@@ -371,7 +555,7 @@ struct Evaluator {
       }
       distance_residual<D>(g.cdist[k], g.csigma[k], p1, p2, &res);
       for (int j = 0; j < 6; ++j) Jk[(size_t)6 * k + j] = res.v[j];
-      r[(size_t)2 * g.N + k] = res.a;
+      rk(k) = res.a;
       cost += 0.5 * res.a * res.a;
       const int o1 = g.off_point(g.point_slot[g.c1[k]]), o2 = g.off_point(g.point_slot[g.c2[k]]);
       for (int j = 0; j < 3; ++j) {
@@ -384,6 +568,11 @@ struct Evaluator {
 
   // squared column norms of the stored Jacobian (tangent columns)
   void squared_column_norms(std::vector<double>& out) const {
+    if (streaming) {  // |J s|^2 column-wise = s^2 |J|^2 (J unscaled at the linearisation point)
+      out.resize((size_t)g.n_t);
+      for (int j = 0; j < g.n_t; ++j) out[j] = cn2[j] * col_scale[j] * col_scale[j];
+      return;
+    }
     const int nv = (int)g.active_frames.size();
     const int ncv = g.n_cam_t + 6 * nv;
     out.assign((size_t)g.n_t, 0.0);
@@ -430,6 +619,17 @@ struct Evaluator {
 
   // J <- J * diag(scale)   (jacobian_->ScaleColumns)
   void scale_columns(const std::vector<double>& sc) {
+    if (streaming) {  // applied when a chunk is recomputed
+      col_scale = sc;
+      for (int k = 0; k < g.K; ++k) {
+        const int o1 = g.off_point(g.point_slot[g.c1[k]]), o2 = g.off_point(g.point_slot[g.c2[k]]);
+        for (int j = 0; j < 3; ++j) {
+          Jk[(size_t)6 * k + j] *= sc[(size_t)o1 + j];
+          Jk[(size_t)6 * k + 3 + j] *= sc[(size_t)o2 + j];
+        }
+      }
+      return;
+    }
 #pragma omp parallel for schedule(static) num_threads(nthreads)
     for (int64_t i = 0; i < g.N; ++i) {
       double* jc = &Jc[(size_t)i * 34];
@@ -499,7 +699,7 @@ struct Evaluator {
       double m = 0;
       for (int j = 0; j < 3; ++j)
         m += Jk[(size_t)6 * k + j] * step[(size_t)o1 + j] + Jk[(size_t)6 * k + 3 + j] * step[(size_t)o2 + j];
-      acc += m * (r[(size_t)2 * g.N + k] + m / 2.0);
+      acc += m * (rk(k) + m / 2.0);
     }
     return -acc;
   }
@@ -592,6 +792,7 @@ struct SchurSolver {
   const Evaluator& ev;
   int nthreads;
   std::vector<double> S, rhs;
+  double model_cost_change = 0.0;  // streaming mode: -m.(r + m/2), m = J (-y), formed during back-substitution
 
   SchurSolver(const Program& prog, const Evaluator& e, int nt) : g(prog), ev(e), nthreads(nt) {}
 
@@ -603,27 +804,31 @@ struct SchurSolver {
     const double* j[3];
     int stride[3];
   };
-  inline void row_blocks(int64_t i, RowBlocks& rb) const {
+  inline void row_blocks(int64_t i, const Evaluator::Rows& w, RowBlocks& rb) const {
     rb.nblk = 0;
     rb.off[rb.nblk] = 0;
     rb.width[rb.nblk] = g.n_cam_t;
-    rb.j[rb.nblk] = &ev.Jc[(size_t)i * 34];
+    rb.j[rb.nblk] = w.jc;
     rb.stride[rb.nblk] = 17;
     rb.nblk++;
     if (g.has_views) {
       rb.off[rb.nblk] = g.red_view(g.view_slot[g.fidx[i]]);
       rb.width[rb.nblk] = 6;
-      rb.j[rb.nblk] = &ev.Jv[(size_t)i * 12];
+      rb.j[rb.nblk] = w.jv;
       rb.stride[rb.nblk] = 6;
       rb.nblk++;
     }
     if (g.has_points && g.coupled[g.pidx[i]]) {
       rb.off[rb.nblk] = g.red_point(g.coupled_slot[g.pidx[i]]);
       rb.width[rb.nblk] = 3;
-      rb.j[rb.nblk] = &ev.Jp[(size_t)i * 6];
+      rb.j[rb.nblk] = w.jp;
       rb.stride[rb.nblk] = 3;
       rb.nblk++;
     }
+  }
+  inline Evaluator::Rows rows_of_input(int64_t i) const {  // stored mode only: rows of input observation i
+    return Evaluator::Rows{&ev.Jc[(size_t)i * 34], g.has_views ? &ev.Jv[(size_t)i * 12] : nullptr,
+                           g.has_points ? &ev.Jp[(size_t)i * 6] : nullptr, &ev.r[(size_t)2 * i]};
   }
   inline double jval(const RowBlocks& rb, int b, int row, int c) const {
     // camera block: tangent column c -> ambient column
@@ -642,6 +847,7 @@ struct SchurSolver {
     const int ne = g.has_points ? (int)g.active_points.size() : 0;
     std::vector<double> inv_ete((size_t)ne * 9, 0.0);
     bool ok = true;
+    if (ev.streaming) const_cast<Evaluator&>(ev).num_block_recomputes += 2;  // elimination + back-substitution
 
 #pragma omp parallel num_threads(nthreads)
     {
@@ -650,6 +856,7 @@ struct SchurSolver {
       std::vector<double> buf((size_t)3 * n);  // E^T F for the current chunk, 3 x n (dense row, sparse use)
       std::vector<int> touched;
       std::vector<char> mark((size_t)n, 0);
+      Evaluator::Chunk chunk;
 
       // F^T F and F^T r of one row into the thread-local lower triangle
       auto add_row = [&](const RowBlocks& rb, const double rr[2], bool add_rhs) {
@@ -672,19 +879,22 @@ struct SchurSolver {
 #pragma omp for schedule(static)
         for (int64_t i = 0; i < g.N; ++i) {
           RowBlocks rb;
-          row_blocks(i, rb);
-          add_row(rb, &ev.r[(size_t)2 * i], true);
+          const Evaluator::Rows w = rows_of_input(i);
+          row_blocks(i, w, rb);
+          add_row(rb, w.r, true);
         }
       } else {
 #pragma omp for schedule(dynamic, 64)
         for (int s = 0; s < ne; ++s) {
           const int p = g.active_points[s];
           const int64_t b0 = g.pt_begin[p], b1 = g.pt_begin[p + 1];
+          if (ev.streaming) ev.fill_chunk(p, true, chunk);
           if (g.coupled[p]) {  // rows without an e-block (NoEBlockRowsUpdate)
             for (int64_t e = b0; e < b1; ++e) {
               RowBlocks rb;
-              row_blocks(g.pt_obs[e], rb);
-              add_row(rb, &ev.r[(size_t)2 * g.pt_obs[e]], true);
+              const Evaluator::Rows w = ev.rows(e, &chunk);
+              row_blocks(g.pt_obs[e], w, rb);
+              add_row(rb, w.r, true);
             }
             continue;
           }
@@ -695,14 +905,15 @@ struct SchurSolver {
           touched.clear();
           for (int64_t e = b0; e < b1; ++e) {
             const int64_t i = g.pt_obs[e];
-            const double* jp = &ev.Jp[(size_t)i * 6];
-            const double* rr = &ev.r[(size_t)2 * i];
+            const Evaluator::Rows w = ev.rows(e, &chunk);
+            const double* jp = w.jp;
+            const double* rr = w.r;
             for (int a = 0; a < 3; ++a) {
               for (int b = 0; b < 3; ++b) ete[3 * a + b] += jp[a] * jp[b] + jp[3 + a] * jp[3 + b];
               ge[a] += jp[a] * rr[0] + jp[3 + a] * rr[1];
             }
             RowBlocks rb;
-            row_blocks(i, rb);
+            row_blocks(i, w, rb);
             for (int bb = 0; bb < rb.nblk; ++bb)
               for (int c = 0; c < rb.width[bb]; ++c) {
                 const int col = rb.off[bb] + c;
@@ -729,13 +940,13 @@ struct SchurSolver {
           for (int a = 0; a < 3; ++a) ig[a] = inv[3 * a] * ge[0] + inv[3 * a + 1] * ge[1] + inv[3 * a + 2] * ge[2];
           for (int64_t e = b0; e < b1; ++e) {
             const int64_t i = g.pt_obs[e];
-            const double* jp = &ev.Jp[(size_t)i * 6];
+            const Evaluator::Rows w = ev.rows(e, &chunk);
+            const double* jp = w.jp;
             double sj[2];
             for (int row = 0; row < 2; ++row)
-              sj[row] = ev.r[(size_t)2 * i + row] -
-                        (jp[3 * row] * ig[0] + jp[3 * row + 1] * ig[1] + jp[3 * row + 2] * ig[2]);
+              sj[row] = w.r[row] - (jp[3 * row] * ig[0] + jp[3 * row + 1] * ig[1] + jp[3 * row + 2] * ig[2]);
             RowBlocks rb;
-            row_blocks(i, rb);
+            row_blocks(i, w, rb);
             for (int bb = 0; bb < rb.nblk; ++bb)
               for (int c = 0; c < rb.width[bb]; ++c)
                 Rl[rb.off[bb] + c] += jval(rb, bb, 0, c) * sj[0] + jval(rb, bb, 1, c) * sj[1];
@@ -766,12 +977,13 @@ struct SchurSolver {
       for (int i = 0; i < n; ++i)
         for (int j = 0; j <= i; ++j) S[(size_t)i * n + j] += s[(size_t)i * n + j];
       for (int i = 0; i < n; ++i) rhs[i] += Rth[t][i];
+      std::vector<double>().swap(Sth[t]);  // release early: n^2 doubles per thread
     }
     // constraint rows (no e-block): F = [coupled point1 | coupled point2]
     for (int k = 0; k < g.K; ++k) {
       const int o[2] = {g.red_point(g.coupled_slot[g.c1[k]]), g.red_point(g.coupled_slot[g.c2[k]])};
       const double* jk = &ev.Jk[(size_t)6 * k];
-      const double rk = ev.r[(size_t)2 * g.N + k];
+      const double rk = ev.rk(k);
       for (int a = 0; a < 2; ++a)
         for (int ca = 0; ca < 3; ++ca) {
           rhs[o[a] + ca] += jk[3 * a + ca] * rk;
@@ -799,30 +1011,75 @@ struct SchurSolver {
       const int ot = g.off_point(g.point_slot[g.coupled_points[c]]);
       for (int j = 0; j < 3; ++j) y[(size_t)ot + j] = rhs[g.red_point((int)c) + j];
     }
+    double mcc_acc = 0.0;  // streaming: sum over rows of m.(r + m/2) with m = J (-y)
     if (g.has_points) {
-#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads)
-      for (int s = 0; s < ne; ++s) {
-        const int p = g.active_points[s];
-        if (g.coupled[p]) continue;
-        double acc[3] = {0, 0, 0};
-        for (int64_t e = g.pt_begin[p]; e < g.pt_begin[p + 1]; ++e) {
-          const int64_t i = g.pt_obs[e];
-          RowBlocks rb;
-          row_blocks(i, rb);
-          double sj[2] = {ev.r[(size_t)2 * i], ev.r[(size_t)2 * i + 1]};
-          for (int bb = 0; bb < rb.nblk; ++bb)
-            for (int c = 0; c < rb.width[bb]; ++c) {
-              const double yy = rhs[rb.off[bb] + c];
-              sj[0] -= jval(rb, bb, 0, c) * yy;
-              sj[1] -= jval(rb, bb, 1, c) * yy;
+#pragma omp parallel num_threads(nthreads) reduction(+ : mcc_acc)
+      {
+        Evaluator::Chunk chunk;
+#pragma omp for schedule(dynamic, 64)
+        for (int s = 0; s < ne; ++s) {
+          const int p = g.active_points[s];
+          if (g.coupled[p] && !ev.streaming) continue;
+          const int64_t b0 = g.pt_begin[p], b1 = g.pt_begin[p + 1];
+          if (ev.streaming) ev.fill_chunk(p, true, chunk);
+          const int op = g.off_point(s);
+          if (!g.coupled[p]) {
+            double acc[3] = {0, 0, 0};
+            for (int64_t e = b0; e < b1; ++e) {
+              const int64_t i = g.pt_obs[e];
+              const Evaluator::Rows w = ev.rows(e, &chunk);
+              RowBlocks rb;
+              row_blocks(i, w, rb);
+              double sj[2] = {w.r[0], w.r[1]};
+              for (int bb = 0; bb < rb.nblk; ++bb)
+                for (int c = 0; c < rb.width[bb]; ++c) {
+                  const double yy = rhs[rb.off[bb] + c];
+                  sj[0] -= jval(rb, bb, 0, c) * yy;
+                  sj[1] -= jval(rb, bb, 1, c) * yy;
+                }
+              const double* jp = w.jp;
+              for (int a = 0; a < 3; ++a) acc[a] += jp[a] * sj[0] + jp[3 + a] * sj[1];
             }
-          const double* jp = &ev.Jp[(size_t)i * 6];
-          for (int a = 0; a < 3; ++a) acc[a] += jp[a] * sj[0] + jp[3 + a] * sj[1];
+            const double* inv = &inv_ete[(size_t)9 * s];
+            for (int a = 0; a < 3; ++a)
+              y[(size_t)op + a] = inv[3 * a] * acc[0] + inv[3 * a + 1] * acc[1] + inv[3 * a + 2] * acc[2];
+          }
+          if (ev.streaming) {  // model cost change rows of this point (trust_region_minimizer.cc: model_residuals = J step)
+            for (int64_t e = b0; e < b1; ++e) {
+              const int64_t i = g.pt_obs[e];
+              const Evaluator::Rows w = ev.rows(e, &chunk);
+              double m[2] = {0, 0};
+              for (int j = 0; j < g.n_cam_t; ++j) {
+                const int c = g.cam_cols[j];
+                m[0] -= w.jc[c] * y[j];
+                m[1] -= w.jc[17 + c] * y[j];
+              }
+              if (g.has_views) {
+                const int o = g.off_view(g.view_slot[g.fidx[i]]);
+                for (int j = 0; j < 6; ++j) {
+                  m[0] -= w.jv[j] * y[(size_t)o + j];
+                  m[1] -= w.jv[6 + j] * y[(size_t)o + j];
+                }
+              }
+              for (int j = 0; j < 3; ++j) {
+                m[0] -= w.jp[j] * y[(size_t)op + j];
+                m[1] -= w.jp[3 + j] * y[(size_t)op + j];
+              }
+              mcc_acc += m[0] * (w.r[0] + m[0] / 2.0) + m[1] * (w.r[1] + m[1] / 2.0);
+            }
+          }
         }
-        const double* inv = &inv_ete[(size_t)9 * s];
-        const int op = g.off_point(s);
-        for (int a = 0; a < 3; ++a) y[(size_t)op + a] = inv[3 * a] * acc[0] + inv[3 * a + 1] * acc[1] + inv[3 * a + 2] * acc[2];
       }
+    }
+    if (ev.streaming) {
+      for (int k = 0; k < g.K; ++k) {
+        const int o1 = g.off_point(g.point_slot[g.c1[k]]), o2 = g.off_point(g.point_slot[g.c2[k]]);
+        double m = 0;
+        for (int j = 0; j < 3; ++j)
+          m -= ev.Jk[(size_t)6 * k + j] * y[(size_t)o1 + j] + ev.Jk[(size_t)6 * k + 3 + j] * y[(size_t)o2 + j];
+        mcc_acc += m * (ev.rk(k) + m / 2.0);
+      }
+      model_cost_change = -mcc_acc;
     }
     for (double v : y)
       if (!std::isfinite(v)) return false;
@@ -1051,14 +1308,15 @@ extern "C" int oracle_time_eval(const lfba_problem* pb, const double* camera, co
   return LFBA_OK;
 }
 
-extern "C" int oracle_solve(const lfba_problem* pb, const lfba_options* opt, double* camera17, double* views6F,
-                            double* points3P, lfba_summary* sum, int num_threads, double max_seconds,
-                            oracle_block_fn fn) {
+static int oracle_solve_impl(const lfba_problem* pb, const lfba_options* opt, double* camera17, double* views6F,
+                             double* points3P, lfba_summary* sum, int num_threads, double max_seconds,
+                             oracle_block_fn fn, bool streaming) {
   const double t_start = now_s();
   Program g;
   if (!build_program(pb, camera17, g)) return LFBA_INVALID_ARGUMENT;
   const int nt = num_threads > 0 ? num_threads : omp_get_max_threads();
   Evaluator ev(g, opt->loss_scale, nt, fn);
+  ev.streaming = streaming;
   ev.alloc_jacobian();
   SchurSolver schur(g, ev, nt);
 
@@ -1178,7 +1436,7 @@ extern "C" int oracle_solve(const lfba_problem* pb, const lfba_options* opt, dou
     it.step_is_valid = 0;
     if (solved) {
       for (double& v : step) v = -v;
-      model_cost_change = ev.model_cost_change(step);
+      model_cost_change = ev.streaming ? schur.model_cost_change : ev.model_cost_change(step);
       it.step_is_valid = model_cost_change > 0.0;
     }
     if (!it.step_is_valid) {
@@ -1223,6 +1481,7 @@ extern "C" int oracle_solve(const lfba_problem* pb, const lfba_options* opt, dou
         // CUBIC interpolation => Ceres evaluates value AND gradient at every trial point.  The Jacobian
         // scratch is shared with the LM state in this restatement, so evaluate into a private evaluator.
         Evaluator le(g, opt->loss_scale, nt, fn);
+        le.streaming = ev.streaming;
         le.alloc_jacobian();
         std::vector<double> gr;
         s.x = a;
@@ -1324,7 +1583,7 @@ extern "C" int oracle_solve(const lfba_problem* pb, const lfba_options* opt, dou
     sum->num_jacobian_evals = ev.num_jac_evals;
     sum->num_observations = g.N;
     sum->num_tracks = 0;
-    sum->num_lenses = 0;
+    sum->num_lenses = ev.num_block_recomputes;  // streaming mode: passes over all blocks (0 in stored mode); oracle-only use of this slot
     sum->gpu_launches = 0;
     sum->setup_time_s = 0;
     sum->solve_time_s = now_s() - t_start;
@@ -1333,4 +1592,19 @@ extern "C" int oracle_solve(const lfba_problem* pb, const lfba_options* opt, dou
       for (int i = 0; i < std::min((int)log.size(), sum->iterations_capacity); ++i) sum->iterations[i] = log[i];
   }
   return status;
+}
+
+extern "C" int oracle_solve(const lfba_problem* pb, const lfba_options* opt, double* camera17, double* views6F,
+                            double* points3P, lfba_summary* sum, int num_threads, double max_seconds,
+                            oracle_block_fn fn) {
+  return oracle_solve_impl(pb, opt, camera17, views6F, points3P, sum, num_threads, max_seconds, fn, false);
+}
+
+// Same solve without the O(N) Jacobian storage (block-recompute): for scenes whose Jacobian in Ceres' layout would not
+// fit the host (416 B per observation). Same algorithm and per-block arithmetic; sums over blocks are taken in point
+// order, so results agree with oracle_solve to rounding (tests/test_oracle_solver.py).
+extern "C" int oracle_solve_streaming(const lfba_problem* pb, const lfba_options* opt, double* camera17,
+                                      double* views6F, double* points3P, lfba_summary* sum, int num_threads,
+                                      double max_seconds, oracle_block_fn fn) {
+  return oracle_solve_impl(pb, opt, camera17, views6F, points3P, sum, num_threads, max_seconds, fn, true);
 }

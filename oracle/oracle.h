@@ -48,6 +48,15 @@ int oracle_solve(const lfba_problem* problem, const lfba_options* options, doubl
                  double* points3P, lfba_summary* summary, int num_threads, double max_seconds,
                  oracle_block_fn block_fn);
 
+/* The same solve without the O(N) Jacobian storage ("streaming", block-recompute mode): the block rows of one point's
+ * observations are re-derived by autodiff wherever Ceres would read its stored Jacobian (evaluation, Schur
+ * elimination, back-substitution), so the 1M-point x 1000-frame scene (41.6 GB of Jacobian in Ceres' layout) runs in
+ * a few GB. Results equal oracle_solve to rounding (sums are taken in point order). On return
+ * summary->num_lenses holds the number of passes over all blocks (3 per LM iteration instead of 1). */
+int oracle_solve_streaming(const lfba_problem* problem, const lfba_options* options, double* camera17,
+                           double* views6F, double* points3P, lfba_summary* summary, int num_threads,
+                           double max_seconds, oracle_block_fn block_fn);
+
 /* Wall-clock seconds of `reps` full residual+Jacobian evaluations (Jet<26> autodiff, Jacobian
  * materialised in Ceres' block layout, gradient formed) — the "M evals/s" CPU baseline. */
 int oracle_time_eval(const lfba_problem* problem, const double* camera17, const double* views6F,

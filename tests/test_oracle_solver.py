@@ -143,3 +143,27 @@ def test_oracle_minimum_agrees_with_an_independent_solver(built):
     # with the reference's own tolerances (ftol 1e-6) the oracle stops slightly above that minimum, never below it
     _, _, _, s2 = ob.solve(pa, sc.camera_init, sc.views_init, sc.points_init, threads=2)
     assert ref.cost * (1 - 1e-9) <= s2["final_cost"] <= ref.cost * (1 + 1e-3)
+
+
+@pytest.mark.parametrize("scene", [
+    dict(n_points=200, n_frames=6, n_constraints=2, seed=7),                       # constraints + coupled points
+    dict(n_points=300, n_frames=24, window=4, seed=5, order=1),                    # windowed (cfg4 family)
+    dict(n_points=120, n_frames=5, seed=13, calib_type=capi.RECALIBRATION),        # manifold + bounds + line search
+])
+def test_streaming_mode_equals_stored_mode(built, scene):
+    """The Jacobian-free (block-recompute) mode that makes the 1M x 1000 scene fit the host follows the same
+    algorithm as the stored-Jacobian mode: same rows, same decisions, costs equal to rounding."""
+    sc = capi.make_scene(None, **scene)
+    init = (sc.camera_init, sc.views_init, sc.points_init)
+    a = ob.solve(sc.problem, *init, threads=2)
+    b = ob.solve(sc.problem, *init, threads=2, streaming=True)
+    sa, sb = a[3], b[3]
+    assert sa["num_iterations"] == sb["num_iterations"] and sa["stop_reason"] == sb["stop_reason"]
+    assert sb["block_passes"] >= 3 * (sb["num_iterations"] - 1) + 1  # evaluate + eliminate + back-substitute
+    for ra, rb in zip(sa["iterations"], sb["iterations"]):
+        assert ra["step_is_successful"] == rb["step_is_successful"]
+        assert abs(ra["cost"] - rb["cost"]) <= 1e-12 * abs(ra["cost"])
+        assert abs(ra["trust_region_radius"] - rb["trust_region_radius"]) <= 1e-6 * ra["trust_region_radius"]
+        assert abs(ra["relative_decrease"] - rb["relative_decrease"]) <= 1e-6
+    assert abs(sa["final_cost"] - sb["final_cost"]) <= 1e-12 * sa["final_cost"]
+    assert np.allclose(a[0], b[0], rtol=1e-7, atol=1e-12)
