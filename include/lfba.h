@@ -121,7 +121,11 @@ typedef struct lfba_options {
   int32_t device;                     /* CUDA device ordinal for a single-GPU solve; -1 = current */
   int32_t num_gpus;                   /* lfba_solve only: shard over this many visible GPUs (single process) */
   int32_t profile;                    /* 1: record per-kernel CUDA-event times into the summary */
-  int32_t reserved[8];
+  int32_t emulate_shards;             /* > 1: run the multi-GPU code path on ONE device — the problem is sharded this many
+                                         ways exactly like num_gpus would, the shards run in lock-step on one stream and a
+                                         device kernel sums their partial systems where the NCCL all-reduce would be
+                                         (SURVEY.md section 4, item 4). lfba_solve and lfba_solver_create honour it. */
+  int32_t reserved[7];
 } lfba_options;
 
 /* One row of the Ceres progress table = the per-iteration parity record. */
@@ -245,6 +249,15 @@ int lfba_solver_run(lfba_solver* s, lfba_summary* summary);
 /* Times `reps` launches of the fused evaluation pass (and, if materialize != 0, of the eval-only kernel
  * that writes residuals + Jacobians to HBM) at the current parameters; returns mean ms per launch. */
 int lfba_solver_time_eval(lfba_solver* s, int reps, int materialize, double* mean_ms);
+/* Diagnostics for parity tests: one fused evaluation pass (the LM loop's own kernel) at the parameters last given by
+ * lfba_solver_set_parameters, and its raw outputs — per (point, frame) track the normal-equation blocks in the CAMERA
+ * frame, rec = [A (6: upper triangle of sum w G^T G, row-major) | b (3: sum w G^T r) | C (3 x NC row-major: sum w G^T Jc)],
+ * G = d r / d P_c (2x3), w = rho' of CauchyLoss (1 without the robust flag); and camsum = [Hcc (lower triangle, row-major,
+ * NC (NC+1)/2) | gc (NC) | cost]. Arrays may be NULL. *n_tracks and *rec_stride are outputs; rec needs
+ * n_tracks * rec_stride doubles (query with rec == NULL first), trk_point / trk_frame n_tracks ints, camsum 64 doubles.
+ * Single-shard sessions only. */
+int lfba_solver_track_blocks(lfba_solver* s, int64_t* n_tracks, int32_t* rec_stride, double* rec, double* camsum64,
+                             int32_t* trk_point, int32_t* trk_frame);
 /* Measures the device's FP64 FMA throughput (TFLOP/s) with a dependent-chain-free DFMA kernel. */
 int lfba_measure_fp64_peak(int device, double* tflops);
 void lfba_solver_destroy(lfba_solver* s);

@@ -21,8 +21,8 @@ _lib = None
 
 _EXPORTS = ["lfba_version", "lfba_last_error", "lfba_status_string", "lfba_options_init", "lfba_device_count",
             "lfba_solve", "lfba_eval", "lfba_comm_unique_id", "lfba_comm_create", "lfba_comm_destroy", "lfba_solver_create", "lfba_solver_set_parameters",
-            "lfba_solver_get_parameters", "lfba_solver_run", "lfba_solver_time_eval", "lfba_measure_fp64_peak",
-            "lfba_solver_destroy"]
+            "lfba_solver_get_parameters", "lfba_solver_run", "lfba_solver_time_eval", "lfba_solver_track_blocks",
+            "lfba_measure_fp64_peak", "lfba_solver_destroy"]
 
 
 def load():
@@ -57,6 +57,7 @@ def load():
     L.lfba_solver_get_parameters.argtypes = [C.c_void_p, dp, dp, dp]
     L.lfba_solver_run.argtypes = [C.c_void_p, C.POINTER(capi.Summary)]
     L.lfba_solver_time_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+    L.lfba_solver_track_blocks.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), dp, dp, ip, ip]
     L.lfba_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.lfba_solver_destroy.argtypes = [C.c_void_p]
     _lib = L
@@ -211,6 +212,21 @@ class DeviceSolver:
         _check(self._L.lfba_solver_time_eval(self._h, reps, 1 if materialize else 0, C.byref(ms)),
                "lfba_solver_time_eval")
         return ms.value
+
+    def track_blocks(self):
+        """lfba_solver_track_blocks: raw outputs of ONE fused evaluation pass at the parameters last set — per-track
+        normal-equation blocks (camera frame) and the camera block; for parity tests of the LM loop's own kernel."""
+        n, rs = C.c_int64(0), C.c_int32(0)
+        _check(self._L.lfba_solver_track_blocks(self._h, C.byref(n), C.byref(rs), None, None, None, None),
+               "lfba_solver_track_blocks")
+        T, RS = n.value, rs.value
+        rec = np.zeros((T, RS))
+        camsum = np.zeros(64)
+        tp = np.zeros(T, np.int32)
+        tf = np.zeros(T, np.int32)
+        _check(self._L.lfba_solver_track_blocks(self._h, C.byref(n), C.byref(rs), capi._dp(rec), capi._dp(camsum),
+                                                capi._ip(tp), capi._ip(tf)), "lfba_solver_track_blocks")
+        return {"rec": rec, "camsum": camsum, "trk_point": tp, "trk_frame": tf, "rec_stride": RS}
 
     def close(self):
         if self._h:

@@ -63,7 +63,7 @@ class Options(C.Structure):
         ("loss_scale", C.c_double),
         ("minimizer_progress_to_stdout", C.c_int32),
         ("device", C.c_int32), ("num_gpus", C.c_int32), ("profile", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("emulate_shards", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 

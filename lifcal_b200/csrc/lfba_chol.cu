@@ -48,7 +48,7 @@ __device__ __forceinline__ void load_tile(const Dev& d, int ti, int tj, int n_au
 // One tile column k. grid.x = number of tile rows i >= k; blockIdx.x = i - k.
 __global__ void __launch_bounds__(256) k_chol_column(Dev d, int k, const int* __restrict__ tile_first) {
   LmState* st = d.st;
-  if (st->done || !st->solve_ok) return;
+  if (linear_phase_idle(st) || !st->solve_ok) return;
   const int i = k + blockIdx.x;
   const int n_aug = d.n + 1;
   if (tile_first[i] > k) return;  // structurally zero tile
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) k_chol_column(Dev d, int k, const int* __
 // so that every access is a contiguous skyline row.
 __global__ void __launch_bounds__(256) k_backsolve(Dev d) {
   LmState* st = d.st;
-  if (st->done || !st->solve_ok) return;
+  if (linear_phase_idle(st) || !st->solve_ok) return;
   const int n = d.n;
   double* y = d.y;
   const double* zrow = d.S + d.row_off[n];
@@ -215,7 +215,7 @@ constexpr int kPrefMax = 6;  // prefetch registers per thread (band) — (6*NBAN
 
 __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
   LmState* st = d.st;
-  if (st->done || !st->solve_ok) return;
+  if (linear_phase_idle(st) || !st->solve_ok) return;
   extern __shared__ double sm[];
   const int F = d.np6 / 6;
   const int bw1 = bw + 1;

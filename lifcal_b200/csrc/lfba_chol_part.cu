@@ -55,7 +55,7 @@ constexpr int kPref = 6;  // prefetch registers per thread for the entering fram
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_part_forward(Dev d, PartDev pd) {
   LmState* st = d.st;
-  if (st->done || !st->solve_ok) return;
+  if (linear_phase_idle(st) || !st->solve_ok) return;
   extern __shared__ double sm[];
   const int j = blockIdx.x, P = pd.P, bw = pd.bw, bw1 = bw + 1, F = pd.F;
   const int fa = pd.bounds[j];
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) k_part_forward(Dev d, PartDev pd) {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_part_assemble(Dev d, PartDev pd, Dev d2, long long s2_len) {
   LmState* st = d.st;
-  if (st->done || !st->solve_ok) return;
+  if (linear_phase_idle(st) || !st->solve_ok) return;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = pd.P, bw = pd.bw, npiv = pd.npiv, nb = npiv + 1;
   const int nsf = 6 * bw * (P - 1);  // separator unknowns
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_part_assemble(Dev d, PartDev pd, Dev d2
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_part_backward(Dev d, PartDev pd, const double* __restrict__ y2) {
   LmState* st = d.st;
-  if (st->done || !st->solve_ok) return;
+  if (linear_phase_idle(st) || !st->solve_ok) return;
   extern __shared__ double sm[];
   const int j = blockIdx.x, P = pd.P, bw = pd.bw, F = pd.F, npiv = pd.npiv;
   const int fa = pd.bounds[j];

@@ -68,7 +68,8 @@ enum EvalScalar {  // tiny buffer reduced (sum) across ranks after the candidate
   ES_NORM2,        // |x+|^2 partial
   ES_GDELTA,       // gradient . delta partial
   ES_BAD,          // non-finite step flag (count)
-  ES_COUNT = 8
+  ES_LSGD,         // recalib: gradient(candidate) . delta partial = phi'(alpha) of the projected line search
+  ES_COUNT = 8     // followed by nranks slots: max |delta| over the parameters of each rank (line-search step-size floor)
 };
 enum SysScalar {   // trailer of the big buffer reduced (sum) across ranks with S and g
   SS_GNORM2 = 0,   // sum of squared gradient over the points of this rank
@@ -88,7 +89,15 @@ struct LmState {
   int first;        // Jacobi scaling still to be computed (iteration 0)
   int pending_row;  // a row is waiting for its gradient norms (k_finalize)
   int n_jac_evals;
-  int ls_needed;    // projected line search would have to contract the step (recalib only)
+  // projected Armijo line search of bounds-constrained problems (recalib; Ceres TrustRegionMinimizer::DoLineSearch)
+  int ls_active;    // a search is in progress: the candidate just evaluated was the trial at step size ls_alpha
+  int ls_trial;     // a contraction trial is pending: this round skips assembly / solve / step, k_ls_apply moves the candidate
+  int ls_iters;     // contractions so far (the row's line_search_iterations)
+  int ls_failed;    // the search gave up: the full step is re-evaluated and taken without the Armijo test
+  int ls_prev_valid, ls_prev_gvalid;
+  double ls_alpha, ls_phi0, ls_dphi0;
+  double ls_prev_x, ls_prev_v, ls_prev_g;
+  double dmax_red;  // max |delta| over the reduced parameters (camera, poses, coupled points)
   double radius, decrease_factor;
   double x_cost, x_norm2, min_cost;
   double gmax, gnorm;
@@ -96,6 +105,9 @@ struct LmState {
   lfba_iteration row;
   unsigned long long t_start, t_iter;
 };
+
+// post-control kernels (assembly, reduced solve, step) do nothing in a round whose only job is a line-search trial
+__host__ __device__ inline bool linear_phase_idle(const LmState* st) { return st->done || st->ls_trial; }
 
 struct Options {
   int max_iter;
@@ -183,6 +195,8 @@ struct Dev {
   double* part_eval;   // [grid_eval * 64]
   double* part_pts;    // [grid_pts * 64]
   double* part_step;   // [grid_pts * 8]
+  double* pstep;       // [3P] recalib: delta of the eliminated points (the line search re-applies it at step size alpha)
+  double* part_ls;     // [grid_pts] recalib: per-CTA partial sums of gradient(candidate) . delta
   int grid_eval, grid_pts;
   LmState* st;
   lfba_iteration* log;

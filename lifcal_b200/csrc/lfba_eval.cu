@@ -194,6 +194,16 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
   }
 }
 
+// per-device opt-in to > 48 KB of dynamic shared memory: call with that device current (Solver::create does)
+void prepare_eval_only_kernels() {
+  cudaFuncSetAttribute(k_eval_only<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<5>() * (int)sizeof(double));
+  cudaFuncSetAttribute(k_eval_only<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
+  cudaFuncSetAttribute(k_eval_only<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<6>() * (int)sizeof(double));
+  cudaFuncSetAttribute(k_eval_only<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<8>() * (int)sizeof(double));
+  cudaFuncSetAttribute(k_eval_only<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
+  cudaFuncSetAttribute(k_eval_only<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<9>() * (int)sizeof(double));
+}
+
 void launch_tables_for(const Dev& d, int which, cudaStream_t s) {
   const int n = d.NL > d.F ? d.NL : d.F;
   if (n > 0) k_tables_for<<<(n + 127) / 128, 128, 0, s>>>(d, which);
@@ -202,16 +212,6 @@ void launch_tables_for(const Dev& d, int which, cudaStream_t s) {
 void launch_eval_only(const Dev& d, const EvalIn& in, const EvalOut& out, int which, cudaStream_t s) {
   if (d.N == 0) return;
   const unsigned grid = (unsigned)((d.N + kEvalBlock - 1) / kEvalBlock);
-  static const bool prepared = [] {
-    cudaFuncSetAttribute(k_eval_only<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<5>() * (int)sizeof(double));
-    cudaFuncSetAttribute(k_eval_only<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
-    cudaFuncSetAttribute(k_eval_only<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<6>() * (int)sizeof(double));
-    cudaFuncSetAttribute(k_eval_only<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<8>() * (int)sizeof(double));
-    cudaFuncSetAttribute(k_eval_only<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
-    cudaFuncSetAttribute(k_eval_only<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<9>() * (int)sizeof(double));
-    return true;
-  }();
-  (void)prepared;
   const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
   switch (nrad * 2 + tang) {
     case 0: k_eval_only<5, 0><<<grid, kEvalBlock, eval_smem_doubles<5>() * sizeof(double), s>>>(d, in, out, which); break;

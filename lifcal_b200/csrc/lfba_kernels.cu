@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(1024) k_reduce_eval(Dev d) {
   const int NH = d.NC * (d.NC + 1) / 2, NV = NH + d.NC + 1;
   __shared__ double sh[64];
   __shared__ double shs[8];
+  __shared__ double sls[2];
   const int v = threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 32 warps; a warp sums one value over the CTAs
   for (int q = warp; q < 64; q += 32) {                        // (lanes stride over the CTAs, then a butterfly: fixed order)
@@ -125,10 +126,21 @@ __global__ void __launch_bounds__(1024) k_reduce_eval(Dev d) {
   if (warp < 8) {
     const int k = warp;
     double s_ = 0.0;
-    if (d.refine_points && (st->iter == 0 || st->solve_ok))
-      for (int b = lane; b < d.grid_pts; b += 32) s_ += d.part_step[(size_t)b * 8 + k];
-    s_ = warp_sum(s_);
+    if (d.refine_points && (st->iter == 0 || st->solve_ok)) {
+      if (k == 5) {  // slot 5 is a maximum: max |delta| over this rank's eliminated points
+        for (int b = lane; b < d.grid_pts; b += 32) s_ = fmax(s_, d.part_step[(size_t)b * 8 + k]);
+      } else {
+        for (int b = lane; b < d.grid_pts; b += 32) s_ += d.part_step[(size_t)b * 8 + k];
+      }
+    }
+    s_ = k == 5 ? warp_max(s_) : warp_sum(s_);
     if (lane == 0) shs[k] = s_;
+  } else if (warp == 8) {  // recalib: gradient(candidate) . delta over this rank's tracks (k_ls_gdot)
+    double s_ = 0.0;
+    if (d.recalib && !st->eval_skip && st->iter > 0)
+      for (int b = lane; b < d.grid_pts; b += 32) s_ += d.part_ls[b];
+    s_ = warp_sum(s_);
+    if (lane == 0) sls[0] = s_;
   }
   __syncthreads();
   if (v == 0) {
@@ -149,14 +161,122 @@ __global__ void __launch_bounds__(1024) k_reduce_eval(Dev d) {
     es[ES_NORM2] = shs[2] + own * st->norm2_red;
     es[ES_GDELTA] = shs[3] + own * st->gdelta_red;
     es[ES_BAD] = shs[4];
-    es[5] = es[6] = es[7] = 0.0;
+    double lsgd = 0.0;
+    if (d.recalib && !st->eval_skip && st->iter > 0) {
+      // camera part of gradient(candidate) . delta: this rank's share of g_c (camsum) times delta_c = -y_c
+      lsgd = sls[0];
+      for (int c = 0; c < d.NC; ++c) {
+        const int r = d.cam_red[c];
+        if (r >= 0) lsgd += sh[NH + c] * (-d.y[r]);
+      }
+    }
+    es[ES_LSGD] = lsgd;
+    es[6] = es[7] = 0.0;
+    for (int r = 0; r < d.nranks; ++r) es[ES_COUNT + r] = r == d.rank ? fmax(shs[5], own * st->dmax_red) : 0.0;
   }
+}
+
+// ---- projected Armijo line search (Ceres ArmijoLineSearch with CUBIC interpolation; line_search.cc, polynomial.cc) ----
+struct LsSample {
+  double x, value, gradient;
+  int value_valid, gradient_valid;
+};
+__device__ double ls_ipow(double x, int e) {
+  double r = 1.0;
+  for (int i = 0; i < e; ++i) r *= x;
+  return r;
+}
+// Polynomial through the samples' values and (where valid) gradients, minimised on [lo, hi]: end points and the
+// stationary points inside (sign changes of p' on a 4096-point grid, bisected).
+__device__ double ls_minimize_interpolant(const LsSample* smp, int ns, double lo, double hi) {
+  int ncon = 0;
+  for (int i = 0; i < ns; ++i) ncon += (smp[i].value_valid ? 1 : 0) + (smp[i].gradient_valid ? 1 : 0);
+  const int deg = ncon - 1;
+  double A[36], b[6], coef[6];
+  for (int i = 0; i < 36; ++i) A[i] = 0.0;
+  int row = 0;
+  for (int i = 0; i < ns; ++i) {
+    if (smp[i].value_valid) {
+      for (int j = 0; j <= deg; ++j) A[row * ncon + j] = ls_ipow(smp[i].x, deg - j);
+      b[row++] = smp[i].value;
+    }
+    if (smp[i].gradient_valid) {
+      for (int j = 0; j < deg; ++j) A[row * ncon + j] = (deg - j) * ls_ipow(smp[i].x, deg - j - 1);
+      b[row++] = smp[i].gradient;
+    }
+  }
+  for (int c = 0; c < ncon; ++c) {  // Gaussian elimination, partial pivoting
+    int piv = c;
+    for (int i = c + 1; i < ncon; ++i)
+      if (fabs(A[i * ncon + c]) > fabs(A[piv * ncon + c])) piv = i;
+    for (int j = 0; j < ncon; ++j) {
+      const double t = A[c * ncon + j];
+      A[c * ncon + j] = A[piv * ncon + j];
+      A[piv * ncon + j] = t;
+    }
+    const double tb = b[c];
+    b[c] = b[piv];
+    b[piv] = tb;
+    const double dd = A[c * ncon + c];
+    if (dd == 0.0) continue;
+    for (int i = c + 1; i < ncon; ++i) {
+      const double f = A[i * ncon + c] / dd;
+      for (int j = c; j < ncon; ++j) A[i * ncon + j] -= f * A[c * ncon + j];
+      b[i] -= f * b[c];
+    }
+  }
+  for (int i = ncon - 1; i >= 0; --i) {  // coefficients, highest degree first
+    double s_ = b[i];
+    for (int j = i + 1; j < ncon; ++j) s_ -= A[i * ncon + j] * coef[j];
+    coef[i] = A[i * ncon + i] != 0.0 ? s_ / A[i * ncon + i] : 0.0;
+  }
+  auto poly = [&](double x) {
+    double v = 0.0;
+    for (int j = 0; j <= deg; ++j) v = v * x + coef[j];
+    return v;
+  };
+  auto dpoly = [&](double x) {
+    double v = 0.0;
+    for (int j = 0; j < deg; ++j) v = v * x + (deg - j) * coef[j];
+    return v;
+  };
+  double best_x = lo, best_v = poly(lo);
+  if (poly(hi) < best_v) {
+    best_v = poly(hi);
+    best_x = hi;
+  }
+  const int G = 4096;
+  double xa = lo, da = dpoly(lo);
+  for (int i = 1; i <= G; ++i) {
+    const double xb = lo + (hi - lo) * i / G, db = dpoly(xb);
+    if ((da <= 0 && db >= 0) || (da >= 0 && db <= 0)) {
+      double l = xa, h = xb, dl = da;
+      for (int it = 0; it < 100; ++it) {
+        const double m = 0.5 * (l + h), dm = dpoly(m);
+        if ((dl <= 0 && dm <= 0) || (dl >= 0 && dm >= 0)) {
+          l = m;
+          dl = dm;
+        } else {
+          h = m;
+        }
+      }
+      const double xm = 0.5 * (l + h), vm = poly(xm);
+      if (vm < best_v) {
+        best_v = vm;
+        best_x = xm;
+      }
+    }
+    xa = xb;
+    da = db;
+  }
+  return best_x;
 }
 
 // ================================================================================================
 // C1. accept / reject — ceres::internal::TrustRegionMinimizer::Minimize loop body after the candidate
-// evaluation (ParameterToleranceReached, FunctionToleranceReached, IsStepSuccessful, HandleSuccessfulStep /
-// StepRejected / HandleInvalidStep) and LevenbergMarquardtStrategy::StepAccepted/StepRejected.
+// evaluation (DoLineSearch for bounds-constrained problems, ParameterToleranceReached, FunctionToleranceReached,
+// IsStepSuccessful, HandleSuccessfulStep / StepRejected / HandleInvalidStep) and
+// LevenbergMarquardtStrategy::StepAccepted/StepRejected.
 // ================================================================================================
 __global__ void k_control_accept(Dev d) {
   LmState* st = d.st;
@@ -188,6 +308,7 @@ __global__ void k_control_accept(Dev d) {
   const double mcc = es[ES_MCC];
   const bool valid = !st->eval_skip && st->solve_ok && es[ES_BAD] == 0.0 && mcc > 0.0;
   if (!valid) {  // HandleInvalidStep
+    st->ls_active = st->ls_failed = st->ls_iters = 0;
     if (++st->num_invalid >= o.max_invalid) {
       st->done = 1;
       st->termination = LFBA_TERM_FAILURE;
@@ -207,17 +328,89 @@ __global__ void k_control_accept(Dev d) {
     return;
   }
   st->num_invalid = 0;
-  if (!st->eval_skip) st->n_jac_evals += 1;
+  st->n_jac_evals += 1;
   double cand_cost = es[ES_COST];
-  if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
+  const bool cost_finite = isfinite(cand_cost);
+  if (!cost_finite) cand_cost = DBL_MAX;
   row.step_is_valid = 1;
   if (d.recalib) {
-    // Projected Armijo test at step size 1 (Ceres DoLineSearch for bounds-constrained problems): if it
-    // holds, the line search returns 1.0 and delta is unchanged. Otherwise the host contracts the step.
-    if (!(cand_cost <= st->x_cost + 1e-4 * es[ES_GDELTA])) {
-      st->ls_needed = 1;
-      st->done = 1;
-      return;
+    // Bounds make Ceres search along delta from step size 1 on phi(a) = cost(Plus(x, a delta)) (projected: Plus clamps
+    // to the box) until phi(a) <= phi(0) + 1e-4 a phi'(0); contraction by minimising the polynomial through phi(0),
+    // phi'(0) and value + gradient of the last two trials, inside [1e-3, 0.6] a; at most 20 trials, a |delta|_inf >= 1e-9.
+    // The candidate just evaluated IS the current trial (a = 1 for the first one): its cost and phi'(a) = g(x_a).delta
+    // came with the fused evaluation pass, no extra evaluation is needed when a = 1 is accepted.
+    if (st->ls_failed) {  // search gave up earlier: this is the full step again, taken as Ceres does (delta unchanged)
+      st->ls_failed = 0;
+      st->ls_active = 0;
+      row.line_search_iterations = st->ls_iters;
+    } else {
+      LsSample cur;
+      cur.x = st->ls_active ? st->ls_alpha : 1.0;
+      cur.value = cand_cost;
+      cur.value_valid = cost_finite ? 1 : 0;
+      cur.gradient = es[ES_LSGD];
+      cur.gradient_valid = (cost_finite && isfinite(cur.gradient)) ? 1 : 0;
+      if (!st->ls_active) {
+        st->ls_phi0 = st->x_cost;
+        st->ls_dphi0 = es[ES_GDELTA];
+        st->ls_iters = 0;
+        st->ls_prev_valid = st->ls_prev_gvalid = 0;
+      }
+      const bool armijo = cur.value_valid && cur.value <= st->ls_phi0 + 1e-4 * st->ls_dphi0 * cur.x;
+      if (!armijo) {
+        bool fail = ++st->ls_iters >= 20;
+        double a_new = 1.0;
+        if (!fail) {
+          const double lo = 1e-3 * cur.x, hi = 0.6 * cur.x;
+          if (!cur.value_valid) {
+            a_new = fmin(fmax(cur.x * 0.5, lo), hi);
+          } else {
+            LsSample smp[3];
+            int ns = 0;
+            smp[ns].x = 0.0;
+            smp[ns].value = st->ls_phi0;
+            smp[ns].gradient = st->ls_dphi0;
+            smp[ns].value_valid = smp[ns].gradient_valid = 1;
+            ++ns;
+            smp[ns++] = cur;
+            if (st->ls_prev_valid) {
+              smp[ns].x = st->ls_prev_x;
+              smp[ns].value = st->ls_prev_v;
+              smp[ns].gradient = st->ls_prev_g;
+              smp[ns].value_valid = 1;
+              smp[ns].gradient_valid = st->ls_prev_gvalid;
+              ++ns;
+            }
+            a_new = ls_minimize_interpolant(smp, ns, lo, hi);
+          }
+          double dmax = 0.0;
+          for (int r = 0; r < d.nranks; ++r) dmax = fmax(dmax, es[ES_COUNT + r]);
+          if (a_new * dmax < 1e-9) fail = true;
+        }
+        if (fail) {
+          if (st->ls_active) {  // back to the full step: one more evaluation at a = 1
+            st->ls_failed = 1;
+            st->ls_alpha = 1.0;
+            st->ls_trial = 1;
+            return;
+          }
+          // the failed trial was a = 1 itself: its evaluation is the candidate
+          row.line_search_iterations = st->ls_iters;
+        } else {
+          st->ls_prev_x = cur.x;
+          st->ls_prev_v = cur.value;
+          st->ls_prev_g = cur.gradient;
+          st->ls_prev_valid = cur.value_valid;
+          st->ls_prev_gvalid = cur.gradient_valid;
+          st->ls_active = 1;
+          st->ls_alpha = a_new;
+          st->ls_trial = 1;
+          return;
+        }
+      } else {
+        row.line_search_iterations = st->ls_iters;  // delta <- a delta: the candidate already is Plus(x, a delta)
+      }
+      st->ls_active = 0;
     }
   }
   row.step_norm = sqrt(es[ES_STEP2]);
@@ -254,6 +447,134 @@ __global__ void k_control_accept(Dev d) {
   st->pending_row = 1;
 }
 
+// ---- line-search support kernels (recalib only) ----
+// phi'(a) = gradient(x_a) . delta at the candidate x_a just evaluated: per track, b_t = G^T r (camera frame, from the
+// fused pass) against the motion of the camera-frame point along delta, R delta_p + M delta_f. Fixed-order partials.
+__global__ void __launch_bounds__(128) k_ls_gdot(Dev d) {
+  LmState* st = d.st;
+  if (st->done || st->eval_skip || st->iter == 0) return;
+  const int cand = 1 - st->cur;
+  const int RS = rec_stride(d.NC);
+  __shared__ double red[4];
+  double acc = 0.0;
+  const double* __restrict__ recs = d.rec[cand];
+  const double* __restrict__ frames = d.frames[cand];
+  const double* __restrict__ points = d.points[cand];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < d.T; t += gridDim.x * blockDim.x) {
+    const int p = d.trk_point[t], f = d.trk_frame[t];
+    const double* fe = frames + (size_t)f * kFrameStride;
+    const double* b = recs + (size_t)t * RS + 6;
+    double mv[3] = {0.0, 0.0, 0.0};
+    if (d.refine_points) {
+      const double* dp = d.pstep + 3 * (size_t)p;
+      mat3_vec(fe, dp, mv);
+    }
+    if (d.refine_poses) {
+      const double* X = points + 3 * (size_t)p;
+      const double* yf = d.y + 6 * f;
+      double m[9];
+      mat3_vec(fe + 9, X, m + 0);
+      mat3_vec(fe + 18, X, m + 3);
+      mat3_vec(fe + 27, X, m + 6);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) mv[i] += -(m[i] * yf[0] + m[3 + i] * yf[1] + m[6 + i] * yf[2]) - yf[3 + i];
+    }
+    acc += b[0] * mv[0] + b[1] * mv[1] + b[2] * mv[2];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) d.part_ls[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// A pending contraction trial: candidate := Plus(x, a delta) for the eliminated points, with their share of |x - x+|^2
+// and |x+|^2 (the slots of k_point_step's partials that depend on the candidate).
+__global__ void __launch_bounds__(128) k_ls_apply(Dev d) {
+  LmState* st = d.st;
+  if (st->done || !st->ls_trial || !d.refine_points) return;
+  const int cur = st->cur, cand = 1 - cur;
+  const double a = st->ls_alpha;
+  __shared__ double red[4 * 2];
+  double acc[2] = {0.0, 0.0};
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.P; p += gridDim.x * blockDim.x) {
+    if (!d.pt_active[p] || d.pt_coupled[p] >= 0) continue;
+    const double* X = d.points[cur] + 3 * (size_t)p;
+    double* Xc = d.points[cand] + 3 * (size_t)p;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double xn = X[j] + a * d.pstep[3 * (size_t)p + j];
+      Xc[j] = xn;
+      const double dl = xn - X[j];
+      acc[0] += dl * dl;
+      acc[1] += xn * xn;
+    }
+  }
+  double out[2];
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int v = 0; v < 2; ++v) {
+      const double s_ = warp_sum(acc[v]);
+      if (lane == 0) red[warp * 2 + v] = s_;
+    }
+    __syncthreads();
+    for (int v = 0; v < 2; ++v) out[v] = (red[v] + red[2 + v]) + (red[4 + v] + red[6 + v]);
+  }
+  if (threadIdx.x == 0) {
+    d.part_step[(size_t)blockIdx.x * 8 + 1] = out[0];
+    d.part_step[(size_t)blockIdx.x * 8 + 2] = out[1];
+  }
+}
+
+// ... and for the reduced parameters (camera with manifold + bounds, poses, coupled points). Last kernel of a trial
+// round: clears the flag.
+__global__ void __launch_bounds__(256) k_ls_apply_reduced(Dev d) {
+  LmState* st = d.st;
+  if (st->done || !st->ls_trial) return;
+  const int cur = st->cur, cand = 1 - cur;
+  const double a = st->ls_alpha;
+  __shared__ double red[8 * 8];
+  __shared__ double out[8];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const double* y = d.y;
+  for (int j = threadIdx.x; j < d.np6; j += blockDim.x) {
+    const double x = d.views[cur][j];
+    const double xn = x + a * (-y[j]);
+    d.views[cand][j] = xn;
+    if (d.frm_active[j / 6]) {
+      const double dl = xn - x;
+      acc[1] += dl * dl;
+      acc[2] += xn * xn;
+    }
+  }
+  for (int j = threadIdx.x; j < 3 * d.Pc; j += blockDim.x) {
+    const int r = d.np6 + j;
+    const int p = d.coupled_pts[j / 3];
+    const double x = d.points[cur][3 * (size_t)p + j % 3];
+    const double xn = x + a * (-y[r]);
+    d.points[cand][3 * (size_t)p + j % 3] = xn;
+    const double dl = xn - x;
+    acc[1] += dl * dl;
+    acc[2] += xn * xn;
+  }
+  for (int c = threadIdx.x; c < 17; c += blockDim.x) {
+    const double x = d.camera[cur][c];
+    double xn = x;
+    const int r = c < d.NC ? d.cam_red[c] : -1;
+    if (r >= 0) xn = x + a * (-y[r]);
+    xn = fmin(fmax(xn, d.cam_lo[c]), d.cam_hi[c]);
+    d.camera[cand][c] = xn;
+    const double dl = xn - x;
+    acc[1] += dl * dl;
+    acc[2] += xn * xn;
+  }
+  block_reduce_store<8>(acc, out, red);
+  if (threadIdx.x == 0) {
+    st->step2_red = out[1];
+    st->norm2_red = out[2];
+    st->ls_trial = 0;
+  }
+}
+
 // ================================================================================================
 // B. system assembly at the accepted state
 // ================================================================================================
@@ -262,7 +583,7 @@ __global__ void k_control_accept(Dev d) {
 template <int NC>
 __global__ void __launch_bounds__(128) k_points(Dev d) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   const int cur = st->cur;
   constexpr int NH = NC * (NC + 1) / 2;
   constexpr int NV = NH + NC + 3;  // Schur cam-cam (NH), Schur cam gradient (NC), |g|^2, fail count, (max separately)
@@ -401,7 +722,7 @@ __device__ __forceinline__ void frame_all_scatter(const Dev& d, int f, int v, do
 template <int NC>
 __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   const int cur = st->cur;
   const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
   constexpr int RS = 9 + 3 * NC;
@@ -558,7 +879,7 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
 template <int NC>
 __global__ void __launch_bounds__(128) k_frame_finish(Dev d, int nsplit) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   constexpr int NV = 21 + 6 + 6 + 6 + 6 * NC;
   const int f = blockIdx.x, v = threadIdx.x;
   if (v >= NV) return;
@@ -570,7 +891,7 @@ __global__ void __launch_bounds__(128) k_frame_finish(Dev d, int nsplit) {
 // Per co-visible frame pair (f1 > f2), one warp: S[f1, f2] = -sum_p W_{p,f1} V_{p,f2}^T.
 __global__ void __launch_bounds__(256) k_pairs(Dev d) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   // one CTA per pair, 1..8 warps (the launcher picks the width so that a rank with few pairs still fills the machine)
   const int pair = blockIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __shared__ double sred[8][36];
@@ -620,7 +941,7 @@ __global__ void __launch_bounds__(256) k_pairs(Dev d) {
 template <int NC>
 __global__ void k_coupled(Dev d) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   const int cur = st->cur;
   constexpr int RS = 9 + 3 * NC;
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
@@ -687,7 +1008,7 @@ __global__ void k_coupled(Dev d) {
 // Distance constraints (OurConstraintFunctionBundle, no loss) between coupled points; rank 0 only, one thread.
 __global__ void k_constraints(Dev d) {
   LmState* st = d.st;
-  if (st->done || d.rank != 0) return;
+  if (linear_phase_idle(st) || d.rank != 0) return;
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const double* pts = d.points[st->cur];
   for (int k = 0; k < d.K; ++k) {
@@ -718,7 +1039,7 @@ __global__ void k_constraints(Dev d) {
 // gradient statistics into the system scalars.
 __global__ void __launch_bounds__(1024) k_add_camera(Dev d) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   const int NC = d.NC, NH = NC * (NC + 1) / 2;
   const double* cs = d.camsum[st->cur];
   __shared__ double sp[64];
@@ -764,7 +1085,7 @@ __global__ void __launch_bounds__(1024) k_add_camera(Dev d) {
 // ================================================================================================
 __global__ void __launch_bounds__(1024) k_finalize(Dev d) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   const Options& o = d.opt;
   __shared__ double sg2[32], sgm[32];
   const bool first = st->first != 0;
@@ -864,10 +1185,11 @@ __global__ void __launch_bounds__(1024) k_finalize(Dev d) {
 template <int NC>
 __global__ void __launch_bounds__(128) k_point_step(Dev d) {
   LmState* st = d.st;
-  if (st->done || !st->solve_ok) return;
+  if (linear_phase_idle(st) || !st->solve_ok) return;
   const int cur = st->cur, cand = 1 - cur;
   __shared__ double red[4 * 8];
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double dmax = 0.0;
   const double* __restrict__ y = d.y;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d.P; p += gridDim.x * blockDim.x) {
     if (!d.pt_active[p] || d.pt_coupled[p] >= 0) continue;
@@ -919,16 +1241,26 @@ __global__ void __launch_bounds__(128) k_point_step(Dev d) {
       acc[2] += xn * xn;
       acc[3] += gp[j] * dl;
       if (!isfinite(yp[j])) acc[4] += 1.0;
+      if (d.recalib) {  // the projected line search re-applies delta at other step sizes
+        d.pstep[3 * (size_t)p + j] = -yp[j];
+        dmax = fmax(dmax, fabs(yp[j]));
+      }
     }
   }
   block_reduce_store<8>(acc, d.part_step + (size_t)blockIdx.x * 8, red);
+  if (d.recalib) {  // slot 5: max |delta| (a maximum, not a sum)
+    dmax = warp_max(dmax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dmax;
+    __syncthreads();
+    if (threadIdx.x == 0) d.part_step[(size_t)blockIdx.x * 8 + 5] = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+  }
 }
 
 // Back substitution output y (reduced) -> candidate camera (SubsetManifold + box bounds), poses, coupled points;
 // reduced-part scalars. One CTA.
 __global__ void __launch_bounds__(256) k_reduced_step(Dev d) {
   LmState* st = d.st;
-  if (st->done) return;
+  if (linear_phase_idle(st)) return;
   const int cur = st->cur, cand = 1 - cur;
   __shared__ double red[8 * 8];
   __shared__ double out[8];
@@ -984,6 +1316,19 @@ __global__ void __launch_bounds__(256) k_reduced_step(Dev d) {
     }
   }
   block_reduce_store<8>(acc, out, red);
+  if (d.recalib) {  // max |delta| over the reduced parameters (line-search step-size floor)
+    double m = 0.0;
+    if (st->solve_ok)
+      for (int j = threadIdx.x; j < d.n; j += blockDim.x) m = fmax(m, fabs(d.y[j]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double mm = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
+      st->dmax_red = mm;
+    }
+  }
   if (threadIdx.x == 0) {
     st->mcc_red = out[0];
     st->step2_red = out[1];
@@ -1008,6 +1353,8 @@ __global__ void __launch_bounds__(128) k_init_norms(Dev d) {
   block_reduce_store<8>(acc, d.part_step + (size_t)blockIdx.x * 8, red);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     double s = 0.0;
+    if (d.recalib)  // IterationZero of a bounds-constrained problem projects the start point into the box
+      for (int c = 0; c < 17; ++c) d.camera[cand][c] = fmin(fmax(d.camera[cand][c], d.cam_lo[c]), d.cam_hi[c]);
     for (int c = 0; c < 17; ++c) s += d.camera[cand][c] * d.camera[cand][c];
     if (d.refine_poses)
       for (int f = 0; f < d.F; ++f)
@@ -1018,7 +1365,7 @@ __global__ void __launch_bounds__(128) k_init_norms(Dev d) {
       s += X[0] * X[0] + X[1] * X[1] + X[2] * X[2];
     }
     d.st->norm2_red = s;
-    d.st->mcc_red = d.st->step2_red = d.st->gdelta_red = 0.0;
+    d.st->mcc_red = d.st->step2_red = d.st->gdelta_red = d.st->dmax_red = 0.0;
   }
 }
 
@@ -1034,7 +1381,10 @@ __global__ void __launch_bounds__(128) k_init_norms(Dev d) {
     default: { constexpr int NC = 9; CALL; } break; \
   }
 
-void prepare_eval_kernels() { prepare_rows_kernels(); }
+void prepare_eval_kernels() {
+  prepare_rows_kernels();
+  prepare_eval_only_kernels();
+}
 void launch_tables(const Dev& d, cudaStream_t s) {
   const int n = d.NL > d.F ? d.NL : d.F;
   k_tables<<<(n + 127) / 128, 128, 0, s>>>(d);
@@ -1044,6 +1394,17 @@ int launch_eval(const Dev& d, int L, cudaStream_t s) {
   return 1;
 }
 void launch_reduce_eval(const Dev& d, cudaStream_t s) { k_reduce_eval<<<1, 1024, 0, s>>>(d); }
+int launch_ls_gdot(const Dev& d, cudaStream_t s) {  // recalib: phi'(a) of the projected line search, before k_reduce_eval
+  if (!d.recalib) return 0;
+  k_ls_gdot<<<d.grid_pts, 128, 0, s>>>(d);
+  return 1;
+}
+int launch_ls_apply(const Dev& d, cudaStream_t s) {  // recalib: moves the candidate when a contraction trial is pending
+  if (!d.recalib) return 0;
+  k_ls_apply<<<d.grid_pts, 128, 0, s>>>(d);
+  k_ls_apply_reduced<<<1, 256, 0, s>>>(d);
+  return 2;
+}
 void launch_control_accept(const Dev& d, cudaStream_t s) { k_control_accept<<<1, 1, 0, s>>>(d); }
 int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
   int launches = 0;

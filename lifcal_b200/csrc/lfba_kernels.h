@@ -11,6 +11,8 @@ void launch_init_norms(const Dev& d, cudaStream_t s);
 void launch_tables(const Dev& d, cudaStream_t s);
 int launch_eval(const Dev& d, int lanes_per_track, cudaStream_t s);  // returns the number of kernels launched
 void launch_reduce_eval(const Dev& d, cudaStream_t s);
+int launch_ls_gdot(const Dev& d, cudaStream_t s);   // recalib only (else no launch); returns kernels launched
+int launch_ls_apply(const Dev& d, cudaStream_t s);  // recalib only
 void launch_control_accept(const Dev& d, cudaStream_t s);
 int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s);  // returns the number of kernels launched
 void launch_finalize(const Dev& d, cudaStream_t s);
@@ -49,6 +51,7 @@ struct EvalIn {
   const int32_t* frame_idx;
 };
 void launch_eval_only(const Dev& d, const EvalIn& in, const EvalOut& out, int which, cudaStream_t s);
+void prepare_eval_only_kernels();  // per device
 void launch_tables_for(const Dev& d, int which, cudaStream_t s);  // tables at parameter buffer `which`
 
 // ---- FP64 peak micro-benchmark ----

@@ -25,6 +25,8 @@
 // Rounds (32 / L length-adjacent tracks, one per L-lane group) are split evenly by ROW count over the warps of the grid.
 #include <cuda_pipeline.h>
 
+#include <mutex>
+
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
 
@@ -34,7 +36,9 @@ namespace lfba {
 // it here device-to-device on the solver's stream right before the kernel. Every use becomes a constant-bank operand of
 // the FP64 instruction itself instead of a shared-memory load with ~30 cycles of exposed latency (two warps per
 // scheduler cannot hide those) and the registers that cached the hot fields are free again.
-// One evaluation per device at a time (one solver stream): concurrent solvers on the SAME device would share it.
+// The symbol is per DEVICE, solvers are per stream: launch_eval_rows chains every (copy, kernel) pair on a device behind
+// the previous evaluation kernel of that device with an event, so two solver handles (or two host threads) on one
+// device cannot overwrite each other's model between copy and use.
 __constant__ CamModel c_cam;
 
 // 16-byte cp.async that ALLOCATES IN L1 (the __pipeline_memcpy_async form is .cg = L2 only): the evaluation order keeps
@@ -411,7 +415,23 @@ void prepare_rows_kernels() {
   prepare_rows_nc<9, 2>();
 }
 
+namespace {
+std::mutex g_cam_mutex;
+cudaEvent_t g_cam_event[64] = {};  // per device: end of the last evaluation kernel that read c_cam
+}  // namespace
+
 void launch_eval_rows(const Dev& d, int L, cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_cam_mutex);
+  cudaEvent_t& ev = g_cam_event[dev & 63];
+  if (ev) cudaStreamWaitEvent(s, ev, 0);
+  else cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  struct Rec {
+    cudaEvent_t e;
+    cudaStream_t s;
+    ~Rec() { cudaEventRecord(e, s); }
+  } rec_at_exit{ev, s};
   cudaMemcpyToSymbolAsync(c_cam, d.cm_buf, sizeof(CamModel), 0, cudaMemcpyDeviceToDevice, s);
   const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
   switch (nrad * 2 + tang) {

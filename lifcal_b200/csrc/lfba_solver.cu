@@ -5,11 +5,23 @@
 // Solver::Options, ceres::Solve); the parameter arrays camera[17], views[6F], p3d_w are updated in place to
 // the last accepted iterate like Ceres does. All LM decisions are taken by device kernels; the host enqueues
 // rounds and polls one flag.
+//
+// Structure: a Solver is ONE SHARD of a problem on one device (its observations, its partial reduced system). A Group
+// is what a caller's handle owns: one shard (single GPU, or this process's rank of an NCCL job), or — test hook
+// lfba_options.emulate_shards — several shards on one device and one stream, run in lock-step. A round has three
+// phases separated by the two points where the partial sums of the shards meet:
+//   phase_eval      tables, fused evaluation at the candidate, (recalib: phi'(a) of the line search), CTA-partial sums
+//   [sum over shards: 8 + nranks scalars]          NCCL all-reduce, or k_shard_allreduce over the emulated shards
+//   phase_assemble  accept/reject (+ projected Armijo line search), Schur assembly at the accepted state
+//   [sum over shards: S | g | gfull | hdiag | scalars]
+//   phase_solve     damping, reduced solve, back-substitution + candidate, (recalib: line-search trial point)
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,6 +54,7 @@ struct Nccl {
   int (*GetUniqueId)(UniqueId*) = nullptr;
   int (*CommInitRank)(comm_t*, int, UniqueId, int) = nullptr;
   int (*CommDestroy)(comm_t) = nullptr;
+  int (*CommAbort)(comm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   void* handle = nullptr;
@@ -59,6 +72,7 @@ struct Nccl {
       n.GetUniqueId = (int (*)(UniqueId*))dlsym(n.handle, "ncclGetUniqueId");
       n.CommInitRank = (int (*)(comm_t*, int, UniqueId, int))dlsym(n.handle, "ncclCommInitRank");
       n.CommDestroy = (int (*)(comm_t))dlsym(n.handle, "ncclCommDestroy");
+      n.CommAbort = (int (*)(comm_t))dlsym(n.handle, "ncclCommAbort");
       n.AllReduce =
           (int (*)(const void*, void*, size_t, int, int, comm_t, cudaStream_t))dlsym(n.handle, "ncclAllReduce");
       n.GetErrorString = (const char* (*)(int))dlsym(n.handle, "ncclGetErrorString");
@@ -70,18 +84,34 @@ struct Nccl {
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclInt32 = 2;    // ncclInt32
 constexpr int kNcclSum = 0, kNcclMax = 2;
+constexpr int kMaxEmulatedShards = 16;
 
 __global__ void k_point_flags(const int32_t* pt_trk_begin, const int32_t* pt_coupled, int32_t* pt_active, int P) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < P) pt_active[p] = (pt_trk_begin[p + 1] > pt_trk_begin[p] || pt_coupled[p] >= 0) ? 1 : 0;
 }
 
+// Emulated shards: what the NCCL all-reduce (sum) does for real ranks — every shard's buffer becomes the sum over all
+// shards, added in shard order (fixed: deterministic).
+struct ShardBufs {
+  double* p[kMaxEmulatedShards];
+  int n;
+};
+__global__ void k_shard_allreduce(ShardBufs b, size_t count) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < b.n; ++r) s += b.p[r][i];
+    for (int r = 0; r < b.n; ++r) b.p[r][i] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct StreamHolder {  // declared first in Solver => destroyed last, after every stream-ordered free has been queued
   cudaStream_t s = nullptr;
   int device = 0;
+  bool owned = true;
   ~StreamHolder() {
-    if (s) {
+    if (s && owned) {
       cudaSetDevice(device);
       cudaStreamSynchronize(s);
       cudaStreamDestroy(s);
@@ -95,9 +125,8 @@ struct Solver {
   uint32_t config = 0;
   int calib_type = 0;
   int device = 0;
+  int sms = 148;
   cudaStream_t stream = nullptr;
-  Nccl::comm_t comm = nullptr;
-  bool own_comm = false;
   int rank = 0, nranks = 1;
   ProblemIndex ix;
   Dev d;
@@ -107,58 +136,48 @@ struct Solver {
   int band_frames = 0;
   PartPlan* part_plan = nullptr;
   int64_t launches = 0;
-  double setup_time = 0;
+  double setup_time = 0, t_create0 = 0;
   int64_t n_obs_global = 0;
+  int K = 0, Pc = 0;
+  double spx = 0, spy = 0, scale = 1;
+  std::vector<int32_t> h_fa;  // [F] frame has observations on this shard, [F] = co-visibility bandwidth of this shard
 
   DevBuf<int32_t> pt_coupled, coupled_pts, pt_active, frm_active, c_p1, c_p2, tile_first, row_c0;
   DevBuf<int64_t> row_off;
   DevBuf<double> c_dist, c_sigma;
   DevBuf<double> camera0, views0, points0;  // parameters given by the caller: every run() starts from them
-  DevBuf<double> camera[2], views[2], points[2], lens, frames[2], rec[2], camsum[2], pdata, pscale, vw;
-  DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one NCCL all-reduce)
-  DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step, frame_part;
+  DevBuf<double> camera[2], views[2], points[2], lens, frames[2], rec[2], camsum[2], pdata, pscale, vw, pstep;
+  DevBuf<double> redbuf;  // S | g | gfull | hdiag | sys_scalars   (one all-reduce)
+  DevBuf<double> rscale, rdamp, y, eval_scalars, part_eval, part_pts, part_step, part_ls, frame_part;
   DevBuf<CamModel> cm_buf;
   DevBuf<LmState> st;
   DevBuf<lfba_iteration> log;
-  size_t S_len = 0, red_len = 0;
-  int* h_done = nullptr;  // pinned
+  size_t S_len = 0, red_len = 0, es_len = ES_COUNT;
   std::vector<int> h_coupled;
   cudaEvent_t ev[LFBA_NUM_KERNEL_TIMERS + 1];
-  cudaEvent_t ev_round[4];
   bool ev_made = false;
+  bool prof = false;
+  LmState h_state{};
 
   ~Solver() {
     cudaSetDevice(device);
-    if (ev_made) {
+    if (ev_made)
       for (auto& e : ev) cudaEventDestroy(e);
-      for (auto& e : ev_round) cudaEventDestroy(e);
-    }
-    if (h_done) cudaFreeHost(h_done);
     part_plan_destroy(part_plan);
-    if (comm && own_comm) Nccl::get().CommDestroy(comm);
     alloc_stream() = stream;  // member buffers are freed (stream-ordered) right after this body
   }
 
-  void allreduce(void* buf, size_t count, int dtype, int op) {
-    if (nranks <= 1 || count == 0) return;
-    const int rc = Nccl::get().AllReduce(buf, buf, count, dtype, op, comm, stream);
-    if (rc != 0) throw CudaError(std::string("ncclAllReduce: ") + Nccl::get().GetErrorString(rc), LFBA_NCCL_ERROR);
-  }
-
-  void create(const lfba_problem& pb, const lfba_options& o, const lfba_comm* cm) {
-    const double t0 = now_s();
-    const bool dbg = std::getenv("LFBA_DEBUG") != nullptr;
-    double tp = t0;
-    auto phase = [&](const char* name) {
-      if (!dbg) return;
-      cudaStreamSynchronize(stream);
-      const double t = now_s();
-      std::fprintf(stderr, "[lfba dbg] setup %-28s %8.2f ms\n", name, 1e3 * (t - tp));
-      tp = t;
-    };
+  // ---- set-up, step 1: device, stream, index of this shard's observations (no communication) ----
+  void create_local(const lfba_problem& pb, const lfba_options& o, int rank_, int nranks_, cudaStream_t shared_stream) {
+    t_create0 = now_s();
     opt = o;
     config = pb.config;
     calib_type = pb.calib_type;
+    rank = rank_;
+    nranks = nranks_;
+    spx = pb.spx;
+    spy = pb.spy;
+    scale = pb.scale;
     const bool rposes = (config & LFBA_CFG_REFINE_POSES) != 0, rpoints = (config & LFBA_CFG_REFINE_POINTS) != 0;
     if (!rposes && rpoints)
       throw CudaError("refinePoses=0 with refine3Dpoints=1 is invalid (null dereference in the reference, "
@@ -175,7 +194,13 @@ struct Solver {
     cudaDeviceProp prop;
     LFBA_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) throw CudaError("device is not sm_100-class: kernels are built for sm_100a only", LFBA_NO_DEVICE);
-    LFBA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    sms = prop.multiProcessorCount;
+    if (shared_stream) {
+      stream = shared_stream;
+      sh.owned = false;
+    } else {
+      LFBA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
     sh.s = stream;
     sh.device = device;
     alloc_stream() = stream;
@@ -186,42 +211,13 @@ struct Solver {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
       }
     }
-    LFBA_CUDA(cudaMallocHost(&h_done, 4 * sizeof(int)));
-    if (cm && cm->nranks > 1) {
-      Nccl& n = Nccl::get();
-      if (!n.ok) throw CudaError("libnccl.so.2 not found", LFBA_NCCL_ERROR);
-      rank = cm->rank;
-      nranks = cm->nranks;
-      if (cm->handle) {
-        comm = (Nccl::comm_t)cm->handle;
-      } else {
-        Nccl::UniqueId id;
-        std::memcpy(id.internal, cm->nccl_unique_id, 128);
-        const int rc = n.CommInitRank(&comm, nranks, id, rank);
-        if (rc != 0) throw CudaError(std::string("ncclCommInitRank: ") + n.GetErrorString(rc), LFBA_NCCL_ERROR);
-        own_comm = true;
-      }
-    }
-
-    auto poolstat = [&](const char* w) {
-      if (!dbg) return;
-      cudaMemPool_t pool;
-      unsigned long long res = 0, used = 0;
-      cudaDeviceGetDefaultMemPool(&pool, device);
-      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res);
-      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-      std::fprintf(stderr, "[lfba dbg] pool %-10s reserved %.2f GB used %.2f GB\n", w, res / 1e9, used / 1e9);
-    };
-    poolstat("start");
-    phase("validate+device+stream");
     build_index(pb, ix, stream, &launches);
-    phase("build_index");
-    const int P = ix.P, F = ix.F, T = ix.T;
-    const int nrad = (int)(config & 3u), tang = (config & LFBA_CFG_TANGENTIAL) ? 1 : 0;
-    const int NC = 5 + nrad + 2 * tang;
+    const int P = ix.P, F = ix.F;
     const bool recalib = calib_type == LFBA_RECALIBRATION;
     const bool use_constraints = rpoints && !recalib && pb.n_constraints > 0;  // :916
-    const int K = use_constraints ? pb.n_constraints : 0;
+    K = use_constraints ? pb.n_constraints : 0;
+    if (K > 0 && (!pb.c_p1 || !pb.c_p2 || !pb.c_dist || !pb.c_sigma))
+      throw CudaError("null constraint array", LFBA_INVALID_ARGUMENT);
 
     // ---- coupled points (touched by a distance constraint): kept in the reduced system ----
     std::vector<int32_t> h_ptc((size_t)P, -1);
@@ -237,7 +233,7 @@ struct Solver {
         h_ptc[p] = (int)h_coupled.size();
         h_coupled.push_back(p);
       }
-    const int Pc = (int)h_coupled.size();
+    Pc = (int)h_coupled.size();
     pt_coupled.alloc(P);
     pt_coupled.upload(h_ptc.data(), P, stream);
     coupled_pts.alloc(std::max(1, Pc));
@@ -255,25 +251,28 @@ struct Solver {
       c_dist.upload(pb.c_dist, K, stream);
       c_sigma.upload(pb.c_sigma, K, stream);
     }
-    // ---- frames with observations anywhere, co-visibility bandwidth, observation count: global ----
-    std::vector<int32_t> h_fa((size_t)F + 2, 0);
+    h_fa.assign((size_t)F + 1, 0);
     for (int f = 0; f < F; ++f) h_fa[f] = ix.h_frame_count[f] > 0 ? 1 : 0;
     h_fa[F] = ix.bandwidth;
+    LFBA_CUDA(cudaStreamSynchronize(stream));  // the host vectors above go out of scope
+  }
+
+  // ---- set-up, step 2: with the frame flags / bandwidth / observation count of ALL shards known ----
+  void create_finish(const std::vector<int32_t>& fa_global, int64_t n_obs_all) {
+    LFBA_CUDA(cudaSetDevice(device));
+    alloc_stream() = stream;
+    const lfba_options& o = opt;
+    const bool rposes = (config & LFBA_CFG_REFINE_POSES) != 0, rpoints = (config & LFBA_CFG_REFINE_POINTS) != 0;
+    const int P = ix.P, F = ix.F, T = ix.T;
+    const int nrad = (int)(config & 3u), tang = (config & LFBA_CFG_TANGENTIAL) ? 1 : 0;
+    const int NC = 5 + nrad + 2 * tang;
+    const bool recalib = calib_type == LFBA_RECALIBRATION;
+    n_obs_global = n_obs_all;
     frm_active.alloc((size_t)F + 2);
-    frm_active.upload(h_fa.data(), (size_t)F + 2, stream);
-    allreduce(frm_active.p, (size_t)F + 1, kNcclInt32, kNcclMax);
-    frm_active.download(h_fa.data(), (size_t)F + 1, stream);
-    DevBuf<double> ncount(1);
-    double h_n = (double)ix.N;
-    ncount.upload(&h_n, 1, stream);
-    allreduce(ncount.p, 1, kNcclFloat64, kNcclSum);
-    ncount.download(&h_n, 1, stream);
-    LFBA_CUDA(cudaStreamSynchronize(stream));
-    n_obs_global = (int64_t)(h_n + 0.5);
-    const int bw = h_fa[F];
+    frm_active.upload(fa_global.data(), (size_t)F + 1, stream);
+    const int bw = fa_global[F];
     band_frames = bw;
 
-    phase("flags+global counts");
     // ---- reduced system layout [poses | coupled points | camera | rhs] and its skyline profile ----
     std::memset(&d, 0, sizeof(d));
     d.np6 = rposes ? 6 * F : 0;
@@ -312,14 +311,15 @@ struct Solver {
     tile_first.alloc(n_tiles);
     tile_first.upload(h_tf.data(), n_tiles, stream);
 
-    phase("layout");
     // ---- buffers ----
     red_len = S_len + 3 * (size_t)n + SS_COUNT + (size_t)nranks;
+    es_len = ES_COUNT + (size_t)nranks;
     redbuf.alloc(red_len);
     rscale.alloc(std::max(1, n));
     rdamp.alloc(std::max(1, n));
     y.alloc(std::max(1, n));
-    eval_scalars.alloc(ES_COUNT);
+    y.zero(stream);
+    eval_scalars.alloc(es_len);
     eval_scalars.zero(stream);
     for (int b = 0; b < 2; ++b) {
       camera[b].alloc(17);
@@ -335,19 +335,23 @@ struct Solver {
     pdata.zero(stream);
     pscale.alloc((size_t)3 * P);
     vw.alloc((size_t)std::max(1, T) * kVWStride);
+    if (recalib) {
+      pstep.alloc((size_t)3 * P);
+      pstep.zero(stream);
+    }
     st.alloc(1);
     log.alloc(kMaxLog);
     cm_buf.alloc(1);
     cm_buf.zero(stream);
 
     // ---- launch geometry ----
-    const int sms = prop.multiProcessorCount;
-    d.grid_eval = std::max(1, std::min(2 * sms, (T * 4 + 127) / 128));
     d.grid_pts = std::max(1, std::min(4 * sms, (P + 127) / 128));
     part_pts.alloc((size_t)d.grid_pts * 64);
     part_step.alloc((size_t)d.grid_pts * 8);
+    part_ls.alloc((size_t)d.grid_pts);
     part_pts.zero(stream);
     part_step.zero(stream);
+    part_ls.zero(stream);
     // lanes per track (L): the fused evaluation walks ROUNDS of 32 / L length-adjacent tracks per warp. L = 1 has no
     // cross-lane reduction and no predicated per-track work (measured at cfg4: 4.9 ms vs 7.3 ms for L = 4), so L grows
     // only while there are too few rounds to give every warp of the grid a few of them.
@@ -364,9 +368,8 @@ struct Solver {
     }
     part_eval.alloc((size_t)d.grid_eval * 64);
     build_stream(ix, lanes, stream, &launches);
-    phase("packed stream");
     {
-      // frames that have tracks ON THIS RANK: a shard of a multi-GPU solve touches F / nranks of them, and one CTA per
+      // frames that have tracks ON THIS SHARD: a shard of a multi-GPU solve touches F / nranks of them, and one CTA per
       // frame would leave most SMs idle — split the frames' track lists over several CTAs then
       int f_local = 0;
       for (int f = 0; f < F; ++f) f_local += ix.h_frame_count[f] > 0 ? 1 : 0;
@@ -381,7 +384,7 @@ struct Solver {
     d.N = ix.N; d.T = T; d.P = P; d.F = F; d.NL = ix.NL; d.K = K; d.NC = NC;
     d.rank = rank; d.nranks = nranks; d.config = config; d.recalib = recalib ? 1 : 0;
     d.refine_poses = rposes ? 1 : 0; d.refine_points = rpoints ? 1 : 0;
-    d.spx = pb.spx; d.spy = pb.spy; d.scale = pb.scale;
+    d.spx = spx; d.spy = spy; d.scale = scale;
     d.opt.max_iter = o.max_num_iterations; d.opt.ftol = o.function_tolerance; d.opt.ptol = o.parameter_tolerance;
     d.opt.gtol = o.gradient_tolerance; d.opt.r0 = o.initial_trust_region_radius; d.opt.rmax = o.max_trust_region_radius;
     d.opt.rmin = o.min_trust_region_radius; d.opt.min_rel_dec = o.min_relative_decrease;
@@ -404,22 +407,21 @@ struct Solver {
       d.frames[b] = frames[b].p; d.rec[b] = rec[b].p; d.camsum[b] = camsum[b].p;
     }
     d.lens = lens.p; d.lens_xy = ix.lens_xy.p; d.cm_buf = cm_buf.p;
-    d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p;
+    d.pdata = pdata.p; d.pscale = pscale.p; d.vw = vw.p; d.pstep = pstep.p;
     d.S = redbuf.p; d.row_off = row_off.p; d.row_c0 = row_c0.p;
     d.g = redbuf.p + S_len; d.gfull = d.g + n; d.hdiag = d.gfull + n; d.sys_scalars = d.hdiag + n;
     d.rscale = rscale.p; d.rdamp = rdamp.p; d.y = y.p; d.eval_scalars = eval_scalars.p;
-    d.part_eval = part_eval.p; d.part_pts = part_pts.p; d.part_step = part_step.p; d.frame_part = frame_part.p;
+    d.part_eval = part_eval.p; d.part_pts = part_pts.p; d.part_step = part_step.p; d.part_ls = part_ls.p;
+    d.frame_part = frame_part.p;
     d.st = st.p; d.log = log.p;
     for (auto& e : ev) LFBA_CUDA(cudaEventCreate(&e));
-    for (auto& e : ev_round) LFBA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ev_made = true;
     prepare_device_kernels();
     prepare_eval_kernels();
     part_plan = part_plan_create(d, band_frames, stream);
     LFBA_CUDA(cudaStreamSynchronize(stream));
-    phase("buffers");
-    poolstat("end");
-    setup_time = now_s() - t0;
+    LFBA_CUDA(cudaGetLastError());
+    setup_time = now_s() - t_create0;
   }
 
   void set_parameters(const double* cam, const double* vw_, const double* pts) {
@@ -436,8 +438,9 @@ struct Solver {
     if (calib_type == LFBA_RECALIBRATION) {  // bounds from the INITIAL values (:943-951)
       const int bj[3] = {1, 3, 4};
       for (int k = 0; k < 3; ++k) {
-        d.cam_lo[bj[k]] = 0.7 * cam[bj[k]];
-        d.cam_hi[bj[k]] = 1.3 * cam[bj[k]];
+        const double a = 0.7 * cam[bj[k]], b = 1.3 * cam[bj[k]];
+        d.cam_lo[bj[k]] = std::min(a, b);
+        d.cam_hi[bj[k]] = std::max(a, b);
       }
     }
     LFBA_CUDA(cudaStreamSynchronize(stream));
@@ -459,134 +462,308 @@ struct Solver {
     LFBA_CUDA(cudaStreamSynchronize(stream));
   }
 
-  LmState h_state{};
-
-  int run(lfba_summary* sum) {
+  // ---- one LM solve, phase by phase (driven by Group::run) ----
+  void begin_run() {
     LFBA_CUDA(cudaSetDevice(device));
-    const double t0 = now_s();
-    const int64_t launches0 = launches;
+    if (!camera0.p) throw CudaError("lfba_solver_run before lfba_solver_set_parameters", LFBA_INVALID_ARGUMENT);
     LmState init;
     std::memset(&init, 0, sizeof(init));
     init.cur = 0;
     init.solve_ok = 1;
     init.radius = opt.initial_trust_region_radius;
     init.decrease_factor = 2.0;
-    if (!camera0.p) throw CudaError("lfba_solver_run before lfba_solver_set_parameters", LFBA_INVALID_ARGUMENT);
     reset_parameters();  // every run starts from the parameters last given by the caller
     LFBA_CUDA(cudaMemcpyAsync(st.p, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
-    if (calib_type == LFBA_RECALIBRATION) {
-      // IterationZero of a bounds-constrained problem projects the start point into the box
-      double cam[17];
-      camera[1].download(cam, 17, stream);
-      LFBA_CUDA(cudaStreamSynchronize(stream));
-      for (int c = 0; c < 17; ++c) cam[c] = std::min(std::max(cam[c], d.cam_lo[c]), d.cam_hi[c]);
-      camera[1].upload(cam, 17, stream);
+    launch_init_norms(d, stream);  // also projects the start point into the box (recalib)
+    ++launches;
+  }
+  void mark(int slot) {
+    if (prof) LFBA_CUDA(cudaEventRecord(ev[slot], stream));
+  }
+  void phase_eval() {
+    if (prof) LFBA_CUDA(cudaEventRecord(ev[LFBA_NUM_KERNEL_TIMERS], stream));
+    launch_tables(d, stream);
+    mark(LFBA_T_LENS);
+    launches += launch_eval(d, lanes, stream);
+    launches += launch_ls_gdot(d, stream);
+    mark(LFBA_T_EVAL);
+    launch_reduce_eval(d, stream);
+    launches += 2;
+  }
+  void phase_assemble() {
+    launch_control_accept(d, stream);
+    mark(LFBA_T_CONTROL);
+    LFBA_CUDA(cudaMemsetAsync(redbuf.p, 0, red_len * sizeof(double), stream));
+    launches += 2;
+    launches += launch_assembly(d, frame_splits, stream);
+    mark(LFBA_T_SCHUR);
+  }
+  void phase_solve() {
+    mark(LFBA_T_ALLREDUCE);
+    launch_finalize(d, stream);
+    mark(LFBA_T_DAMP);
+    launches += 1 + launch_reduced_solve(d, n_tiles, tile_first.p, band_frames, stream, part_plan);
+    mark(LFBA_T_CHOL);
+    launches += launch_steps(d, stream);
+    launches += launch_ls_apply(d, stream);
+    mark(LFBA_T_POINTSTEP);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Sharding by point: contiguous point ranges balanced by observation count; every observation of a point goes to the
+// point's owner (the per-point 3x3 elimination needs them together); constraint-coupled points live on shard 0.
+// ------------------------------------------------------------------------------------------------
+struct HostShards {
+  std::vector<int> owner;
+  struct Arrays {
+    std::vector<double> ox, oy, mx, my;
+    std::vector<int32_t> pi, fi;
+  };
+  std::vector<Arrays> sh;
+  void split(const lfba_problem& pb, int G) {
+    const int P = pb.n_points;
+    const int64_t N = pb.n_obs;
+    if (P <= 0 || pb.n_frames <= 0 || N < 0) throw CudaError("empty problem: need n_frames > 0 and n_points > 0", LFBA_INVALID_ARGUMENT);
+    if (N > 0 && (!pb.obs_x || !pb.obs_y || !pb.ml_x || !pb.ml_y || !pb.point_idx || !pb.frame_idx))
+      throw CudaError("null observation array", LFBA_INVALID_ARGUMENT);
+    for (int64_t i = 0; i < N; ++i)
+      if (pb.point_idx[i] < 0 || pb.point_idx[i] >= P || pb.frame_idx[i] < 0 || pb.frame_idx[i] >= pb.n_frames)
+        throw CudaError("observation index out of range", LFBA_INVALID_ARGUMENT);
+    const bool use_c = (pb.config & LFBA_CFG_REFINE_POINTS) && pb.calib_type != LFBA_RECALIBRATION && pb.n_constraints > 0;
+    if (use_c) {
+      if (!pb.c_p1 || !pb.c_p2 || !pb.c_dist || !pb.c_sigma) throw CudaError("null constraint array", LFBA_INVALID_ARGUMENT);
+      for (int k = 0; k < pb.n_constraints; ++k)
+        if (pb.c_p1[k] < 0 || pb.c_p1[k] >= P || pb.c_p2[k] < 0 || pb.c_p2[k] >= P)
+          throw CudaError("constraint point id out of range", LFBA_INVALID_ARGUMENT);
     }
-    cudaEvent_t e_begin = ev[LFBA_NUM_KERNEL_TIMERS];
+    std::vector<int64_t> cnt((size_t)P + 1, 0);
+    for (int64_t i = 0; i < N; ++i) cnt[pb.point_idx[i] + 1]++;
+    for (int p = 0; p < P; ++p) cnt[p + 1] += cnt[p];
+    owner.assign((size_t)P, 0);
+    for (int p = 0; p < P; ++p) owner[p] = (int)std::min<int64_t>(G - 1, (cnt[p] * G) / std::max<int64_t>(1, N));
+    if (use_c)
+      for (int k = 0; k < pb.n_constraints; ++k) owner[pb.c_p1[k]] = owner[pb.c_p2[k]] = 0;
+    sh.assign((size_t)G, Arrays());
+    for (int64_t i = 0; i < N; ++i) {
+      Arrays& s = sh[(size_t)owner[pb.point_idx[i]]];
+      s.ox.push_back(pb.obs_x[i]);
+      s.oy.push_back(pb.obs_y[i]);
+      s.mx.push_back(pb.ml_x[i]);
+      s.my.push_back(pb.ml_y[i]);
+      s.pi.push_back(pb.point_idx[i]);
+      s.fi.push_back(pb.frame_idx[i]);
+    }
+  }
+  lfba_problem view(const lfba_problem& pb, int r) const {
+    lfba_problem lp = pb;
+    lp.n_obs = (int64_t)sh[r].ox.size();
+    lp.obs_x = sh[r].ox.data();
+    lp.obs_y = sh[r].oy.data();
+    lp.ml_x = sh[r].mx.data();
+    lp.ml_y = sh[r].my.data();
+    lp.point_idx = sh[r].pi.data();
+    lp.frame_idx = sh[r].fi.data();
+    return lp;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct Group {
+  std::vector<std::unique_ptr<Solver>> sh;
+  std::vector<int> owner;  // emulated shards: owner of each point
+  Nccl::comm_t comm = nullptr;
+  bool own_comm = false;
+  int rank = 0, nranks = 1;  // of this process in the NCCL job (1 when single-GPU or emulated)
+  int* h_done = nullptr;     // pinned
+  cudaEvent_t ev_round[4];
+  bool ev_made = false;
+  lfba_options opt;
+  const std::atomic<int>* comm_aborted = nullptr;  // lfba_solve(num_gpus): set when a peer aborted the communicators
+
+  ~Group() {
+    if (!sh.empty()) cudaSetDevice(sh[0]->device);
+    if (ev_made)
+      for (auto& e : ev_round) cudaEventDestroy(e);
+    if (h_done) cudaFreeHost(h_done);
+    while (!sh.empty()) sh.pop_back();  // reverse order: shard 0 owns the stream the emulated shards share
+    if (comm && own_comm && !(comm_aborted && comm_aborted->load())) Nccl::get().CommDestroy(comm);
+  }
+  Solver& s0() { return *sh[0]; }
+  bool emulated() const { return sh.size() > 1; }
+
+  void nccl_allreduce(void* buf, size_t count, int dtype, int op) {
+    if (nranks <= 1 || count == 0) return;
+    const int rc = Nccl::get().AllReduce(buf, buf, count, dtype, op, comm, s0().stream);
+    if (rc != 0) throw CudaError(std::string("ncclAllReduce: ") + Nccl::get().GetErrorString(rc), LFBA_NCCL_ERROR);
+  }
+  // where the partial sums of the shards meet; which: 0 = evaluation scalars, 1 = reduced system
+  void reduce(int which) {
+    if (emulated()) {
+      ShardBufs b;
+      b.n = (int)sh.size();
+      for (int r = 0; r < b.n; ++r) b.p[r] = which == 0 ? sh[r]->eval_scalars.p : sh[r]->redbuf.p;
+      const size_t count = which == 0 ? s0().es_len : s0().red_len;
+      const int grid = (int)std::min<size_t>(4 * (size_t)s0().sms, (count + 255) / 256);
+      k_shard_allreduce<<<std::max(1, grid), 256, 0, s0().stream>>>(b, count);
+      s0().launches += 1;
+    } else if (nranks > 1) {
+      if (which == 0) nccl_allreduce(s0().eval_scalars.p, s0().es_len, kNcclFloat64, kNcclSum);
+      else nccl_allreduce(s0().redbuf.p, s0().red_len, kNcclFloat64, kNcclSum);
+    }
+  }
+
+  void create(const lfba_problem& pb, const lfba_options& o, const lfba_comm* cm) {
+    opt = o;
+    const int E = o.emulate_shards > 1 ? o.emulate_shards : 1;
+    if (E > 1 && cm && cm->nranks > 1)
+      throw CudaError("emulate_shards cannot be combined with an NCCL communicator", LFBA_INVALID_ARGUMENT);
+    if (E > kMaxEmulatedShards) throw CudaError("emulate_shards > 16", LFBA_INVALID_ARGUMENT);
+    if (E > 1) {
+      HostShards hs;
+      hs.split(pb, E);
+      owner = hs.owner;
+      for (int r = 0; r < E; ++r) {
+        sh.emplace_back(new Solver());
+        const lfba_problem lp = hs.view(pb, r);
+        sh[r]->create_local(lp, o, r, E, r == 0 ? nullptr : sh[0]->stream);
+      }
+    } else {
+      sh.emplace_back(new Solver());
+      if (cm && cm->nranks > 1) {
+        rank = cm->rank;
+        nranks = cm->nranks;
+      }
+      sh[0]->create_local(pb, o, rank, nranks, nullptr);
+      if (nranks > 1) {
+        Nccl& n = Nccl::get();
+        if (!n.ok) throw CudaError("libnccl.so.2 not found", LFBA_NCCL_ERROR);
+        if (cm->handle) {
+          comm = (Nccl::comm_t)cm->handle;
+        } else {
+          Nccl::UniqueId id;
+          std::memcpy(id.internal, cm->nccl_unique_id, 128);
+          const int rc = n.CommInitRank(&comm, nranks, id, rank);
+          if (rc != 0) throw CudaError(std::string("ncclCommInitRank: ") + n.GetErrorString(rc), LFBA_NCCL_ERROR);
+          own_comm = true;
+        }
+      }
+    }
+    // ---- frames with observations anywhere, co-visibility bandwidth, observation count: over all shards ----
+    const int F = s0().ix.F;
+    std::vector<int32_t> fa((size_t)F + 1, 0);
+    int64_t n_all = 0;
+    for (auto& s : sh) {
+      for (int f = 0; f <= F; ++f) fa[f] = std::max(fa[f], s->h_fa[f]);
+      n_all += s->ix.N;
+    }
+    if (nranks > 1) {
+      Solver& s = s0();
+      alloc_stream() = s.stream;
+      DevBuf<int32_t> dfa((size_t)F + 1);
+      DevBuf<double> dn(1);
+      double h_n = (double)n_all;
+      dfa.upload(fa.data(), (size_t)F + 1, s.stream);
+      dn.upload(&h_n, 1, s.stream);
+      nccl_allreduce(dfa.p, (size_t)F + 1, kNcclInt32, kNcclMax);
+      nccl_allreduce(dn.p, 1, kNcclFloat64, kNcclSum);
+      dfa.download(fa.data(), (size_t)F + 1, s.stream);
+      dn.download(&h_n, 1, s.stream);
+      LFBA_CUDA(cudaStreamSynchronize(s.stream));
+      n_all = (int64_t)(h_n + 0.5);
+    }
+    for (auto& s : sh) s->create_finish(fa, n_all);
+    LFBA_CUDA(cudaMallocHost(&h_done, 4 * sizeof(int)));
+    for (auto& e : ev_round) LFBA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_made = true;
+  }
+
+  void set_parameters(const double* c, const double* v, const double* p) {
+    for (auto& s : sh) s->set_parameters(c, v, p);
+  }
+  void get_parameters(double* c, double* v, double* p) {
+    Solver& a = s0();
+    a.get_parameters(a.h_state.cur, c, v, p);
+    if (p && emulated()) {  // every shard moved only its own points
+      std::vector<double> tmp((size_t)3 * a.ix.P);
+      for (size_t r = 1; r < sh.size(); ++r) {
+        sh[r]->get_parameters(sh[r]->h_state.cur, nullptr, nullptr, tmp.data());
+        for (int q = 0; q < a.ix.P; ++q)
+          if (owner[q] == (int)r)
+            for (int j = 0; j < 3; ++j) p[3 * (size_t)q + j] = tmp[3 * (size_t)q + j];
+      }
+    }
+  }
+
+  int run(lfba_summary* sum) {
+    Solver& a = s0();
+    LFBA_CUDA(cudaSetDevice(a.device));
+    cudaStream_t stream = a.stream;
+    const double t0 = now_s();
+    std::vector<int64_t> launches0;
+    for (auto& s : sh) launches0.push_back(s->launches);
+    const bool prof = opt.profile != 0 && !emulated();
+    a.prof = prof;
     double kms[LFBA_NUM_KERNEL_TIMERS] = {0};
     int64_t kcalls[LFBA_NUM_KERNEL_TIMERS] = {0};
-    const bool prof = opt.profile != 0;
-    const bool debug = std::getenv("LFBA_DEBUG") != nullptr;
     cudaEvent_t e_run0, e_run1;
     LFBA_CUDA(cudaEventCreate(&e_run0));
     LFBA_CUDA(cudaEventCreate(&e_run1));
     LFBA_CUDA(cudaEventRecord(e_run0, stream));
-    launch_init_norms(d, stream);
-    ++launches;
-
-    auto mark = [&](int slot) { if (prof) LFBA_CUDA(cudaEventRecord(ev[slot], stream)); };
-    const int max_rounds = opt.max_num_iterations + 8;
+    for (auto& s : sh) s->begin_run();
+    // recalib: a round may be a line-search trial (no LM row); each iteration has at most 20 contractions + 1
+    const int max_rounds = (opt.max_num_iterations + 8) * (a.d.recalib ? 22 : 1);
     int rounds = 0;
     for (; rounds < max_rounds; ++rounds) {
-      if (prof) LFBA_CUDA(cudaEventRecord(e_begin, stream));
-      launch_tables(d, stream);
-      mark(LFBA_T_LENS);
-      launches += launch_eval(d, lanes, stream) - 1;
-      mark(LFBA_T_EVAL);
-      launch_reduce_eval(d, stream);
-      allreduce(d.eval_scalars, ES_COUNT, kNcclFloat64, kNcclSum);
-      launch_control_accept(d, stream);
-      mark(LFBA_T_CONTROL);
-      LFBA_CUDA(cudaMemsetAsync(redbuf.p, 0, red_len * sizeof(double), stream));
-      launches += 5;
-      launches += launch_assembly(d, frame_splits, stream);
-      mark(LFBA_T_SCHUR);
-      allreduce(redbuf.p, red_len, kNcclFloat64, kNcclSum);
-      mark(LFBA_T_ALLREDUCE);
-      launch_finalize(d, stream);
-      mark(LFBA_T_DAMP);
-      launches += 1 + launch_reduced_solve(d, n_tiles, tile_first.p, band_frames, stream, part_plan);
-      mark(LFBA_T_CHOL);
-      launches += launch_steps(d, stream);
-      mark(LFBA_T_POINTSTEP);
+      for (auto& s : sh) s->phase_eval();
+      reduce(0);
+      for (auto& s : sh) s->phase_assemble();
+      reduce(1);
+      for (auto& s : sh) s->phase_solve();
       // The host runs ONE round ahead of the device: round r + 1 is enqueued before the `done` flag of round r is read,
       // so the stream never drains between rounds (every kernel early-outs on the device flag once the solve is over;
       // all ranks see the same flags, so they enqueue the same rounds and the NCCL calls stay matched).
       const int slot = rounds & 3;
-      LFBA_CUDA(cudaMemcpyAsync(h_done + slot, &st.p->done, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      LFBA_CUDA(cudaMemcpyAsync(h_done + slot, &a.st.p->done, sizeof(int), cudaMemcpyDeviceToHost, stream));
       LFBA_CUDA(cudaEventRecord(ev_round[slot], stream));
-      if (prof || debug) {
+      LFBA_CUDA(cudaGetLastError());  // launch-configuration errors do not surface in later memcpy / sync calls
+      if (prof) {
         LFBA_CUDA(cudaStreamSynchronize(stream));
+        const int order[] = {LFBA_T_LENS, LFBA_T_EVAL, LFBA_T_CONTROL, LFBA_T_SCHUR, LFBA_T_ALLREDUCE, LFBA_T_DAMP,
+                             LFBA_T_CHOL, LFBA_T_POINTSTEP};
+        cudaEvent_t prev = a.ev[LFBA_NUM_KERNEL_TIMERS];
+        for (int k : order) {
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, prev, a.ev[k]);
+          kms[k] += ms;
+          kcalls[k] += 1;
+          prev = a.ev[k];
+        }
+        if (h_done[slot]) {
+          ++rounds;
+          break;
+        }
       } else if (rounds >= 1) {
         LFBA_CUDA(cudaEventSynchronize(ev_round[(rounds - 1) & 3]));
         if (h_done[(rounds - 1) & 3]) {
           ++rounds;
           break;
         }
-        continue;
-      } else {
-        continue;
-      }
-      if (prof) {
-        const int order[] = {LFBA_T_LENS, LFBA_T_EVAL, LFBA_T_CONTROL, LFBA_T_SCHUR, LFBA_T_ALLREDUCE, LFBA_T_DAMP,
-                             LFBA_T_CHOL, LFBA_T_POINTSTEP};
-        cudaEvent_t prev = e_begin;
-        for (int k : order) {
-          float ms = 0.f;
-          cudaEventElapsedTime(&ms, prev, ev[k]);
-          kms[k] += ms;
-          kcalls[k] += 1;
-          prev = ev[k];
-        }
-      }
-      if (debug) {
-        double es[ES_COUNT];
-        LmState hs;
-        LFBA_CUDA(cudaMemcpy(es, d.eval_scalars, sizeof(es), cudaMemcpyDeviceToHost));
-        LFBA_CUDA(cudaMemcpy(&hs, st.p, sizeof(hs), cudaMemcpyDeviceToHost));
-        std::vector<double> hp((size_t)d.grid_pts * 8), hy((size_t)std::max(1, d.n));
-        part_step.download(hp.data(), hp.size(), stream);
-        y.download(hy.data(), (size_t)d.n, stream);
-        LFBA_CUDA(cudaStreamSynchronize(stream));
-        std::fprintf(stderr, "[lfba dbg] round %d: es cost=%.10e mcc=%.10e step2=%.6e norm2=%.6e gd=%.6e bad=%g | st iter=%d cur=%d "
-                     "done=%d skip=%d ok=%d x_cost=%.10e radius=%.4e red: mcc=%.6e step2=%.6e norm2=%.6e | part_step[0]=%.6e %.6e %.6e\n",
-                     rounds, es[0], es[1], es[2], es[3], es[4], es[5], hs.iter, hs.cur, hs.done, hs.eval_skip, hs.solve_ok,
-                     hs.x_cost, hs.radius, hs.mcc_red, hs.step2_red, hs.norm2_red, hp[0], hp[1], hp[2]);
-        double ymax = 0;
-        for (int j = 0; j < d.n; ++j) ymax = std::max(ymax, std::fabs(hy[j]));
-        std::fprintf(stderr, "[lfba dbg]   |y|max=%.6e y[0..5]=%.4e %.4e %.4e %.4e %.4e %.4e\n", ymax, hy[0], hy[1], hy[2],
-                     d.n > 3 ? hy[3] : 0.0, d.n > 4 ? hy[4] : 0.0, d.n > 5 ? hy[5] : 0.0);
-      }
-      if (h_done[slot]) {
-        ++rounds;
-        break;
       }
     }
     LFBA_CUDA(cudaEventRecord(e_run1, stream));
-    LFBA_CUDA(cudaMemcpyAsync(&h_state, st.p, sizeof(LmState), cudaMemcpyDeviceToHost, stream));
+    for (auto& s : sh) LFBA_CUDA(cudaMemcpyAsync(&s->h_state, s->st.p, sizeof(LmState), cudaMemcpyDeviceToHost, s->stream));
     LFBA_CUDA(cudaStreamSynchronize(stream));
+    LFBA_CUDA(cudaGetLastError());
     float run_ms = 0.f;
     cudaEventElapsedTime(&run_ms, e_run0, e_run1);
     cudaEventDestroy(e_run0);
     cudaEventDestroy(e_run1);
-    int status = h_state.status;
-    if (h_state.ls_needed) {
-      set_error("projected line search had to contract the step (recalib): not supported by the device loop yet");
-      status = LFBA_FAILURE;
-    }
-    if (!h_state.done) {  // safety net: the round budget ran out (cannot happen: max_iter is tested on device)
-      h_state.termination = LFBA_NO_CONVERGENCE;
-      h_state.stop_reason = LFBA_STOP_MAX_ITERATIONS;
+    LmState& hs = a.h_state;
+    int status = hs.status;
+    if (!hs.done) {  // safety net: the round budget ran out (cannot happen: max_iter is tested on device)
+      hs.termination = LFBA_NO_CONVERGENCE;
+      hs.stop_reason = LFBA_STOP_MAX_ITERATIONS;
     }
     if (sum) {
       lfba_iteration* rows = sum->iterations;
@@ -594,28 +771,28 @@ struct Solver {
       std::memset(sum, 0, sizeof(*sum));
       sum->iterations = rows;
       sum->iterations_capacity = cap;
-      sum->termination_type = h_state.termination;
-      sum->stop_reason = h_state.stop_reason;
-      sum->num_iterations = h_state.n_rows;
-      sum->num_successful_steps = h_state.n_success;
-      sum->num_unsuccessful_steps = h_state.n_fail;
-      sum->reduced_system_size = d.n;
-      sum->final_cost = h_state.x_cost;
-      sum->num_jacobian_evals = h_state.n_jac_evals;
-      sum->num_observations = n_obs_global;
-      sum->num_tracks = ix.T;
-      sum->num_lenses = ix.NL;
-      sum->gpu_launches = launches - launches0;
-      sum->setup_time_s = setup_time;
+      sum->termination_type = hs.termination;
+      sum->stop_reason = hs.stop_reason;
+      sum->num_iterations = hs.n_rows;
+      sum->num_successful_steps = hs.n_success;
+      sum->num_unsuccessful_steps = hs.n_fail;
+      sum->reduced_system_size = a.d.n;
+      sum->final_cost = hs.x_cost;
+      sum->num_jacobian_evals = hs.n_jac_evals;
+      sum->num_observations = a.n_obs_global;
+      sum->num_tracks = a.ix.T;
+      sum->num_lenses = a.ix.NL;
+      for (size_t r = 0; r < sh.size(); ++r) sum->gpu_launches += sh[r]->launches - launches0[r];
+      sum->setup_time_s = a.setup_time;
       sum->solve_time_s = now_s() - t0;
       sum->solve_gpu_ms = run_ms;
       for (int k = 0; k < LFBA_NUM_KERNEL_TIMERS; ++k) {
         sum->kernel_ms[k] = kms[k];
         sum->kernel_calls[k] = kcalls[k];
       }
-      const int nrows = std::min(h_state.n_rows, kMaxLog);
+      const int nrows = std::min(hs.n_rows, kMaxLog);
       std::vector<lfba_iteration> hl((size_t)std::max(1, nrows));
-      if (nrows > 0) log.download(hl.data(), nrows, stream);
+      if (nrows > 0) a.log.download(hl.data(), nrows, stream);
       LFBA_CUDA(cudaStreamSynchronize(stream));
       if (nrows > 0) sum->initial_cost = hl[0].cost;
       if (rows)
@@ -637,7 +814,7 @@ struct Solver {
 using namespace lfba;
 
 struct lfba_solver {
-  Solver s;
+  Group g;
 };
 
 template <class F>
@@ -687,6 +864,7 @@ void lfba_options_init(lfba_options* o) {
   o->device = -1;
   o->num_gpus = 1;
   o->profile = 0;
+  o->emulate_shards = 0;
 }
 int lfba_device_count(void) {
   int n = 0;
@@ -737,7 +915,7 @@ int lfba_solver_create(const lfba_problem* pb, const lfba_options* opt, const lf
   *out = nullptr;
   lfba_solver* h = new lfba_solver();
   const int rc = guarded([&] {
-    h->s.create(*pb, *opt, comm);
+    h->g.create(*pb, *opt, comm);
     return (int)LFBA_OK;
   });
   if (rc != LFBA_OK) {
@@ -750,27 +928,27 @@ int lfba_solver_create(const lfba_problem* pb, const lfba_options* opt, const lf
 int lfba_solver_set_parameters(lfba_solver* h, const double* c, const double* v, const double* p) {
   if (!h || !c || !v || !p) return LFBA_INVALID_ARGUMENT;
   return guarded([&] {
-    h->s.set_parameters(c, v, p);
+    h->g.set_parameters(c, v, p);
     return (int)LFBA_OK;
   });
 }
 int lfba_solver_get_parameters(lfba_solver* h, double* c, double* v, double* p) {
   if (!h) return LFBA_INVALID_ARGUMENT;
   return guarded([&] {
-    h->s.get_parameters(h->s.h_state.cur, c, v, p);
+    h->g.get_parameters(c, v, p);
     return (int)LFBA_OK;
   });
 }
 int lfba_solver_run(lfba_solver* h, lfba_summary* sum) {
   if (!h) return LFBA_INVALID_ARGUMENT;
-  return guarded([&] { return h->s.run(sum); });
+  return guarded([&] { return h->g.run(sum); });
 }
 void lfba_solver_destroy(lfba_solver* h) { delete h; }
 
 int lfba_solver_time_eval(lfba_solver* h, int reps, int materialize, double* mean_ms) {
   if (!h || reps <= 0 || !mean_ms) return LFBA_INVALID_ARGUMENT;
   return guarded([&] {
-    Solver& s = h->s;
+    Solver& s = h->g.s0();
     LFBA_CUDA(cudaSetDevice(s.device));
     alloc_stream() = s.stream;
     // evaluate at the accepted parameters: present them as the candidate of a fresh state
@@ -804,12 +982,39 @@ int lfba_solver_time_eval(lfba_solver* h, int reps, int materialize, double* mea
     }
     LFBA_CUDA(cudaEventRecord(e1, s.stream));
     LFBA_CUDA(cudaEventSynchronize(e1));
+    LFBA_CUDA(cudaGetLastError());
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     s.launches += reps + 2;
     *mean_ms = ms / reps;
+    return (int)LFBA_OK;
+  });
+}
+
+int lfba_solver_track_blocks(lfba_solver* h, int64_t* n_tracks, int32_t* rec_stride_out, double* rec, double* camsum64,
+                             int32_t* trk_point, int32_t* trk_frame) {
+  if (!h) return LFBA_INVALID_ARGUMENT;
+  return guarded([&] {
+    if (h->g.emulated()) throw CudaError("lfba_solver_track_blocks: single-shard sessions only", LFBA_INVALID_ARGUMENT);
+    Solver& s = h->g.s0();
+    LFBA_CUDA(cudaSetDevice(s.device));
+    const int RS = rec_stride(s.d.NC);
+    if (n_tracks) *n_tracks = s.ix.T;
+    if (rec_stride_out) *rec_stride_out = RS;
+    if (!rec && !camsum64 && !trk_point && !trk_frame) return (int)LFBA_OK;
+    s.begin_run();  // fresh state: the caller's parameters are the candidate (buffer 1)
+    launch_tables(s.d, s.stream);
+    launch_eval(s.d, s.lanes, s.stream);
+    launch_reduce_eval(s.d, s.stream);
+    s.launches += 3;
+    if (rec) s.rec[1].download(rec, (size_t)s.ix.T * RS, s.stream);
+    if (camsum64) s.camsum[1].download(camsum64, 64, s.stream);
+    if (trk_point) s.ix.trk_point.download(trk_point, s.ix.T, s.stream);
+    if (trk_frame) s.ix.trk_frame.download(trk_frame, s.ix.T, s.stream);
+    LFBA_CUDA(cudaStreamSynchronize(s.stream));
+    LFBA_CUDA(cudaGetLastError());
     return (int)LFBA_OK;
   });
 }
@@ -831,10 +1036,13 @@ int lfba_eval(const lfba_problem* pb, const lfba_options* opt_in, const double* 
   if (!pb || !cam || !views || !points) return LFBA_INVALID_ARGUMENT;
   lfba_options o;
   if (opt_in) o = *opt_in; else lfba_options_init(&o);
+  o.emulate_shards = 0;
   return guarded([&] {
-    Solver s;
-    s.create(*pb, o, nullptr);
-    s.set_parameters(cam, views, points);
+    Group g;
+    g.create(*pb, o, nullptr);
+    g.set_parameters(cam, views, points);
+    Solver& s = g.s0();
+    alloc_stream() = s.stream;
     const int64_t N = s.ix.N;
     DevBuf<double> res((size_t)2 * N), jc, jv, jp, st(8);
     if (jac_camera) jc.alloc((size_t)34 * N);
@@ -845,6 +1053,7 @@ int lfba_eval(const lfba_problem* pb, const lfba_options* opt_in, const double* 
     EvalOut out{res.p, jc.p, jv.p, jp.p, st.p, inlier_threshold * inlier_threshold};
     launch_tables_for(s.d, 0, s.stream);
     launch_eval_only(s.d, in, out, 0, s.stream);
+    LFBA_CUDA(cudaGetLastError());
     if (residuals) res.download(residuals, (size_t)2 * N, s.stream);
     if (jac_camera) jc.download(jac_camera, (size_t)34 * N, s.stream);
     if (jac_view) jv.download(jac_view, (size_t)12 * N, s.stream);
@@ -873,8 +1082,7 @@ int lfba_eval(const lfba_problem* pb, const lfba_options* opt_in, const double* 
   });
 }
 
-// Single-process entry: one GPU, or `num_gpus` GPUs with one host thread per GPU (points are split into
-// contiguous ranges balanced by observation count; every observation of a point goes to the point's owner).
+// Single-process entry: one GPU, `emulate_shards` shards on one GPU, or `num_gpus` GPUs with one host thread per GPU.
 int lfba_solve(const lfba_problem* pb, const lfba_options* opt_in, double* cam, double* views, double* points,
                lfba_summary* sum) {
   if (!pb || !cam || !views || !points) return LFBA_INVALID_ARGUMENT;
@@ -883,88 +1091,139 @@ int lfba_solve(const lfba_problem* pb, const lfba_options* opt_in, double* cam, 
   const int G = std::max(1, o.num_gpus);
   if (G == 1) {
     return guarded([&] {
-      Solver s;
-      s.create(*pb, o, nullptr);
-      s.set_parameters(cam, views, points);
-      const int rc = s.run(sum);
-      if (rc == LFBA_OK || s.h_state.n_rows > 0) s.get_parameters(s.h_state.cur, cam, views, points);
+      Group g;
+      g.create(*pb, o, nullptr);
+      g.set_parameters(cam, views, points);
+      const int rc = g.run(sum);
+      if (rc == LFBA_OK || g.s0().h_state.n_rows > 0) g.get_parameters(cam, views, points);
       return rc;
     });
   }
-  // ---- multi-GPU in one process ----
+  // ---- multi-GPU in one process: validate and shard first, then one host thread per GPU ----
+  if (o.emulate_shards > 1) {
+    set_error("emulate_shards cannot be combined with num_gpus > 1");
+    return LFBA_INVALID_ARGUMENT;
+  }
   const int avail = lfba_device_count();
   if (avail < G) {
     set_error("num_gpus exceeds the number of usable devices");
     return LFBA_NO_DEVICE;
   }
-  const int P = pb->n_points;
-  const int64_t N = pb->n_obs;
-  std::vector<int64_t> cnt((size_t)P + 1, 0);
-  for (int64_t i = 0; i < N; ++i) cnt[pb->point_idx[i] + 1]++;
-  for (int p = 0; p < P; ++p) cnt[p + 1] += cnt[p];
-  std::vector<int> owner((size_t)P, 0);
-  for (int p = 0; p < P; ++p) owner[p] = (int)std::min<int64_t>(G - 1, (cnt[p] * G) / std::max<int64_t>(1, N));
-  const bool use_c = (pb->config & LFBA_CFG_REFINE_POINTS) && pb->calib_type != LFBA_RECALIBRATION;
-  if (use_c)
-    for (int k = 0; k < pb->n_constraints; ++k) owner[pb->c_p1[k]] = owner[pb->c_p2[k]] = 0;
-  struct Shard {
-    std::vector<double> ox, oy, mx, my;
-    std::vector<int32_t> pi, fi;
-  };
-  std::vector<Shard> sh((size_t)G);
-  for (int64_t i = 0; i < N; ++i) {
-    Shard& s = sh[(size_t)owner[pb->point_idx[i]]];
-    s.ox.push_back(pb->obs_x[i]);
-    s.oy.push_back(pb->obs_y[i]);
-    s.mx.push_back(pb->ml_x[i]);
-    s.my.push_back(pb->ml_y[i]);
-    s.pi.push_back(pb->point_idx[i]);
-    s.fi.push_back(pb->frame_idx[i]);
+  HostShards hs;
+  {
+    const int rc = guarded([&] {
+      hs.split(*pb, G);
+      return (int)LFBA_OK;
+    });
+    if (rc != LFBA_OK) return rc;
   }
+  const int P = pb->n_points;
   lfba_comm base;
   std::memset(&base, 0, sizeof(base));
-  base.handle = nullptr;
   base.nranks = G;
-  int rc0 = lfba_comm_unique_id(base.nccl_unique_id);
+  const int rc0 = lfba_comm_unique_id(base.nccl_unique_id);
   if (rc0 != LFBA_OK) return rc0;
+  Nccl& nccl = Nccl::get();
   std::vector<int> rcs((size_t)G, LFBA_OK);
   std::vector<std::string> errs((size_t)G);
   std::vector<std::vector<double>> pts_out((size_t)G);
+  std::vector<double> c17(17), v6((size_t)6 * pb->n_frames);
+  std::vector<Nccl::comm_t> comms((size_t)G, nullptr);
+  // pre-flight rendezvous: every rank finishes its non-collective set-up (device, memory, index) before ANY rank
+  // enters NCCL; if one fails, nobody does (a rank stuck alone in ncclCommInitRank would never return)
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, preflight_failed = 0;
+  std::atomic<int> late_failure{0};
   std::vector<std::thread> th;
   for (int r = 0; r < G; ++r)
     th.emplace_back([&, r] {
+      bool past_rendezvous = false;
       rcs[r] = guarded([&] {
-        lfba_problem lp = *pb;
-        lp.n_obs = (int64_t)sh[r].ox.size();
-        lp.obs_x = sh[r].ox.data();
-        lp.obs_y = sh[r].oy.data();
-        lp.ml_x = sh[r].mx.data();
-        lp.ml_y = sh[r].my.data();
-        lp.point_idx = sh[r].pi.data();
-        lp.frame_idx = sh[r].fi.data();
+        const lfba_problem lp = hs.view(*pb, r);
         lfba_options lo = o;
         lo.device = r;
-        lfba_comm c = base;
-        c.rank = r;
-        Solver s;
-        s.create(lp, lo, &c);
-        s.set_parameters(cam, views, points);
+        lo.emulate_shards = 0;
+        Group g;
+        g.opt = lo;
+        g.rank = r;
+        g.nranks = G;
+        g.comm_aborted = &late_failure;
+        g.sh.emplace_back(new Solver());
+        int pre_rc = LFBA_OK;
+        std::string pre_err;
+        try {
+          g.sh[0]->create_local(lp, lo, r, G, nullptr);
+        } catch (const CudaError& e) {
+          pre_rc = e.code;
+          pre_err = e.what();
+        } catch (const std::exception& e) {
+          pre_rc = LFBA_CUDA_ERROR;
+          pre_err = e.what();
+        }
+        bool any_failed;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          if (pre_rc != LFBA_OK) ++preflight_failed;
+          ++arrived;
+          cv.notify_all();
+          cv.wait(lk, [&] { return arrived == G; });
+          any_failed = preflight_failed > 0;
+        }
+        past_rendezvous = true;
+        if (pre_rc != LFBA_OK) throw CudaError(pre_err, pre_rc);
+        if (any_failed) throw CudaError("another rank failed during set-up", LFBA_FAILURE);
+        Nccl::UniqueId id;
+        std::memcpy(id.internal, base.nccl_unique_id, 128);
+        const int nrc = nccl.CommInitRank(&g.comm, G, id, r);
+        if (nrc != 0) throw CudaError(std::string("ncclCommInitRank: ") + nccl.GetErrorString(nrc), LFBA_NCCL_ERROR);
+        g.own_comm = true;
+        comms[r] = g.comm;
+        // the rest of Group::create for an already-indexed shard
+        Solver& s = g.s0();
+        const int F = s.ix.F;
+        std::vector<int32_t> fa = s.h_fa;
+        {
+          alloc_stream() = s.stream;
+          DevBuf<int32_t> dfa((size_t)F + 1);
+          DevBuf<double> dn(1);
+          double h_n = (double)s.ix.N;
+          dfa.upload(fa.data(), (size_t)F + 1, s.stream);
+          dn.upload(&h_n, 1, s.stream);
+          g.nccl_allreduce(dfa.p, (size_t)F + 1, kNcclInt32, kNcclMax);
+          g.nccl_allreduce(dn.p, 1, kNcclFloat64, kNcclSum);
+          dfa.download(fa.data(), (size_t)F + 1, s.stream);
+          dn.download(&h_n, 1, s.stream);
+          LFBA_CUDA(cudaStreamSynchronize(s.stream));
+          s.create_finish(fa, (int64_t)(h_n + 0.5));
+        }
+        LFBA_CUDA(cudaMallocHost(&g.h_done, 4 * sizeof(int)));
+        for (auto& e : g.ev_round) LFBA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g.ev_made = true;
+        g.set_parameters(cam, views, points);
         lfba_summary local;
         std::memset(&local, 0, sizeof(local));
         lfba_summary* ps = (r == 0) ? sum : &local;
-        const int rc = s.run(ps);
+        const int rc = g.run(ps);
         pts_out[r].resize((size_t)3 * P);
-        if (r == 0) {
-          std::vector<double> c17(17), v6((size_t)6 * pb->n_frames);
-          s.get_parameters(s.h_state.cur, c17.data(), v6.data(), pts_out[r].data());
-          std::memcpy(cam, c17.data(), 17 * sizeof(double));
-          std::memcpy(views, v6.data(), v6.size() * sizeof(double));
-        } else {
-          s.get_parameters(s.h_state.cur, nullptr, nullptr, pts_out[r].data());
-        }
+        if (r == 0) g.get_parameters(c17.data(), v6.data(), pts_out[r].data());
+        else g.get_parameters(nullptr, nullptr, pts_out[r].data());
+        comms[r] = nullptr;
         return rc;
       });
       errs[r] = g_last_error;
+      if (rcs[r] != LFBA_OK) {
+        if (!past_rendezvous) {  // failed before the rendezvous (e.g. while sharding views): still let the others pass it
+          std::unique_lock<std::mutex> lk(mu);
+          ++preflight_failed;
+          ++arrived;
+          cv.notify_all();
+        } else if (late_failure.exchange(1) == 0 && nccl.CommAbort) {
+          // a rank died after NCCL was up: abort the peers' communicators so that they do not wait in a collective forever
+          for (int q = 0; q < G; ++q)
+            if (q != r && comms[q]) nccl.CommAbort(comms[q]);
+        }
+      }
     });
   for (auto& t : th) t.join();
   for (int r = 0; r < G; ++r)
@@ -972,8 +1231,11 @@ int lfba_solve(const lfba_problem* pb, const lfba_options* opt_in, double* cam, 
       set_error("rank " + std::to_string(r) + ": " + errs[r]);
       return rcs[r];
     }
+  // all ranks succeeded: only now touch the caller's arrays
+  std::memcpy(cam, c17.data(), 17 * sizeof(double));
+  std::memcpy(views, v6.data(), v6.size() * sizeof(double));
   for (int p = 0; p < P; ++p)
-    for (int j = 0; j < 3; ++j) points[3 * (size_t)p + j] = pts_out[(size_t)owner[p]][3 * (size_t)p + j];
+    for (int j = 0; j < 3; ++j) points[3 * (size_t)p + j] = pts_out[(size_t)hs.owner[p]][3 * (size_t)p + j];
   return LFBA_OK;
 }
 
