@@ -129,6 +129,7 @@ struct Dev {
   int rank, nranks;
   uint32_t config;
   int recalib, refine_poses, refine_points;
+  int debug;                // LFBA_DEBUG set: the control kernel prints its line-search decisions
   double spx, spy, scale;
   Options opt;
   // observations (sorted by point, frame)

@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <cstdlib>
 #include <float.h>
+#include <cstdio>
 
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(1024) k_reduce_eval(Dev d) {
       }
     }
     es[ES_LSGD] = lsgd;
-    es[6] = es[7] = 0.0;
+    es[7] = 0.0;
     for (int r = 0; r < d.nranks; ++r) es[ES_COUNT + r] = r == d.rank ? fmax(shs[5], own * st->dmax_red) : 0.0;
   }
 }
@@ -357,6 +358,9 @@ __global__ void k_control_accept(Dev d) {
         st->ls_prev_valid = st->ls_prev_gvalid = 0;
       }
       const bool armijo = cur.value_valid && cur.value <= st->ls_phi0 + 1e-4 * st->ls_dphi0 * cur.x;
+      if (d.debug)
+        printf("[lfba dbg] iter %d line search: a=%.17g phi=%.17g dphi=%.17g | phi0=%.17g dphi0=%.17g armijo=%d trials=%d\n",
+               st->iter, cur.x, cur.value, cur.gradient, st->ls_phi0, st->ls_dphi0, (int)armijo, st->ls_iters);
       if (!armijo) {
         bool fail = ++st->ls_iters >= 20;
         double a_new = 1.0;

@@ -384,6 +384,7 @@ struct Solver {
     d.N = ix.N; d.T = T; d.P = P; d.F = F; d.NL = ix.NL; d.K = K; d.NC = NC;
     d.rank = rank; d.nranks = nranks; d.config = config; d.recalib = recalib ? 1 : 0;
     d.refine_poses = rposes ? 1 : 0; d.refine_points = rpoints ? 1 : 0;
+    d.debug = std::getenv("LFBA_DEBUG") != nullptr ? 1 : 0;
     d.spx = spx; d.spy = spy; d.scale = scale;
     d.opt.max_iter = o.max_num_iterations; d.opt.ftol = o.function_tolerance; d.opt.ptol = o.parameter_tolerance;
     d.opt.gtol = o.gradient_tolerance; d.opt.r0 = o.initial_trust_region_radius; d.opt.rmax = o.max_trust_region_radius;

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -1496,6 +1497,10 @@ static int oracle_solve_impl(const lfba_problem* pb, const lfba_options* opt, do
       int ls_iters = 0;
       bool success = true;
       eval_at(1.0, current);
+      const bool ls_debug = std::getenv("LFBA_DEBUG") != nullptr;
+      if (ls_debug)
+        std::printf("[oracle dbg] iter %d line search: a=%.17g phi=%.17g dphi=%.17g | phi0=%.17g dphi0=%.17g\n", iteration,
+                    current.x, current.value, current.gradient, initial.value, initial.gradient);
       while (!current.value_valid || current.value > initial.value + 1e-4 * initial.gradient * current.x) {
         if (++ls_iters >= 20) {
           success = false;
@@ -1515,6 +1520,9 @@ static int oracle_solve_impl(const lfba_problem* pb, const lfba_options* opt, do
         }
         previous = current;
         eval_at(a_new, current);
+        if (ls_debug)
+          std::printf("[oracle dbg] iter %d line search: a=%.17g phi=%.17g dphi=%.17g\n", iteration, current.x, current.value,
+                      current.gradient);
       }
       it.line_search_iterations = ls_iters;
       if (success)

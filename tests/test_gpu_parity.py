@@ -338,7 +338,7 @@ def test_fused_kernel_track_blocks_match_oracle_block_products(gpu, cfg_extra):
 def test_recalib_projected_line_search_contracts_like_the_oracle(gpu, case):
     """recalib: bounds put Ceres on its constrained path (src/CameraCalibration.cpp:927-953). Scenes whose
     bL0 upper bound (1.3 x initial value) sits just below the true value: the full LM step violates the Armijo test and the
-    projected line search contracts it (alpha < 1), 1..12 trials per iteration. Row-for-row parity with the oracle."""
+    projected line search contracts it (alpha < 1), several trials per iteration. Row-for-row parity with the oracle."""
     rel = 2e-4 if case == "start_on_bound" else 0.02
     sc = capi.make_scene(None, n_points=150, n_frames=6, seed=13, calib_type=capi.RECALIBRATION,
                          init_intrinsics_rel=rel, init_center_px=1.0 if case == "start_on_bound" else 10.0)
@@ -349,7 +349,7 @@ def test_recalib_projected_line_search_contracts_like_the_oracle(gpu, case):
     spread, (ocam, ovw, opt_, os_) = _oracle_spread(sc.problem, init)
     ls_o = [r["line_search_iterations"] for r in os_["iterations"]]
     ls_g = [r["line_search_iterations"] for r in s["iterations"]]
-    assert max(ls_o) >= (1 if case == "start_on_bound" else 5), ls_o  # the scene does exercise the contraction
+    assert max(ls_o) >= 2 and sum(1 for v in ls_o if v > 0) >= 2, ls_o  # the scene does exercise the contraction
     assert ls_g == ls_o, (ls_g, ls_o)
     _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread, name=f"recalib_ls:{case}")
     assert cam[0] == cam0[0] and cam[2] == cam0[2]
