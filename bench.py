@@ -35,7 +35,9 @@ if ROOT not in sys.path:
 # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the ncu --set full
 # capture of the same build (profiles/README.md); None where no capture exists for that workload
 NCU_TRAFFIC = {"cfg4": 4.397e9}  # 3.262 GB read + 1.135 GB written per launch (profiles/r01_ncu_k_eval_rows_cfg4.txt)
+NCU_TRAFFIC_EVAL_ONLY = {"cfg4": 5.1557e10}  # 3.17 GB read + 48.39 GB written (profiles/r01_ncu_k_eval_only_cfg4.txt)
 FP64_INST_PER_OBS = 262.4  # ncu source counters of k_eval_rows<9,2,1> (profiles/README.md): loop + per-track part / N
+REC_STRIDE_NC9 = 36        # doubles per track record at NC = 9 (lfba_device.cuh rec_stride)
 METRIC = "lm_residual_jacobian_evals_per_s"
 UNIT = "M evals/s"
 WORKLOADS = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4}
@@ -148,54 +150,64 @@ def pinned_problem(pa):
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU baseline (oracle) on a bounded sample of the workload
+# CPU baseline: the Ceres-2.1.0-equivalent oracle on the SAME scene (same seed, every observation)
 # ---------------------------------------------------------------------------------------------------
-def cpu_sample_spec(workload: str, small: bool):
-    """A bounded sample of the workload with the same structure (window, flags, observations per view)."""
-    from lifcal_b200 import capi
-    preset = WORKLOADS[workload]
-    if workload == "cfg4":
-        n_points, n_frames = (6000, 12) if small else (20000, 24)
-        return capi.scene_spec(preset, n_points=n_points, n_frames=n_frames, order=1), \
-            f"{n_points} points x {n_frames} frames of cfg4 (window 4, same flags)"
-    if workload == "cfg3":
-        n_points, n_frames = (2000, 40) if small else (5000, 60)
-        return capi.scene_spec(preset, n_points=n_points, n_frames=n_frames), \
-            f"{n_points} points x {n_frames} frames of cfg3 (window 20, same flags)"
-    if workload == "cfg2":
-        n_points = 1000 if small else 5000
-        return capi.scene_spec(preset, n_points=n_points), f"{n_points} points x 20 frames of cfg2"
-    return capi.scene_spec(preset), "the full cfg1 scene"
+def _mem_available_gb() -> float:
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
 
 
-def run_cpu_baseline(workload: str, small: bool, steps: int = 1, warmup: int = 0):
-    from lifcal_b200 import capi
+def host_threads() -> int:
+    """All host cores this process may use — torchrun exports OMP_NUM_THREADS=1, which would silently make the CPU arm
+    single-threaded at N > 1 (the reference uses hardware_concurrency(), src/CameraCalibration.cpp:961)."""
     from oracle import binding as ob
-    spec, desc = cpu_sample_spec(workload, small)
-    sc = capi.Scene(spec)
-    # all host cores this process may use — torchrun exports OMP_NUM_THREADS=1, which would silently make the reference
-    # arm single-threaded at N > 1
     try:
         ncores = len(os.sched_getaffinity(0))
     except AttributeError:
         ncores = os.cpu_count() or 1
-    threads = max(ob.max_threads(), ncores)
-    times, evals, iters = [], 0, 0
-    for k in range(warmup + steps):
+    return max(ob.max_threads(), ncores)
+
+
+def run_cpu_baseline(workload: str, lm_iterations: int | None, scene=None, repeats: int = 1, warmup: int = 0):
+    """Times the oracle on the benchmarked scene itself. cfg1-cfg3: the complete solve. cfg4 (1.12e8 observations, about
+    35 s per Jacobian pass on 16 cores): a solve TRUNCATED after `lm_iterations` LM iterations — every Ceres iteration
+    costs the same (one Jacobian evaluation, one Schur elimination + dense LLT, one cost evaluation), so the
+    evaluations-per-second rate of the truncated solve is the rate of the complete one. Jacobian stored in Ceres' block
+    layout (416 B per observation: 47 GB at cfg4) when the host has the memory, else the block-recompute mode."""
+    from lifcal_b200 import capi
+    from oracle import binding as ob
+    if scene is None:
+        scene = capi.Scene(capi.scene_spec(WORKLOADS[workload], order=1))
+    pa = scene.problem
+    n = pa.n_obs
+    threads = host_threads()
+    need_gb = 416.0 * n / 1e9 + 16.0 * n / 1e9 + 8.0 * threads * (17 + 6 * pa.n_frames) ** 2 / 1e9
+    streaming = _mem_available_gb() < 1.3 * need_gb + 8.0
+    opts = ob.default_options() if lm_iterations is None else ob.default_options(max_num_iterations=int(lm_iterations))
+    dt, evals, rows = 0.0, 0, 0
+    for k in range(warmup + repeats):
         t0 = time.perf_counter()
-        _, _, _, s = ob.solve(sc.problem, sc.camera_init, sc.views_init, sc.points_init, threads=threads)
-        dt = time.perf_counter() - t0
+        _, _, _, s = ob.solve(pa, scene.camera_init, scene.views_init, scene.points_init, options=opts, threads=threads,
+                              streaming=streaming)
         if k >= warmup:
-            times.append(dt)
+            dt += time.perf_counter() - t0
             evals += s["num_jacobian_evals"]
-            iters += s["num_iterations"]
-    total = sum(times)
-    n = sc.problem.n_obs
-    return {"value": n * evals / total / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{desc}: {n} observations, {iters // max(1, steps)} LM iterations/solve, "
-                      f"{total / max(1, steps):.2f} s/solve; oracle = Ceres-2.1.0-equivalent restatement "
-                      f"(Jet<26> autodiff, DENSE_SCHUR, dense LLT), functor pinned bit-exact to the reference headers",
-            "lm_iters_per_s": iters / total, "seconds": total, "n_obs": n, "steps": steps}
+            rows += s["num_iterations"]
+    what = "complete solve" if lm_iterations is None else f"solve truncated after {lm_iterations} LM iteration(s) (rate extrapolates: every iteration costs the same)"
+    return {"value": n * evals / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"the benchmarked scene itself ({workload}, same seed, all {n} observations): {what}; "
+                      f"{repeats} solve(s) timed after {warmup} warm-up: {rows} LM rows, {evals} Jacobian evaluations in {dt:.1f} s; oracle = Ceres-2.1.0-equivalent "
+                      f"restatement (Jet<26> autodiff, DENSE_SCHUR, dense LLT), functor pinned bit-exact to the reference "
+                      f"headers; Jacobian {'recomputed per point block (block_passes=%d)' % s['block_passes'] if streaming else 'stored in Ceres block layout'}",
+            "lm_iters_per_s": max(0, rows - repeats) / dt, "seconds": dt, "n_obs": n, "lm_rows": rows, "repeats": repeats,
+            "warmup": warmup,
+            "jacobian_evals": evals, "same_scene": True, "oracle_mode": "streaming" if streaming else "stored",
+            "final_cost": s["final_cost"]}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -207,6 +219,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("LFBA_BENCH_WORKLOAD", "cfg4"), choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iterations", type=int, default=3,
+                    help="cfg4 only: LM iterations of the CPU solve that --impl reference times (the scene is the full one)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
@@ -216,18 +230,24 @@ def main():
     config = {"workload": f"{args.workload}: {WORKLOAD_DESC[args.workload]}", "flags": "nRadial=2,tangential,robust(Cauchy 0.5),"
               "refinePoses,refinePoints,mlAdj", "l2": "inputs larger than L2 (no flush needed)"}
 
-    # ------------------------------------------------------------------ reference arm: CPU oracle
+    # ------------------------------------------------------------------ reference arm: CPU oracle on the same scene
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = run_cpu_baseline(args.workload, small=True, steps=max(1, args.steps), warmup=min(1, args.warmup))
+        small = args.workload in ("cfg1", "cfg2")
+        iters = None if args.workload != "cfg4" else args.cpu_iterations
+        reps, wu = (max(1, min(args.steps, 3)), min(1, args.warmup)) if small else (1, 0)
+        cb = run_cpu_baseline(args.workload, iters, repeats=reps, warmup=wu)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": min(1, args.warmup), "ms_per_step": 1e3 * cb["seconds"] / max(1, args.steps),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(config, sample=cb["sample"]), "lm_iters_per_s": cb["lm_iters_per_s"],
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "steps": reps, "warmup": wu, "requested_steps": args.steps, "requested_warmup": args.warmup,
+                "steps_note": "a step is one LM solve of the FULL benchmarked scene on the host cores (cfg4: truncated after "
+                              "--cpu-iterations LM iterations; the rate extrapolates); K repetitions of a 1.12e8-observation "
+                              "CPU solve would take hours, so fewer steps than requested are timed",
+                "ms_per_step": 1e3 * cb["seconds"] / reps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "lm_iters_per_s": cb["lm_iters_per_s"],
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_scene", "oracle_mode")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "final_cost": cb["final_cost"], "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -303,37 +323,39 @@ def main():
     # Algorithmic HBM bytes of one launch: 20 B per observation (double2 + int32 of the packed
     # stream) + the per-track record written, (9 + 3 NC) * 8 B = 288 B per (point, frame) track.
     eval_ms = ds.time_eval(reps=10, materialize=False)
-    rec_stride = 9 + 3 * 9
+    rec_stride = REC_STRIDE_NC9
     alg_bytes = 20.0 * n_local + 8.0 * rec_stride * s["num_tracks"]
     peak, peak_src = measured_peaks()
-    roofline = {"bound": "hbm", "kernel": "k_eval_rows (fused residual + analytic Jacobian + Cauchy weighting + per-track Gram "
+    # FP64 peak: MEASURED_PEAKS.json has no FP64 figure, so the DFMA rate is measured here, on this device, in this run
+    # (dependent-chain-free DFMA kernel, lfba_measure_fp64_peak); nominal 148 SMs x 64 lanes x 2 x 1.965 GHz = 37.2 TFLOP/s
+    fp64_peak = api.measure_fp64_peak(local_rank)
+    ach_tf = FP64_INST_PER_OBS * n_local / (eval_ms * 1e-3) * 2.0 / 1e12  # every FP64 instruction counted as one FMA (2 flop)
+    roofline = {"bound": "fp64", "kernel": "k_eval_rows (fused residual + analytic Jacobian + Cauchy weighting + per-track Gram "
                 "-> normal-equation blocks; Jacobian never leaves registers)",
-                "achieved": alg_bytes / (eval_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_bytes / (eval_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.workload),
-                "peak_source": peak_src, "ms_per_launch": eval_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "this kernel is FP64-pipe bound by design (30 B/observation of HBM traffic against 263 FP64 "
-                        "instructions): its fraction of the HBM roof is small on purpose; see fp64 for the pipe "
-                        "utilisation and roofline_eval_only for the HBM-bound kernel that materialises the Jacobian"}
+                "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+                "traffic": NCU_TRAFFIC.get(args.workload),
+                "peak_source": "DFMA rate measured in this run on this device (MEASURED_PEAKS.json has no FP64 entry)",
+                "ms_per_launch": eval_ms, "fp64_inst_per_observation": FP64_INST_PER_OBS,
+                "fp64_inst_source": "ncu smsp__sass_thread_inst_executed_op_fp64 of the same build / observations (profiles/README.md)",
+                "fused_eval_m_evals_per_s": n_local / (eval_ms * 1e-3) / 1e6,
+                "hbm": {"bound": "hbm", "achieved": alg_bytes / (eval_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg_bytes / (eval_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg_bytes,
+                        "note": "secondary: 20 B per observation streamed + one track record written per (point, frame); the "
+                                "kernel is FP64-pipe bound (DESIGN.md section 4)"}}
     extra = {}
     if rank == 0 and world == 1:
         try:
+            # eval-only kernel, Jacobian materialised: SURVEY.md 8(d) algorithmic bytes = 56 + 16 (NC + 6 + 3) = 344 B per
+            # observation at NC = 9 (reads 40 B, writes r 16 B and the 2 x (NC + 6 + 3) LIVE Jacobian columns)
             mat_ms = ds.time_eval(reps=3, materialize=True)
-            mat_bytes = (28.0 + 16.0 + 16.0 * 26.0) * n_local
-            extra["roofline_eval_only"] = {"bound": "hbm", "kernel": "k_eval_only (residual + Jacobian materialised in Ceres' "
-                                           "block layout, 2x(17+6+3) doubles per observation)",
+            mat_bytes = 344.0 * n_local
+            extra["roofline_eval_only"] = {"bound": "hbm", "kernel": "k_eval_only (residual + Jacobian materialised per observation)",
                                            "achieved": mat_bytes / (mat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                            "frac": mat_bytes / (mat_ms * 1e-3) / 1e9 / peak, "ms_per_launch": mat_ms,
-                                           "algorithmic_bytes_per_launch": mat_bytes,
-                                           "traffic": 5.1557e10 if args.workload == "cfg4" else None,  # ncu: 3.17 GB read + 48.39 GB written
+                                           "algorithmic_bytes_per_launch": mat_bytes, "bytes_per_observation": 344,
+                                           "traffic": NCU_TRAFFIC_EVAL_ONLY.get(args.workload),
                                            "m_evals_per_s": n_local / (mat_ms * 1e-3) / 1e6}
-            fp64 = api.measure_fp64_peak(local_rank)
-            # FP64 instructions per observation of the fused kernel, from the ncu source counters of the same build
-            # (profiles/README.md): per-observation loop + the per-track expansion amortised over the track
-            fp64_inst_per_obs = FP64_INST_PER_OBS
-            ach = fp64_inst_per_obs * n_local / (eval_ms * 1e-3) * 2.0 / 1e12  # counted as 2 flop per FP64 instruction
-            extra["fp64"] = {"bound": "fp64", "measured_dfma_peak_tflops": fp64, "fp64_inst_per_observation": fp64_inst_per_obs,
-                             "achieved_tflops_equiv": ach, "frac": ach / fp64,
-                             "fused_eval_m_evals_per_s": n_local / (eval_ms * 1e-3) / 1e6}
         except Exception as e:  # noqa: BLE001
             extra["roofline_eval_only"] = {"error": str(e)}
     ds.close()
@@ -392,8 +414,12 @@ def main():
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e}
     line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = {k: v for k, v in run_cpu_baseline(args.workload, small=False).items()
-                                if k in ("value", "unit", "cores", "kind", "sample", "lm_iters_per_s")}
+        # same scene object the GPU just solved; cfg4: one LM iteration (two Jacobian passes) keeps the default run short
+        small = args.workload in ("cfg1", "cfg2")
+        cb = run_cpu_baseline(args.workload, 1 if args.workload == "cfg4" else None, scene=sc, repeats=2 if small else 1,
+                              warmup=1 if small else 0)
+        line["cpu_baseline"] = {k: v for k, v in cb.items()
+                                if k in ("value", "unit", "cores", "kind", "sample", "lm_iters_per_s", "same_scene", "oracle_mode")}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
