@@ -348,7 +348,7 @@ def main():
         try:
             # eval-only kernel, Jacobian materialised: SURVEY.md 8(d) algorithmic bytes = 56 + 16 (NC + 6 + 3) = 344 B per
             # observation at NC = 9 (reads 40 B, writes r 16 B and the 2 x (NC + 6 + 3) LIVE Jacobian columns)
-            mat_ms = ds.time_eval(reps=3, materialize=True)
+            mat_ms = ds.time_eval(reps=3, materialize=2)  # camera block as its live 2 x NC columns
             mat_bytes = 344.0 * n_local
             extra["roofline_eval_only"] = {"bound": "hbm", "kernel": "k_eval_only (residual + Jacobian materialised per observation)",
                                            "achieved": mat_bytes / (mat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

@@ -246,8 +246,9 @@ int lfba_solver_set_parameters(lfba_solver* s, const double* camera17, const dou
 int lfba_solver_get_parameters(lfba_solver* s, double* camera17, double* views6F, double* points3P);
 /* Runs the LM loop on the device-resident state. */
 int lfba_solver_run(lfba_solver* s, lfba_summary* summary);
-/* Times `reps` launches of the fused evaluation pass (and, if materialize != 0, of the eval-only kernel
- * that writes residuals + Jacobians to HBM) at the current parameters; returns mean ms per launch. */
+/* Times `reps` launches of the fused evaluation pass (materialize = 0) or of the eval-only kernel that writes residuals +
+ * Jacobians to HBM at the current parameters: materialize = 1 in Ceres' block layout (camera block 2 x 17, what lfba_eval
+ * returns), materialize = 2 with the camera block's live columns only (2 x NC). Returns mean ms per launch. */
 int lfba_solver_time_eval(lfba_solver* s, int reps, int materialize, double* mean_ms);
 /* Diagnostics for parity tests: one fused evaluation pass (the LM loop's own kernel) at the parameters last given by
  * lfba_solver_set_parameters, and its raw outputs — per (point, frame) track the normal-equation blocks in the CAMERA

@@ -208,8 +208,9 @@ class DeviceSolver:
         return cam, vw, pt
 
     def time_eval(self, reps=10, materialize=False) -> float:
+        """materialize: False/0 fused pass; True/1 eval-only kernel, Ceres layout; 2 eval-only, live camera columns only."""
         ms = C.c_double(0)
-        _check(self._L.lfba_solver_time_eval(self._h, reps, 1 if materialize else 0, C.byref(ms)),
+        _check(self._L.lfba_solver_time_eval(self._h, reps, int(materialize), C.byref(ms)),
                "lfba_solver_time_eval")
         return ms.value
 

@@ -6,8 +6,8 @@
 // (416 B per observation). The LM loop never uses this kernel (its Jacobian stays in registers); it serves
 // lfba_eval(): calcReprojectionError (src/CameraCalibration.cpp:1026-1103), parity tests, and the
 // "M residual+Jacobian evals/s" metric with the Jacobian written to HBM.
-// Algorithmic HBM bytes per observation: read 28 (double2 + 3 x int32), write 16 + 16*(17 + 6 + 3) = 432.
-// HBM-bound: the outputs are staged per CTA in shared memory and streamed out coalesced (see stream_out).
+// Algorithmic HBM bytes per observation: read 28 (double2 + 3 x int32), write 16 + 16 (WC + 6 + 3), WC = 17 (Ceres layout)
+// or NC (live columns). HBM-bound: the outputs are staged per CTA in shared memory and leave through the TMA engine.
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
 
@@ -33,53 +33,42 @@ __global__ void k_tables_for(Dev d, int which) {
   if (i < d.F) frame_entry(d.views[which] + 6 * i, d.frames[which] + (size_t)i * kFrameStride);
 }
 
-// Output staging: every thread produces 54 doubles (r 2, J_camera 34, J_view 12, J_point 6) for ITS observation, i.e.
-// at a 272 / 96 / 48 / 16-byte stride in HBM. Written directly that is one 32-byte sector per 8-byte store (measured:
-// 25% of the HBM roofline). The CTA therefore stages its 128 observations in shared memory (row stride padded to an
-// odd number of doubles: conflict-free for the strided writes AND for the linear read-back) and then streams each
-// output array out with fully coalesced 8-byte stores: the 128 rows of a CTA are one contiguous range of each array.
+// Output staging: every thread produces 2 + 2 WC + 12 + 6 doubles (r, J_camera, J_view, J_point) for ITS observation, i.e.
+// at a 16 / 16 WC / 96 / 48-byte stride in HBM. Written directly that is one 32-byte sector per 8-byte store (measured: 25% of
+// the HBM roofline). The CTA therefore stages its 128 observations in shared memory in EXACTLY the layout of the output
+// arrays (unpadded: the 128 rows of a CTA are one contiguous range of each array) and one thread hands the four tiles to
+// the TMA engine: cp.async.bulk.global.shared::cta (SASS UBLKCP) streams each tile out at full line granularity while the
+// SM's load/store pipe is already free for the next CTA. (The predecessor read the staging area back with 8-byte LDS/STG
+// pairs: 7.4 G warp instructions and 243 M bank conflicts per launch at the 1M x 1000 scene, L1TEX wavefront pipe 57%.)
+// WC = 17 (Ceres' block layout, 8 of 17 columns structurally zero: lfba_eval) or NC (live columns only: the layout SURVEY.md
+// 8(d) counts, 344 B per observation at NC = 9).
 constexpr int kEvalBlock = 128;
-constexpr int kStrideV = 13, kStrideP = 7, kStrideR = 3;  // padded rows of 12 / 6 / 2 doubles
-// the camera block is staged without its 17 - NC structurally zero columns (they are written as zeros on the way out):
-// 2 NC doubles per observation, padded to an odd stride; at least 17 so that a warp's 32 rows hold its 4 KB lens scratch
-template <int NC>
-constexpr int stride_c() { return 2 * NC + 1 < 17 ? 17 : 2 * NC + 1; }
-template <int NC>
-constexpr int eval_smem_doubles() { return kEvalBlock * (stride_c<NC>() + kStrideV + kStrideP + kStrideR); }
-
-template <int W, int STRIDE>
-__device__ __forceinline__ void stream_out(const double* __restrict__ sm, double* __restrict__ dst, int rows) {
-  // dst[row * W + c] = sm[row * STRIDE + c] for the CTA's `rows` observations; consecutive threads -> consecutive doubles:
-  // conflict-free 8-byte shared-memory reads (the rows are padded by one double) and 256 contiguous bytes per warp store.
-  // (16-byte stores were measured no faster: the odd row stride makes their shared-memory side 2-way conflicted.)
-  const int total = rows * W;
-  for (int j = threadIdx.x; j < total; j += kEvalBlock) {
-    const int row = j / W, c = j - row * W;
-    __stcs(dst + j, sm[row * STRIDE + c]);  // streaming store: written once, never re-read by this kernel
-  }
+template <int NC, bool COMPACT>
+constexpr int cam_width() { return COMPACT ? NC : 17; }
+template <int NC, bool COMPACT>
+constexpr int eval_smem_doubles() {
+  // camera tile first; it also hosts the lens-gather scratch (32 entries x 16 doubles per warp = 4 x 512 doubles)
+  return kEvalBlock * (2 * cam_width<NC, COMPACT>() + 12 + 6 + 2) < 4 * 512 + kEvalBlock * 20
+             ? 4 * 512 + kEvalBlock * 20
+             : kEvalBlock * (2 * cam_width<NC, COMPACT>() + 12 + 6 + 2);
 }
 
-// camera block: Ceres' 2 x 17 row-major layout from the staged 2 x NC live columns
-template <int NC, int STRIDE>
-__device__ __forceinline__ void stream_out_camera(const double* __restrict__ sm, double* __restrict__ dst, int rows) {
-  const int total = rows * 34;
-  for (int j = threadIdx.x; j < total; j += kEvalBlock) {
-    const int row = j / 34, c = j - row * 34;
-    const int rr = c >= 17 ? 1 : 0, cc = c - 17 * rr;
-    __stcs(dst + j, cc < NC ? sm[row * STRIDE + rr * NC + cc] : 0.0);
-  }
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
 }
 
-template <int NC, int NRAD>
+template <int NC, int NRAD, bool COMPACT>
 __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, EvalOut out, int which) {
   __shared__ CamModel cm;
   __shared__ double sred[4 * 6];
-  extern __shared__ double stage[];
-  double* sC = stage;
-  constexpr int kStrideC = stride_c<NC>();
-  double* sV = sC + kEvalBlock * kStrideC;
-  double* sP = sV + kEvalBlock * kStrideV;
-  double* sR = sP + kEvalBlock * kStrideP;
+  extern __shared__ __align__(128) double stage[];
+  constexpr int WC = cam_width<NC, COMPACT>();
+  double* sC = stage;                       // [128][2 WC]
+  double* sV = sC + kEvalBlock * 2 * WC;    // [128][12]
+  double* sP = sV + kEvalBlock * 12;        // [128][6]
+  double* sR = sP + kEvalBlock * 6;         // [128][2]
   if (threadIdx.x == 0) cam_model_init(cm, d.camera[which], d.config, d.spx, d.spy, d.scale, d.opt.loss_a);
   __syncthreads();
   const int64_t i0 = blockIdx.x * (int64_t)kEvalBlock;
@@ -87,13 +76,13 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
   double ex2 = 0.0, ey2 = 0.0, mx = 0.0, my = 0.0, inl = 0.0, cost = 0.0;
   // Cooperative gather of the 128-byte lens-table entries of the warp's 32 observations: 8 consecutive lanes fetch the
   // 8 consecutive 16-byte chunks of ONE entry (4 lines per warp instruction instead of 32), the chunks are transposed
-  // to their owner through an XOR-swizzled shared-memory scratch (conflict-free both ways). The scratch lives in the
-  // warp's own part of the output staging area, which it only fills afterwards.
+  // to their owner through an XOR-swizzled shared-memory scratch (conflict-free both ways). The scratch lives at the
+  // start of the staging area, which is only filled afterwards (behind a CTA barrier).
   double ecoop[kLensStride];
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lid = i < d.N ? __ldcs(in.lens_id + i) : -1;
-    double2* scratch = reinterpret_cast<double2*>(sC + warp * 32 * kStrideC);  // 32 entries x 8 chunks
+    double2* scratch = reinterpret_cast<double2*>(stage + warp * 512);  // 32 entries x 8 chunks
     const double2* lens2 = reinterpret_cast<const double2*>(d.lens);
     const int chunk = lane & 7, lane8 = lane & ~7;
 #pragma unroll
@@ -109,8 +98,8 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
       ecoop[2 * c] = v2.x;
       ecoop[2 * c + 1] = v2.y;
     }
-    __syncwarp();
   }
+  __syncthreads();  // every warp is done with its scratch: the staging tiles may overwrite it
   if (i < d.N) {
     const double2 o = __ldcs(in.obs + i);
     const int p = __ldcs(in.point_idx + i), f = __ldcs(in.frame_idx + i);
@@ -125,15 +114,19 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
     track_setup(cm, Pc, tc);
     double r[2], G[6], J[2 * NC];
     obs_eval<NC, NRAD>(cm, tc, e, o.x, o.y, r, G, J);
-    sR[threadIdx.x * kStrideR] = r[0];
-    sR[threadIdx.x * kStrideR + 1] = r[1];
+    *reinterpret_cast<double2*>(sR + threadIdx.x * 2) = make_double2(r[0], r[1]);
     if (out.jac_camera) {
-      double* jc = sC + threadIdx.x * kStrideC;
+      double2* jc = reinterpret_cast<double2*>(sC + threadIdx.x * 2 * WC);  // rows of 2 WC doubles: 16-byte aligned
+      double row2[2 * WC];
 #pragma unroll
-      for (int k = 0; k < 2 * NC; ++k) jc[k] = J[k];
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int c = 0; c < WC; ++c) row2[rr * WC + c] = c < NC ? J[rr * NC + c] : 0.0;
+#pragma unroll
+      for (int k = 0; k < WC; ++k) jc[k] = make_double2(row2[2 * k], row2[2 * k + 1]);
     }
     if (out.jac_view) {
-      double* jv = sV + threadIdx.x * kStrideV;
+      double jv[12];
       double m[9];
       mat3_vec(fe + 9, X, m + 0);
       mat3_vec(fe + 18, X, m + 3);
@@ -146,15 +139,21 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
               d.refine_poses ? G[3 * row] * m[3 * k] + G[3 * row + 1] * m[3 * k + 1] + G[3 * row + 2] * m[3 * k + 2] : 0.0;
           jv[6 * row + 3 + k] = d.refine_poses ? G[3 * row + k] : 0.0;
         }
+      double2* dst = reinterpret_cast<double2*>(sV + threadIdx.x * 12);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dst[k] = make_double2(jv[2 * k], jv[2 * k + 1]);
     }
     if (out.jac_point) {
-      double* jp = sP + threadIdx.x * kStrideP;
+      double jp[6];
 #pragma unroll
       for (int row = 0; row < 2; ++row)
 #pragma unroll
         for (int k = 0; k < 3; ++k)
           jp[3 * row + k] =
               d.refine_points ? G[3 * row] * fe[k] + G[3 * row + 1] * fe[3 + k] + G[3 * row + 2] * fe[6 + k] : 0.0;
+      double2* dst = reinterpret_cast<double2*>(sP + threadIdx.x * 6);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dst[k] = make_double2(jp[2 * k], jp[2 * k + 1]);
     }
     const double s = r[0] * r[0] + r[1] * r[1];
     double rho;
@@ -179,12 +178,17 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
     }
     if (lane == 0) sred[warp * 6 + v] = x;
   }
-  __syncthreads();  // also orders the staging writes before the read-back
-  const int rows = (int)(d.N - i0 < (int64_t)kEvalBlock ? d.N - i0 : (int64_t)kEvalBlock);
-  stream_out<2, kStrideR>(sR, out.residuals + 2 * i0, rows);
-  if (out.jac_camera) stream_out_camera<NC, kStrideC>(sC, out.jac_camera + 34 * i0, rows);
-  if (out.jac_view) stream_out<12, kStrideV>(sV, out.jac_view + 12 * i0, rows);
-  if (out.jac_point) stream_out<6, kStrideP>(sP, out.jac_point + 6 * i0, rows);
+  // the staging writes (generic proxy) must be visible to the TMA engine (async proxy) before it reads them
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const unsigned rows = (unsigned)(d.N - i0 < (int64_t)kEvalBlock ? d.N - i0 : (int64_t)kEvalBlock);
+  if (threadIdx.x == 0) {
+    bulk_store(out.residuals + 2 * i0, sR, rows * 2 * 8);
+    if (out.jac_camera) bulk_store(out.jac_camera + (size_t)2 * WC * i0, sC, rows * 2 * WC * 8);
+    if (out.jac_view) bulk_store(out.jac_view + 12 * i0, sV, rows * 12 * 8);
+    if (out.jac_point) bulk_store(out.jac_point + 6 * i0, sP, rows * 6 * 8);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
   if (threadIdx.x < 6 && out.stats) {
     const int v = threadIdx.x;
     double x = sred[v];
@@ -192,16 +196,25 @@ __global__ void __launch_bounds__(kEvalBlock, 4) k_eval_only(Dev d, EvalIn in, E
     if (v == 2 || v == 3) atomic_max_double(out.stats + v, x);
     else atomicAdd(out.stats + v, x);
   }
+  // the CTA's shared memory must stay allocated until the engine has read it
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // per-device opt-in to > 48 KB of dynamic shared memory: call with that device current (Solver::create does)
+template <int NC, int NRAD>
+static void prepare_eval_nc() {
+  cudaFuncSetAttribute(k_eval_only<NC, NRAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       eval_smem_doubles<NC, false>() * (int)sizeof(double));
+  cudaFuncSetAttribute(k_eval_only<NC, NRAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       eval_smem_doubles<NC, true>() * (int)sizeof(double));
+}
 void prepare_eval_only_kernels() {
-  cudaFuncSetAttribute(k_eval_only<5, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<5>() * (int)sizeof(double));
-  cudaFuncSetAttribute(k_eval_only<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
-  cudaFuncSetAttribute(k_eval_only<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<6>() * (int)sizeof(double));
-  cudaFuncSetAttribute(k_eval_only<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<8>() * (int)sizeof(double));
-  cudaFuncSetAttribute(k_eval_only<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<7>() * (int)sizeof(double));
-  cudaFuncSetAttribute(k_eval_only<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, eval_smem_doubles<9>() * (int)sizeof(double));
+  prepare_eval_nc<5, 0>();
+  prepare_eval_nc<7, 0>();
+  prepare_eval_nc<6, 1>();
+  prepare_eval_nc<8, 1>();
+  prepare_eval_nc<7, 2>();
+  prepare_eval_nc<9, 2>();
 }
 
 void launch_tables_for(const Dev& d, int which, cudaStream_t s) {
@@ -209,17 +222,25 @@ void launch_tables_for(const Dev& d, int which, cudaStream_t s) {
   if (n > 0) k_tables_for<<<(n + 127) / 128, 128, 0, s>>>(d, which);
 }
 
+template <int NC, int NRAD>
+static void launch_eval_nc(const Dev& d, const EvalIn& in, const EvalOut& out, int which, unsigned grid, cudaStream_t s) {
+  if (out.compact_camera)
+    k_eval_only<NC, NRAD, true><<<grid, kEvalBlock, eval_smem_doubles<NC, true>() * sizeof(double), s>>>(d, in, out, which);
+  else
+    k_eval_only<NC, NRAD, false><<<grid, kEvalBlock, eval_smem_doubles<NC, false>() * sizeof(double), s>>>(d, in, out, which);
+}
+
 void launch_eval_only(const Dev& d, const EvalIn& in, const EvalOut& out, int which, cudaStream_t s) {
   if (d.N == 0) return;
   const unsigned grid = (unsigned)((d.N + kEvalBlock - 1) / kEvalBlock);
   const int nrad = (int)(d.config & 3u), tang = (d.config & 0x4u) ? 1 : 0;
   switch (nrad * 2 + tang) {
-    case 0: k_eval_only<5, 0><<<grid, kEvalBlock, eval_smem_doubles<5>() * sizeof(double), s>>>(d, in, out, which); break;
-    case 1: k_eval_only<7, 0><<<grid, kEvalBlock, eval_smem_doubles<7>() * sizeof(double), s>>>(d, in, out, which); break;
-    case 2: k_eval_only<6, 1><<<grid, kEvalBlock, eval_smem_doubles<6>() * sizeof(double), s>>>(d, in, out, which); break;
-    case 3: k_eval_only<8, 1><<<grid, kEvalBlock, eval_smem_doubles<8>() * sizeof(double), s>>>(d, in, out, which); break;
-    case 4: k_eval_only<7, 2><<<grid, kEvalBlock, eval_smem_doubles<7>() * sizeof(double), s>>>(d, in, out, which); break;
-    default: k_eval_only<9, 2><<<grid, kEvalBlock, eval_smem_doubles<9>() * sizeof(double), s>>>(d, in, out, which); break;
+    case 0: launch_eval_nc<5, 0>(d, in, out, which, grid, s); break;
+    case 1: launch_eval_nc<7, 0>(d, in, out, which, grid, s); break;
+    case 2: launch_eval_nc<6, 1>(d, in, out, which, grid, s); break;
+    case 3: launch_eval_nc<8, 1>(d, in, out, which, grid, s); break;
+    case 4: launch_eval_nc<7, 2>(d, in, out, which, grid, s); break;
+    default: launch_eval_nc<9, 2>(d, in, out, which, grid, s); break;
   }
 }
 

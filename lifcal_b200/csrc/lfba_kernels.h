@@ -43,6 +43,7 @@ struct EvalOut {
   double* jac_point;   // [2N*3] or null
   double* stats;       // [8]: sum ex^2, sum ey^2, max|ex|, max|ey|, inliers, cost
   double inlier_thr2;
+  int compact_camera;  // 0: jac_camera is 2 x 17 per observation (Ceres' block, zero columns written); 1: 2 x NC (live columns)
 };
 struct EvalIn {
   const double2* obs;      // input order

@@ -963,15 +963,16 @@ int lfba_solver_time_eval(lfba_solver* h, int reps, int materialize, double* mea
     LFBA_CUDA(cudaEventCreate(&e1));
     DevBuf<double> res, jc, jv, jp, stats;
     EvalIn in{s.ix.obs_in.p, s.ix.lens_id_in.p, s.ix.point_in.p, s.ix.frame_in.p};
-    EvalOut out{nullptr, nullptr, nullptr, nullptr, nullptr, 1.0};
+    EvalOut out{nullptr, nullptr, nullptr, nullptr, nullptr, 1.0, 0};
     if (materialize) {
+      const int compact = materialize == 2 ? 1 : 0;  // 2: camera block as 2 x NC live columns (SURVEY.md 8(d) layout)
       res.alloc((size_t)2 * s.ix.N);
-      jc.alloc((size_t)34 * s.ix.N);
+      jc.alloc((size_t)2 * (compact ? s.d.NC : 17) * s.ix.N);
       jv.alloc((size_t)12 * s.ix.N);
       jp.alloc((size_t)6 * s.ix.N);
       stats.alloc(8);
       stats.zero(s.stream);
-      out = EvalOut{res.p, jc.p, jv.p, jp.p, stats.p, 1.0};
+      out = EvalOut{res.p, jc.p, jv.p, jp.p, stats.p, 1.0, compact};
     }
     const int which = s.h_state.cur;
     launch_tables(s.d, s.stream);
@@ -1051,7 +1052,7 @@ int lfba_eval(const lfba_problem* pb, const lfba_options* opt_in, const double* 
     if (jac_point) jp.alloc((size_t)6 * N);
     st.zero(s.stream);
     EvalIn in{s.ix.obs_in.p, s.ix.lens_id_in.p, s.ix.point_in.p, s.ix.frame_in.p};
-    EvalOut out{res.p, jc.p, jv.p, jp.p, st.p, inlier_threshold * inlier_threshold};
+    EvalOut out{res.p, jc.p, jv.p, jp.p, st.p, inlier_threshold * inlier_threshold, 0};
     launch_tables_for(s.d, 0, s.stream);
     launch_eval_only(s.d, in, out, 0, s.stream);
     LFBA_CUDA(cudaGetLastError());

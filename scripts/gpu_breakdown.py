@@ -35,11 +35,14 @@ def main():
         ds2.run()
         s2 = ds2.run()
         ev = ds2.time_eval(10, False)
-        evm = ds2.time_eval(3, True)
+        evm = ds2.time_eval(3, 1)
+        evc = ds2.time_eval(3, 2)
         print(json.dumps({"workload": name, "unprofiled_solve_gpu_ms": round(s2["solve_gpu_ms"], 3),
                           "solve_wall_s": round(s2["solve_time_s"], 4), "fused_eval_ms": round(ev, 4),
                           "fused_M_evals_s": round(n / ev / 1e3, 1), "fused_GBs": round((20 * n + 288 * s["num_tracks"]) / ev / 1e6, 1),
-                          "eval_only_ms": round(evm, 4), "eval_only_GBs": round(460 * n / evm / 1e6, 1)}))
+                          "eval_only_ceres_layout_ms": round(evm, 4), "eval_only_ceres_GBs_460B": round(460 * n / evm / 1e6, 1),
+                          "eval_only_compact_ms": round(evc, 4), "eval_only_compact_GBs_344B": round(344 * n / evc / 1e6, 1),
+                          "eval_only_compact_M_evals_s": round(n / evc / 1e3, 1)}))
         ds.close()
         ds2.close()
         sys.stdout.flush()
