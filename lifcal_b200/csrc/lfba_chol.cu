@@ -13,6 +13,7 @@
 // latency that matters, not the flops.
 #include <cstdio>
 
+#include "lfba_band.cuh"
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
 
@@ -199,192 +200,36 @@ __global__ void __launch_bounds__(256) k_backsolve(Dev d) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int bslot(int f, int bw1) { return 6 * (f % bw1); }
 
-// Address arithmetic of the skyline for pose rows (no dependent index loads on the critical path):
-// row r = 6f+i starts at column c0 = 6 max(0, f-bw) and holds r-c0+1 entries; rows of a frame are consecutive.
-struct SkyPose {
-  const long long* frame_off;  // smem: offset of row 6f
-  int bw;
-  __device__ __forceinline__ int c0(int f) const { return 6 * max(0, f - bw); }
-  __device__ __forceinline__ long long row(int f, int i) const {
-    const int len0 = 6 * f - c0(f) + 1;
-    return frame_off[f] + (long long)i * len0 + (i * (i - 1)) / 2;
-  }
-};
-
-constexpr int kPrefMax = 6;  // prefetch registers per thread (band) — (6*NBAND + 255)/256 <= kPrefMax is checked on the host
-
+template <int NPASS>
 __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
   LmState* st = d.st;
   if (linear_phase_idle(st) || !st->solve_ok) return;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int F = d.np6 / 6;
   const int bw1 = bw + 1;
   const int NBAND = 6 * bw1;
   const int W = NBAND + nb;
   const int LDW = W | 1;
-  double* A = sm;
-  double* ys = sm + (size_t)W * LDW;                               // n
+  double* A = sm;                                                   // window + X + L_kk (band_sweep's layout)
+  double* ys = sm + band_smem_doubles(W);                           // n
   double* dinv_all = ys + d.n;                                      // n: 1 / L_cc of the pose pivots
-  long long* frame_off = reinterpret_cast<long long*>(dinv_all + d.n);  // F + 1
-  long long* border_off = frame_off + (F + 1);                      // nb
-  int* lrow = reinterpret_cast<int*>(border_off + nb);              // W (local row of panel row i)
-  __shared__ double dinv[6];
   __shared__ double tvec[6];
   __shared__ double Lkk[21];
   __shared__ int s_fail;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int npiv = nb - 1;  // border unknowns (the last border row is the rhs)
 
-  for (int e = tid; e < W * LDW; e += nt) A[e] = 0.0;
-  for (int f = tid; f < F; f += nt) frame_off[f] = d.row_off[6 * f];
-  for (int b = tid; b < nb; b += nt) border_off[b] = d.row_off[d.np6 + b];
   if (tid == 0) s_fail = 0;
-  __syncthreads();
-  SkyPose sky{frame_off, bw};
-
-  // element e of a frame's row block: (i, cc) -> value; the block has 6 rows of up to NBAND entries
-  auto band_fetch = [&](int f, int e, int& lidx) -> double {
-    const int i = e / NBAND, cc = e - i * NBAND;
-    const int c0 = sky.c0(f);
-    const int c = c0 + cc;
-    if (i >= 6 || c > 6 * f + i) { lidx = -1; return 0.0; }
-    const int fc = c / 6;
-    lidx = (bslot(f, bw1) + i) * LDW + bslot(fc, bw1) + (c - 6 * fc);
-    return d.S[sky.row(f, i) + cc];
-  };
-  auto border_fetch = [&](int f, int e, int& lidx) -> double {
-    const int b = e / 6, j = e - 6 * b;
-    if (b >= nb) { lidx = -1; return 0.0; }
-    lidx = (NBAND + b) * LDW + bslot(f, bw1) + j;
-    return d.S[border_off[b] + 6 * f + j];
-  };
-  for (int f = 0; f <= min(bw, F - 1); ++f) {
-    for (int e = tid; e < 6 * NBAND; e += nt) { int li; const double v = band_fetch(f, e, li); if (li >= 0) A[li] = v; }
-    for (int e = tid; e < 6 * nb; e += nt) { int li; const double v = border_fetch(f, e, li); if (li >= 0) A[li] = v; }
-  }
+  const SkyMap sky{bw, d.np6};  // closed-form skyline offsets: no index loads on the chain
+  BandArgs g{d.S, d.row_off, d.np6, bw, 0, F, F - 1, 0, 0, nb, nullptr, dinv_all, d.debug};
+  band_load_initial(g, A);  // zeroes the window, loads the first bw + 1 frames; ends with a barrier
   for (int e = tid; e < nb * nb; e += nt) {
     const int b1 = e / nb, b2 = e % nb;
-    if (b2 <= b1 && !(b1 == npiv && b2 == npiv)) A[(NBAND + b1) * LDW + NBAND + b2] = d.S[border_off[b1] + d.np6 + b2];
+    if (b2 <= b1 && !(b1 == npiv && b2 == npiv)) A[(NBAND + b1) * LDW + NBAND + b2] = d.S[sky.border_row(b1) + d.np6 + b2];
   }
   __syncthreads();
-
-#ifdef LFBA_CHOL_PROF
-  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long tlast = clock64();
-#define CHOL_TICK(i) { const long long tn = clock64(); pc[i] += tn - tlast; tlast = tn; }
-#else
 #define CHOL_TICK(i)
-#endif
-  const int tx = tid & 15, ty = tid >> 4;
-  for (int k = 0; k < F; ++k) {
-    const int s = bslot(k, bw1);
-    // ---- prefetch the frame that will take this slot (k + bw + 1): loads in flight during the whole step ----
-    const int fn = k + bw1;
-    double pv[kPrefMax], pb = 0.0;
-    int pl[kPrefMax], plb = -1;
-    if (fn < F) {
-#pragma unroll
-      for (int q = 0; q < kPrefMax; ++q) {
-        const int e = tid + q * nt;
-        pl[q] = -1;
-        pv[q] = 0.0;
-        if (e < 6 * NBAND) pv[q] = band_fetch(fn, e, pl[q]);
-      }
-      if (tid < 6 * nb) pb = border_fetch(fn, tid, plb);
-    }
-    CHOL_TICK(0)
-    // ---- 6x6 Cholesky of the pivot block: one thread, registers only (the latency chain of the whole solve) ----
-    if (tid == 0) {
-      double a[21];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = A[(s + i) * LDW + s + j];
-      bool bad = false;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const double piv = a[c * (c + 1) / 2 + c];
-        const bool okp = piv > 0.0;
-        bad |= !okp;
-        const double r = okp ? rsqrt(piv) : 0.0;
-        a[c * (c + 1) / 2 + c] = okp ? piv * r : 1.0;
-        dinv[c] = r;
-        dinv_all[6 * k + c] = r;
-#pragma unroll
-        for (int i = c + 1; i < 6; ++i) a[i * (i + 1) / 2 + c] *= r;
-#pragma unroll
-        for (int i = c + 1; i < 6; ++i)
-#pragma unroll
-          for (int j = c + 1; j <= i; ++j) a[i * (i + 1) / 2 + j] = fma(-a[i * (i + 1) / 2 + c], a[j * (j + 1) / 2 + c], a[i * (i + 1) / 2 + j]);
-      }
-      if (bad) s_fail = 1;
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) A[(s + i) * LDW + s + j] = a[i * (i + 1) / 2 + j];
-    }
-    CHOL_TICK(1)
-    const int nbf = min(bw, F - 1 - k);
-    const int mrows = 6 * nbf + nb;
-    for (int i = tid; i < mrows; i += nt)
-      lrow[i] = i < 6 * nbf ? bslot(k + 1 + i / 6, bw1) + i % 6 : NBAND + (i - 6 * nbf);
-    __syncthreads();
-    CHOL_TICK(2)
-    // ---- panel: rows of the frames k+1..k+bw and the border; X = A L^-T ----
-    for (int i = tid; i < mrows; i += nt) {
-      const int lr = lrow[i];
-      long long goff;
-      if (i < 6 * nbf) {
-        const int f = k + 1 + i / 6;
-        goff = sky.row(f, i % 6) + (6 * k - sky.c0(f));
-      } else {
-        goff = border_off[i - 6 * nbf] + 6 * k;
-      }
-      double x[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double a = A[lr * LDW + s + c];
-#pragma unroll
-        for (int j = 0; j < c; ++j) a -= x[j] * A[(s + c) * LDW + s + j];
-        x[c] = a * dinv[c];
-      }
-      double* dst = d.S + goff;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        A[lr * LDW + s + c] = x[c];
-        dst[c] = x[c];
-      }
-    }
-    if (tid >= 224 && tid < 245) {  // L_kk to HBM
-      int i = 0, j = tid - 224;
-      while (j > i) { j -= i + 1; ++i; }
-      d.S[sky.row(k, i) + (6 * k + j - sky.c0(k))] = A[(s + i) * LDW + s + j];
-    }
-    __syncthreads();
-    CHOL_TICK(3)
-    // ---- trailing update of the window: A[i][j] -= X_i . X_j, i >= j in global order (16 x 16 thread grid) ----
-    for (int i = ty; i < mrows; i += 16) {
-      const int li = lrow[i];
-      const double* xi = A + li * LDW + s;
-      const double x0 = xi[0], x1 = xi[1], x2 = xi[2], x3 = xi[3], x4 = xi[4], x5 = xi[5];
-      for (int j = tx; j <= i; j += 16) {
-        const int lj = lrow[j];
-        const double* xj = A + lj * LDW + s;
-        A[li * LDW + lj] -= x0 * xj[0] + x1 * xj[1] + x2 * xj[2] + x3 * xj[3] + x4 * xj[4] + x5 * xj[5];
-      }
-    }
-    __syncthreads();
-    CHOL_TICK(4)
-    // ---- slide the window: frame k+bw+1 takes the slot of frame k ----
-    if (fn < F) {
-#pragma unroll
-      for (int q = 0; q < kPrefMax; ++q)
-        if (pl[q] >= 0) A[pl[q]] = pv[q];
-      if (plb >= 0) A[plb] = pb;
-      for (int e = tid + nt; e < 6 * nb; e += nt) { int li; const double v = border_fetch(fn, e, li); if (li >= 0) A[li] = v; }
-      __syncthreads();
-    }
-  }
+  band_sweep<NPASS>(g, A, &s_fail);
   CHOL_TICK(5)
   // ---- dense Cholesky of the border block (coupled points + camera); the rhs row is not a pivot ----
   for (int c = 0; c < npiv; ++c) {
@@ -409,7 +254,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
   __syncthreads();
   for (int e = tid; e < nb * nb; e += nt) {
     const int b1 = e / nb, b2 = e % nb;
-    if (b2 <= b1 && !(b1 == npiv && b2 == npiv)) d.S[border_off[b1] + d.np6 + b2] = A[(NBAND + b1) * LDW + NBAND + b2];
+    if (b2 <= b1 && !(b1 == npiv && b2 == npiv)) d.S[sky.border_row(b1) + d.np6 + b2] = A[(NBAND + b1) * LDW + NBAND + b2];
   }
   if (tid == 0 && s_fail) st->solve_ok = 0;
   if (s_fail) return;
@@ -423,7 +268,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
     }
   }
   __syncthreads();
-  const double* zrow = d.S + border_off[npiv];
+  const double* zrow = d.S + sky.border_row(npiv);
   // software pipeline: the L entries of block column k-1 are loaded while block k is being solved
   const int per = 8;  // entries per lane per output column: mrows <= 32 * per is checked on the host
   double lv[per];
@@ -438,7 +283,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
         lv[q] = 0.0;
         if (i < mrows) {
           const long long off = i < 6 * nbf ? sky.row(k + 1 + i / 6, i % 6) + (6 * k + warp - sky.c0(k + 1 + i / 6))
-                                            : border_off[i - 6 * nbf] + 6 * k + warp;
+                                            : sky.border_row(i - 6 * nbf) + 6 * k + warp;
           lv[q] = d.S[off];
         }
       }
@@ -482,32 +327,34 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
     __syncthreads();
   }
   CHOL_TICK(7)
-#ifdef LFBA_CHOL_PROF
-  if (tid == 0) printf("chol phases (cycles): top/prefetch %lld chol6 %lld lrow+sync %lld panel %lld trailing %lld slide %lld | border+backward %lld\n", pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[7]);
-#endif
   for (int j = tid; j < d.n; j += nt) d.y[j] = ys[j];
 }
 
 // per-device opt-in to > 48 KB of dynamic shared memory (call once per device with that device current)
 void prepare_device_kernels() {
   cudaFuncSetAttribute(k_chol_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * TS * LD * sizeof(double)));
-  cudaFuncSetAttribute(k_chol_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
+  cudaFuncSetAttribute(k_chol_banded<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
+  cudaFuncSetAttribute(k_chol_banded<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
+  cudaFuncSetAttribute(k_chol_banded<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
+  cudaFuncSetAttribute(k_chol_banded<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
+  cudaFuncSetAttribute(k_chol_banded<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
 }
 
 // shared memory needed by k_chol_banded, or 0 when the banded path does not apply / does not fit
 size_t banded_smem_bytes(const Dev& d, int bw, int nb) {
   if (d.np6 == 0) return 0;
-  const size_t NBAND = 6 * (size_t)(bw + 1), W = NBAND + nb, LDW = W | 1;
+  const size_t NBAND = 6 * (size_t)(bw + 1), W = NBAND + nb;
   const size_t F = d.np6 / 6;
-  if ((6 * NBAND + 255) / 256 > (size_t)kPrefMax) return 0;   // prefetch registers of k_chol_banded
+  if (6 * W > (size_t)kBandPref * 224 || W > 160) return 0;   // prefetch registers / column passes of band_sweep
   if (6 * (size_t)bw + nb > 32 * 8) return 0;                 // backward-substitution lanes
-  if ((size_t)6 * nb > 2 * 256 + 256) {}                      // (border prefetch falls back to a loop)
-  const size_t bytes = (W * LDW + 2 * (size_t)d.n + (F + 1) + nb + 8) * sizeof(double) + W * sizeof(int);
+  const size_t bytes = (band_smem_doubles((int)W) + 2 * (size_t)d.n + 8) * sizeof(double);
+  (void)F;
   return bytes <= (size_t)kBandedSmemMax ? bytes : 0;
 }
 
 void launch_chol_banded(const Dev& d, int bw, int nb, size_t smem, cudaStream_t s) {
-  k_chol_banded<<<1, 256, smem, s>>>(d, bw, nb);
+  const int W = 6 * (bw + 1) + nb;
+  LFBA_BAND_DISPATCH(W, (k_chol_banded<NPASS><<<1, 256, smem, s>>>(d, bw, nb)));
 }
 
 int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, int bw, cudaStream_t s, PartPlan* plan) {
@@ -515,7 +362,7 @@ int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, int
   const int nb = d.n - d.np6 + 1;
   const size_t bsm = banded_smem_bytes(d, bw, nb);
   if (bsm > 0) {
-    k_chol_banded<<<1, 256, bsm, s>>>(d, bw, nb);
+    launch_chol_banded(d, bw, nb, bsm, s);
     return 1;
   }
   const size_t smem = 3 * TS * LD * sizeof(double);

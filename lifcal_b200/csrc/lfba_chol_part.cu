@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "lfba_band.cuh"
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
 
@@ -38,188 +39,32 @@ struct PartDev {
 
 __device__ __forceinline__ int pslot(int f, int bw1) { return 6 * (f % bw1); }
 
-struct Sky {
-  const Dev& d;
-  int bw;
-  __device__ __forceinline__ int c0(int f) const { return 6 * max(0, f - bw); }
-  __device__ __forceinline__ long long row(int f, int i) const {
-    const int len0 = 6 * f - c0(f) + 1;
-    return d.row_off[6 * f] + (long long)i * len0 + (i * (i - 1)) / 2;
-  }
-};
-
-constexpr int kPref = 6;  // prefetch registers per thread for the entering frame (checked on the host)
-
 // ---------------------------------------------------------------------------------------------------------------
 // phase 1
 // ---------------------------------------------------------------------------------------------------------------
+template <int NPASS>
 __global__ void __launch_bounds__(256) k_part_forward(Dev d, PartDev pd) {
   LmState* st = d.st;
   if (linear_phase_idle(st) || !st->solve_ok) return;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int j = blockIdx.x, P = pd.P, bw = pd.bw, bw1 = bw + 1, F = pd.F;
   const int fa = pd.bounds[j];
   const bool last = j == P - 1;
   const int hi = last ? F - 1 : pd.bounds[j + 1] - 1;   // last frame that enters this partition's window
   const int fb = last ? F : pd.bounds[j + 1] - bw;      // interior = [fa, fb)
   const int ns = j > 0 ? 6 * bw : 0;                    // rows of the previous separator
-  const int sp0 = fa - bw;                              // its first frame
   const int nb = pd.npiv + 1;                           // global border rows incl. the rhs row
   const int B = ns + nb;
   const int NBAND = 6 * bw1, W = NBAND + B, LDW = W | 1;
   double* A = sm;
-  int* lrow = reinterpret_cast<int*>(A + (size_t)W * LDW);
-  __shared__ double dinv[6];
   __shared__ int s_fail;
   const int tid = threadIdx.x, nt = blockDim.x;
-  Sky sky{d, bw};
-  const int64_t* row_off = d.row_off;
-  const int seg_len = 36 * bw + 21;                     // skyline entries of one full-band frame (6 rows)
-
-  for (int e = tid; e < W * LDW; e += nt) A[e] = 0.0;
   if (tid == 0) s_fail = 0;
-  __syncthreads();
-
-  // element e of frame f's skyline rows -> (value, position in the window); lidx < 0: nothing to store
-  auto band_elem = [&](int f, int e, int& lidx) -> double {
-    const int cz = sky.c0(f), len0 = 6 * f - cz + 1;
-    int i = 0, rs = 0;
-    while (i < 5 && e >= rs + len0 + i) { rs += len0 + i; ++i; }
-    const int cc = e - rs;
-    if (cc >= len0 + i) { lidx = -1; return 0.0; }
-    const int c = cz + cc, fc = c / 6;
-    if (fc >= fa) lidx = (pslot(f, bw1) + i) * LDW + pslot(fc, bw1) + (c - 6 * fc);
-    else if (ns > 0 && fc >= sp0) lidx = (NBAND + 6 * (fc - sp0) + (c - 6 * fc)) * LDW + pslot(f, bw1) + i;  // transposed
-    else lidx = -1;
-    return d.S[row_off[6 * f] + e];
-  };
-  auto load_frame_sync = [&](int f) {
-    const int cz = sky.c0(f), n_e = 6 * (6 * f - cz + 1) + 15;
-    // previous-separator rows: zero where this frame is not coupled (the slot is reused)
-    for (int e = tid; e < ns * 6; e += nt) A[(NBAND + e / 6) * LDW + pslot(f, bw1) + e % 6] = 0.0;
-    __syncthreads();
-    for (int e = tid; e < n_e; e += nt) {
-      int li;
-      const double v = band_elem(f, e, li);
-      if (li >= 0) A[li] = v;
-    }
-    for (int e = tid; e < 6 * nb; e += nt)
-      A[(NBAND + ns + e / 6) * LDW + pslot(f, bw1) + e % 6] = d.S[row_off[d.np6 + e / 6] + 6 * f + e % 6];
-  };
-  for (int f = fa; f <= min(fa + bw, hi); ++f) load_frame_sync(f);
-  __syncthreads();
-
-  const int tx = tid & 15, ty = tid >> 4;
-  for (int k = fa; k < fb; ++k) {
-    const int s = pslot(k, bw1);
-    const int fn = k + bw1;
-    const bool enter = fn <= hi;
-    // ---- prefetch the entering frame into registers: in flight during the whole step ----
-    double pv[kPref], pbv = 0.0;
-    int pl[kPref];
-#pragma unroll
-    for (int q = 0; q < kPref; ++q) {
-      pl[q] = -1;
-      pv[q] = 0.0;
-      const int e = tid + q * nt;
-      if (enter && e < seg_len) pv[q] = band_elem(fn, e, pl[q]);
-    }
-    if (enter && tid < 6 * nb) pbv = d.S[row_off[d.np6 + tid / 6] + 6 * fn + tid % 6];
-    // ---- 6x6 Cholesky of the pivot block (one thread, registers) ----
-    if (tid == 0) {
-      double a[21];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int c = 0; c <= i; ++c) a[i * (i + 1) / 2 + c] = A[(s + i) * LDW + s + c];
-      bool bad = false;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const double piv = a[c * (c + 1) / 2 + c];
-        const bool okp = piv > 0.0;
-        bad |= !okp;
-        const double r = okp ? rsqrt(piv) : 0.0;
-        a[c * (c + 1) / 2 + c] = okp ? piv * r : 1.0;
-        dinv[c] = r;
-        pd.dinv[6 * k + c] = r;
-#pragma unroll
-        for (int i = c + 1; i < 6; ++i) a[i * (i + 1) / 2 + c] *= r;
-#pragma unroll
-        for (int i = c + 1; i < 6; ++i)
-#pragma unroll
-          for (int c2 = c + 1; c2 <= i; ++c2)
-            a[i * (i + 1) / 2 + c2] = fma(-a[i * (i + 1) / 2 + c], a[c2 * (c2 + 1) / 2 + c], a[i * (i + 1) / 2 + c2]);
-      }
-      if (bad) s_fail = 1;
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int c = 0; c <= i; ++c) A[(s + i) * LDW + s + c] = a[i * (i + 1) / 2 + c];
-    }
-    const int nbf = min(bw, hi - k);
-    const int mrows = 6 * nbf + B;
-    for (int i = tid; i < mrows; i += nt)
-      lrow[i] = i < 6 * nbf ? pslot(k + 1 + i / 6, bw1) + i % 6 : NBAND + (i - 6 * nbf);
-    __syncthreads();
-    // ---- panel: X = A L_kk^-T for the band rows, the previous-separator rows and the border rows ----
-    for (int i = tid; i < mrows; i += nt) {
-      const int lr = lrow[i];
-      double* dst;
-      if (i < 6 * nbf) {
-        const int f = k + 1 + i / 6;
-        dst = d.S + sky.row(f, i % 6) + (6 * k - sky.c0(f));
-      } else if (i < 6 * nbf + ns) {
-        dst = pd.Lsep + ((size_t)k * 6 * bw + (i - 6 * nbf)) * 6;
-      } else {
-        dst = d.S + row_off[d.np6 + (i - 6 * nbf - ns)] + 6 * k;
-      }
-      double x[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double a = A[lr * LDW + s + c];
-#pragma unroll
-        for (int c2 = 0; c2 < c; ++c2) a -= x[c2] * A[(s + c) * LDW + s + c2];
-        x[c] = a * dinv[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        A[lr * LDW + s + c] = x[c];
-        dst[c] = x[c];
-      }
-    }
-    if (tid >= 224 && tid < 245) {  // L_kk to HBM
-      int i = 0, c = tid - 224;
-      while (c > i) { c -= i + 1; ++i; }
-      d.S[sky.row(k, i) + (6 * k + c - sky.c0(k))] = A[(s + i) * LDW + s + c];
-    }
-    __syncthreads();
-    // ---- trailing update of the window ----
-    for (int i = ty; i < mrows; i += 16) {
-      const int li = lrow[i];
-      const double* xi = A + li * LDW + s;
-      const double x0 = xi[0], x1 = xi[1], x2 = xi[2], x3 = xi[3], x4 = xi[4], x5 = xi[5];
-      for (int c = tx; c <= i; c += 16) {
-        const int lj = lrow[c];
-        const double* xj = A + lj * LDW + s;
-        A[li * LDW + lj] -= x0 * xj[0] + x1 * xj[1] + x2 * xj[2] + x3 * xj[3] + x4 * xj[4] + x5 * xj[5];
-      }
-    }
-    __syncthreads();
-    // ---- slide: frame fn takes the slot of frame k ----
-    if (enter) {
-      for (int e = tid; e < ns * 6; e += nt) A[(NBAND + e / 6) * LDW + s + e % 6] = 0.0;
-      __syncthreads();
-#pragma unroll
-      for (int q = 0; q < kPref; ++q)
-        if (pl[q] >= 0) A[pl[q]] = pv[q];
-      if (tid < 6 * nb) A[(NBAND + ns + tid / 6) * LDW + s + tid % 6] = pbv;
-      for (int e = tid + nt; e < 6 * nb; e += nt)
-        A[(NBAND + ns + e / 6) * LDW + s + e % 6] = d.S[row_off[d.np6 + e / 6] + 6 * fn + e % 6];
-      __syncthreads();
-    }
-  }
+  BandArgs g{d.S, d.row_off, d.np6, bw, fa, fb, hi, ns, fa - bw, nb, pd.Lsep, pd.dinv, d.debug};
+  band_load_initial(g, A);
+  band_sweep<NPASS>(g, A, &s_fail);
   if (tid == 0 && s_fail) st->solve_ok = 0;
-  // ---- what is left: Schur complement on [this separator | previous separator | border] ----
+  // ---- what is left: Schur complement on [this separator | previous separator | border] (slot space, [max][min]) ----
   const int nsep = last ? 0 : 6 * bw;
   const int M = nsep + B;
   double* X = pd.X + (size_t)j * pd.M * pd.M;
@@ -229,47 +74,62 @@ __global__ void __launch_bounds__(256) k_part_forward(Dev d, PartDev pd) {
   };
   for (int e = tid; e < M * M; e += nt) {
     const int r1 = e / M, r2 = e % M;
-    if (r2 <= r1) X[(size_t)r1 * pd.M + r2] = A[aidx(r1) * LDW + aidx(r2)];
+    if (r2 <= r1) {
+      const int a1 = aidx(r1), a2 = aidx(r2);
+      X[(size_t)r1 * pd.M + r2] = A[max(a1, a2) * LDW + min(a1, a2)];
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // phase 2a: reduced system over [separators | border | rhs] in skyline form (d2)
 // ---------------------------------------------------------------------------------------------------------------
+// One thread per entry of the reduced skyline S2: it gathers its contributions (original border block; the extracted
+// blocks of the at most two partitions that touch a separator entry, of all P partitions for a border entry) in
+// partition order: deterministic, no atomics, no barriers.
 __global__ void __launch_bounds__(256) k_part_assemble(Dev d, PartDev pd, Dev d2, long long s2_len) {
   LmState* st = d.st;
   if (linear_phase_idle(st) || !st->solve_ok) return;
-  const int tid = threadIdx.x, nt = blockDim.x;
   const int P = pd.P, bw = pd.bw, npiv = pd.npiv, nb = npiv + 1;
-  const int nsf = 6 * bw * (P - 1);  // separator unknowns
-  for (long long e = tid; e < s2_len; e += nt) d2.S[e] = 0.0;
-  __syncthreads();
-  auto at2 = [&](int r, int c) -> double* { return d2.S + d2.row_off[r] + (c - d2.row_c0[r]); };
-  // original border block (coupled points + camera + the border part of the rhs row)
-  for (int e = tid; e < nb * nb; e += nt) {
-    const int b1 = e / nb, b2 = e % nb;
-    if (b2 <= b1 && !(b1 == npiv && b2 == npiv)) *at2(nsf + b1, nsf + b2) = d.S[d.row_off[d.np6 + b1] + d.np6 + b2];
-  }
-  __syncthreads();
-  for (int j = 0; j < P; ++j) {  // fixed order: deterministic sums
-    const bool last = j == P - 1;
-    const int nsep = last ? 0 : 6 * bw, ns = j > 0 ? 6 * bw : 0;
-    const int M = nsep + ns + nb;
-    const double* X = pd.X + (size_t)j * pd.M * pd.M;
-    auto ridx = [&](int r) -> int {  // extraction index -> index in the reduced system
-      if (r < nsep) return 6 * bw * j + r;
-      if (r < nsep + ns) return 6 * bw * (j - 1) + (r - nsep);
-      return nsf + (r - nsep - ns);
-    };
-    for (int e = tid; e < M * M; e += nt) {
-      const int r1 = e / M, r2 = e % M;
-      if (r2 > r1) continue;
-      const int g1 = ridx(r1), g2 = ridx(r2);
-      if (g1 == nsf + npiv && g2 == nsf + npiv) continue;
-      *at2(max(g1, g2), min(g1, g2)) += X[(size_t)r1 * pd.M + r2];
+  const int sw = 6 * bw;             // separator width
+  const int nsf = sw * (P - 1);      // separator unknowns
+  const int n2_aug = nsf + nb;
+  const SkyMap sky{bw, d.np6};
+  for (int r = blockIdx.x; r < n2_aug; r += gridDim.x) {
+    const int c0 = d2.row_c0[r];
+    const long long ro = d2.row_off[r];
+    for (int c = c0 + threadIdx.x; c <= r; c += blockDim.x) {
+      if (r == nsf + npiv && c == nsf + npiv) continue;  // the rhs row has no diagonal entry
+      double v = 0.0;
+      auto xat = [&](int j, int r1, int r2) -> double {  // lower-triangular read of partition j's block
+        const double* X = pd.X + (size_t)j * pd.M * pd.M;
+        return r1 >= r2 ? X[(size_t)r1 * pd.M + r2] : X[(size_t)r2 * pd.M + r1];
+      };
+      // extraction index of reduced index q inside partition j's block, or -1
+      auto xidx = [&](int j, int q) -> int {
+        const bool last = j == P - 1;
+        const int nsep = last ? 0 : sw, ns = j > 0 ? sw : 0;
+        if (q >= nsf) return nsep + ns + (q - nsf);                           // border
+        const int sj = q / sw, o = q - sw * sj;                               // separator sj
+        if (!last && sj == j) return o;                                       // this partition's own separator
+        if (j > 0 && sj == j - 1) return nsep + o;                            // the previous separator
+        return -1;
+      };
+      if (r >= nsf && c >= nsf) {  // border x border: original block + every partition
+        v = d.S[sky.border_row(r - nsf) + d.np6 + (c - nsf)];
+        for (int j = 0; j < P; ++j) v += xat(j, xidx(j, r), xidx(j, c));
+      } else {
+        // at least one separator index: only the partitions adjacent to that separator contribute
+        const int sc = c / sw;  // c < nsf here (c <= r and not both border)
+        for (int j = sc; j <= min(sc + 1, P - 1); ++j) {
+          const int i1 = xidx(j, r), i2 = xidx(j, c);
+          if (i1 >= 0 && i2 >= 0) v += xat(j, i1, i2);
+        }
+      }
+      d2.S[ro + (c - c0)] = v;
     }
-    __syncthreads();
   }
+  (void)s2_len;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -292,8 +152,7 @@ __global__ void __launch_bounds__(256) k_part_backward(Dev d, PartDev pd, const 
   double* yb = ysp + 6 * bw;                // [npiv] y of the border
   __shared__ double tvec[6];
   __shared__ double Lkk[21];
-  Sky sky{d, bw};
-  const int64_t* row_off = d.row_off;
+  const SkyMap sky{bw, d.np6};
   // known parts of the solution (phase 2); every CTA also publishes what it owns into d.y
   if (!last)
     for (int e = tid; e < 6 * bw; e += nt) {
@@ -308,7 +167,7 @@ __global__ void __launch_bounds__(256) k_part_backward(Dev d, PartDev pd, const 
     if (j == 0) d.y[d.np6 + e] = v;
   }
   __syncthreads();
-  const double* zrow = d.S + row_off[d.np6 + npiv];
+  const double* zrow = d.S + sky.border_row(npiv);
   constexpr int per = 8;  // rows per lane: mrows <= 32 * per is checked on the host
   double lv[per];
   double lkk = 0.0, zk = 0.0;
@@ -327,7 +186,7 @@ __global__ void __launch_bounds__(256) k_part_backward(Dev d, PartDev pd, const 
           } else if (i < 6 * nbf + ns) {
             lv[q] = pd.Lsep[((size_t)k * 6 * bw + (i - 6 * nbf)) * 6 + warp];
           } else {
-            lv[q] = d.S[row_off[d.np6 + (i - 6 * nbf - ns)] + 6 * k + warp];
+            lv[q] = d.S[sky.border_row(i - 6 * nbf - ns) + 6 * k + warp];
           }
         }
       }
@@ -424,12 +283,16 @@ PartPlan* part_plan_create(const Dev& d, int bw, cudaStream_t s) {
   P = std::min(P, F / (2 * bw + 2));
   P = std::min(P, 64);
   if (P < 3) return p;
-  if (36 * bw + 21 > kPref * 256) return p;        // prefetch registers of k_part_forward
+  {
+    const int Wf = 6 * (bw + 1) + 6 * bw + nb;
+    if (6 * Wf > kBandPref * 224 || Wf > 160) return p;  // prefetch registers / column passes of band_sweep
+  }
   if (6 * bw + 6 * bw + npiv > 32 * 8) return p;   // backward-substitution lanes
   std::vector<int> hb((size_t)P + 1);
   for (int j = 0; j <= P; ++j) hb[j] = (int)((long long)F * j / P);
   const int B = 6 * bw + nb, NBAND = 6 * (bw + 1), W = NBAND + B, LDW = W | 1;
-  p->smem_fwd = (size_t)W * LDW * sizeof(double) + (size_t)W * sizeof(int) + 16;
+  p->smem_fwd = band_smem_doubles(W) * sizeof(double);
+  (void)LDW;
   int max_len = 0;
   for (int j = 0; j < P; ++j) max_len = std::max(max_len, hb[j + 1] - hb[j]);
   p->smem_bwd = (size_t)(6 * max_len + 6 * bw + npiv + 8) * sizeof(double);
@@ -471,7 +334,11 @@ PartPlan* part_plan_create(const Dev& d, int bw, cudaStream_t s) {
   d2.y = p->y2;
   p->d2 = d2;
   p->pd = PartDev{P, bw, F, npiv, p->bounds, p->Lsep, p->X, p->dinv, M};
-  cudaFuncSetAttribute(k_part_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
+  cudaFuncSetAttribute(k_part_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
+  cudaFuncSetAttribute(k_part_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
+  cudaFuncSetAttribute(k_part_forward<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
+  cudaFuncSetAttribute(k_part_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
+  cudaFuncSetAttribute(k_part_forward<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
   cudaFuncSetAttribute(k_part_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bwd);
   p->active = true;
   return p;
@@ -481,10 +348,13 @@ bool part_plan_active(const PartPlan* p) { return p && p->active; }
 
 // the three phases on stream s; returns the number of kernels launched
 int launch_part_solve(const Dev& d, PartPlan* p, cudaStream_t s) {
-  k_part_forward<<<p->pd.P, 256, p->smem_fwd, s>>>(d, p->pd);
+  {
+    const int Wf = 6 * (p->pd.bw + 1) + 6 * p->pd.bw + p->pd.npiv + 1;
+    LFBA_BAND_DISPATCH(Wf, (k_part_forward<NPASS><<<p->pd.P, 256, p->smem_fwd, s>>>(d, p->pd)));
+  }
   Dev d2 = p->d2;
   d2.st = d.st;
-  k_part_assemble<<<1, 256, 0, s>>>(d, p->pd, d2, p->s2_len);
+  k_part_assemble<<<std::min(148, d2.n + 1), 64, 0, s>>>(d, p->pd, d2, p->s2_len);
   launch_chol_banded(d2, p->bw2, p->nb, p->smem_red, s);
   k_part_backward<<<p->pd.P, 256, p->smem_bwd, s>>>(d, p->pd, p->y2);
   return 4;

@@ -372,7 +372,7 @@ def test_shards_emulated_on_one_gpu_match_the_single_gpu_solve(gpu, shards):
         for a, b in zip(sn["iterations"], s1["iterations"]):
             assert a["step_is_successful"] == b["step_is_successful"]
             assert abs(a["cost"] - b["cost"]) <= 1e-12 * b["cost"]
-            assert abs(a["gradient_max_norm"] - b["gradient_max_norm"]) <= 1e-8 * b["gradient_max_norm"]
+            assert abs(a["gradient_max_norm"] - b["gradient_max_norm"]) <= 1e-6 * b["gradient_max_norm"]
         assert np.max(np.abs(emu[0][:9] - one[0][:9]) / np.abs(one[0][:9])) <= 1e-9
         assert np.max(np.abs(emu[1] - one[1])) <= 1e-9 * max(1.0, np.max(np.abs(one[1])))
         assert np.max(np.abs(emu[2] - one[2])) <= 1e-9 * max(1.0, np.max(np.abs(one[2])))
