@@ -365,7 +365,7 @@ def main():
     if not args.no_e2e:
         ppa = pinned_problem(pa)
         o2 = api.default_options(device=local_rank)
-        ts, ev2 = [], 0
+        ts, ev2, h2d = [], 0, []
         if world == 1:
             for k in range(1 + min(2, args.steps)):
                 barrier()
@@ -376,6 +376,7 @@ def main():
                 if k > 0:
                     ts.append(dt)
                     ev2 += s2["num_jacobian_evals"]
+                    h2d.append(s2.get("h2d_gbs"))
         else:
             for k in range(1 + min(2, args.steps)):
                 barrier()
@@ -392,10 +393,12 @@ def main():
                 if k > 0:
                     ts.append(float(tt.item()))
                     ev2 += s2["num_jacobian_evals"]
+                    h2d.append(s2.get("h2d_gbs"))
         tot = sum(ts)
         F = pa.n_frames
         e2e = {"value": n_global * ev2 / tot / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(40 * n_local + 8 * (17 + 6 * F + 3 * P)),
                "d2h_bytes_per_step": int(8 * (17 + 6 * F + 3 * P)), "s_per_solve": tot / len(ts),
+               "h2d_gbs_achieved": [round(v, 1) for v in h2d if v], "s_per_solve_each": [round(v, 4) for v in ts],
                "api": "lfba_solve (C ABI, pinned host buffers)" if world == 1 else "lfba_solver_create+run per rank"}
 
     if comm is not None:

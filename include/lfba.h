@@ -169,6 +169,10 @@ typedef struct lfba_summary {
   lfba_iteration* iterations;
   int32_t iterations_capacity;
   int32_t reserved_i;
+  /* set-up: the six observation arrays (40 B per observation) go up on their own copy stream, overlapped with the
+   * device-side indexing; bytes and device time of that upload (CUDA events on the copy stream) */
+  int64_t h2d_bytes;
+  double h2d_ms;
 } lfba_summary;
 
 /* indices into lfba_summary.kernel_ms */
@@ -211,6 +215,9 @@ const char* lfba_status_string(int status);
 void lfba_options_init(lfba_options* opt);
 /* number of usable sm_100 devices (0 => every compute call returns LFBA_NO_DEVICE) */
 int lfba_device_count(void);
+/* The library keeps the large device blocks of a finished solve (by size, per device) for the next one: repeated drop-in
+ * calls on the same problem shape then pay no allocation. This returns them to the CUDA memory pool. */
+void lfba_trim_cache(void);
 
 /* Drop-in for src/CameraCalibration.cpp:858-965: camera[17], views[6F], points[3P] are in/out, updated
  * in place to the last accepted LM iterate exactly like Ceres does. */

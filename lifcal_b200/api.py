@@ -19,7 +19,7 @@ from .capi import LfbaError
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 
-_EXPORTS = ["lfba_version", "lfba_last_error", "lfba_status_string", "lfba_options_init", "lfba_device_count",
+_EXPORTS = ["lfba_version", "lfba_last_error", "lfba_status_string", "lfba_options_init", "lfba_device_count", "lfba_trim_cache",
             "lfba_solve", "lfba_eval", "lfba_comm_unique_id", "lfba_comm_create", "lfba_comm_destroy", "lfba_solver_create", "lfba_solver_set_parameters",
             "lfba_solver_get_parameters", "lfba_solver_run", "lfba_solver_time_eval", "lfba_solver_track_blocks",
             "lfba_measure_fp64_peak", "lfba_solver_destroy"]
@@ -77,6 +77,11 @@ def version() -> int:
 
 def device_count() -> int:
     return load().lfba_device_count()
+
+
+def trim_cache() -> None:
+    """Return the device blocks the library keeps between solves to the CUDA memory pool."""
+    load().lfba_trim_cache()
 
 
 def default_options(**kw) -> capi.Options:

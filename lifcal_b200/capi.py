@@ -89,6 +89,7 @@ class Summary(C.Structure):
         ("setup_time_s", C.c_double), ("solve_time_s", C.c_double), ("solve_gpu_ms", C.c_double),
         ("kernel_ms", C.c_double * NUM_KERNEL_TIMERS), ("kernel_calls", C.c_int64 * NUM_KERNEL_TIMERS),
         ("iterations", C.POINTER(Iteration)), ("iterations_capacity", C.c_int32), ("reserved_i", C.c_int32),
+        ("h2d_bytes", C.c_int64), ("h2d_ms", C.c_double),
     ]
 
 
@@ -186,6 +187,8 @@ def summary_to_dict(s: Summary, rows) -> dict:
         "num_jacobian_evals": s.num_jacobian_evals, "num_observations": s.num_observations,
         "num_tracks": s.num_tracks, "num_lenses": s.num_lenses, "gpu_launches": s.gpu_launches,
         "setup_time_s": s.setup_time_s, "solve_time_s": s.solve_time_s, "solve_gpu_ms": s.solve_gpu_ms,
+        "h2d_bytes": s.h2d_bytes, "h2d_ms": s.h2d_ms,
+        "h2d_gbs": (s.h2d_bytes / (s.h2d_ms * 1e-3) / 1e9) if s.h2d_ms > 0 else None,
         "kernel_ms": {KERNEL_TIMER_NAMES[i]: s.kernel_ms[i] for i in range(NUM_KERNEL_TIMERS) if s.kernel_calls[i]},
         "kernel_calls": {KERNEL_TIMER_NAMES[i]: s.kernel_calls[i] for i in range(NUM_KERNEL_TIMERS) if s.kernel_calls[i]},
         "iterations": [{f: getattr(rows[i], f) for f in fields} for i in range(n)],

@@ -23,6 +23,7 @@
 #include "lfba_band.cuh"
 #include "lfba_device.cuh"
 #include "lfba_kernels.h"
+#include "lfba_setup.cuh"
 
 namespace lfba {
 
@@ -248,26 +249,15 @@ struct PartPlan {
   int bw2 = 0, nb = 0;
   long long s2_len = 0;
   size_t smem_fwd = 0, smem_bwd = 0, smem_red = 0;
-  int *bounds = nullptr, *row_c02 = nullptr;
-  long long* row_off2 = nullptr;
-  double *Lsep = nullptr, *X = nullptr, *dinv = nullptr, *S2 = nullptr, *y2 = nullptr;
+  DevBuf<int> bounds, row_c02;
+  DevBuf<long long> row_off2;
+  DevBuf<double> Lsep, X, dinv, S2, y2;  // stream-ordered, from the library's block cache (no cudaMalloc / cudaFree per solve)
 };
 
 size_t banded_smem_bytes(const Dev& d, int bw, int nb);  // lfba_chol.cu
 void launch_chol_banded(const Dev& d, int bw, int nb, size_t smem, cudaStream_t s);  // lfba_chol.cu
 
-void part_plan_destroy(PartPlan* p) {
-  if (!p) return;
-  cudaFree(p->bounds);
-  cudaFree(p->row_c02);
-  cudaFree(p->row_off2);
-  cudaFree(p->Lsep);
-  cudaFree(p->X);
-  cudaFree(p->dinv);
-  cudaFree(p->S2);
-  cudaFree(p->y2);
-  delete p;
-}
+void part_plan_destroy(PartPlan* p) { delete p; }
 
 // Decides whether the partitioned path applies (enough frames per partition, shared memory) and builds its buffers.
 PartPlan* part_plan_create(const Dev& d, int bw, cudaStream_t s) {
@@ -313,27 +303,26 @@ PartPlan* part_plan_create(const Dev& d, int bw, cudaStream_t s) {
   p->smem_red = banded_smem_bytes(d2, bw2, nb);
   if (p->smem_red == 0) return p;
   const int M = 12 * bw + nb;
-  cudaMalloc(&p->bounds, (P + 1) * sizeof(int));
-  cudaMalloc(&p->row_c02, n2_aug * sizeof(int));
-  cudaMalloc(&p->row_off2, (n2_aug + 1) * sizeof(long long));
-  cudaMalloc(&p->Lsep, (size_t)F * 6 * bw * 6 * sizeof(double));
-  cudaMalloc(&p->X, (size_t)P * M * M * sizeof(double));
-  cudaMalloc(&p->dinv, (size_t)6 * F * sizeof(double));
-  cudaMalloc(&p->S2, (size_t)p->s2_len * sizeof(double));
-  cudaMalloc(&p->y2, (size_t)n2 * sizeof(double));
-  if (!p->bounds || !p->row_c02 || !p->row_off2 || !p->Lsep || !p->X || !p->dinv || !p->S2 || !p->y2) return p;
-  cudaMemcpyAsync(p->bounds, hb.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(p->row_c02, c0.data(), n2_aug * sizeof(int), cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(p->row_off2, off.data(), (n2_aug + 1) * sizeof(long long), cudaMemcpyHostToDevice, s);
-  cudaMemsetAsync(p->Lsep, 0, (size_t)F * 6 * bw * 6 * sizeof(double), s);
-  cudaMemsetAsync(p->X, 0, (size_t)P * M * M * sizeof(double), s);
+  p->bounds.alloc((size_t)P + 1);  // alloc_stream() == s (Solver::create_finish)
+  p->row_c02.alloc((size_t)n2_aug);
+  p->row_off2.alloc((size_t)n2_aug + 1);
+  p->Lsep.alloc((size_t)F * 6 * bw * 6);
+  p->X.alloc((size_t)P * M * M);
+  p->dinv.alloc((size_t)6 * F);
+  p->S2.alloc((size_t)p->s2_len);
+  p->y2.alloc((size_t)n2);
+  p->bounds.upload(hb.data(), (size_t)P + 1, s);
+  p->row_c02.upload(c0.data(), (size_t)n2_aug, s);
+  p->row_off2.upload(off.data(), (size_t)n2_aug + 1, s);
+  p->Lsep.zero(s);
+  p->X.zero(s);
   cudaStreamSynchronize(s);  // the host vectors go out of scope
-  d2.S = p->S2;
-  d2.row_off = reinterpret_cast<const int64_t*>(p->row_off2);
-  d2.row_c0 = p->row_c02;
-  d2.y = p->y2;
+  d2.S = p->S2.p;
+  d2.row_off = reinterpret_cast<const int64_t*>(p->row_off2.p);
+  d2.row_c0 = p->row_c02.p;
+  d2.y = p->y2.p;
   p->d2 = d2;
-  p->pd = PartDev{P, bw, F, npiv, p->bounds, p->Lsep, p->X, p->dinv, M};
+  p->pd = PartDev{P, bw, F, npiv, p->bounds.p, p->Lsep.p, p->X.p, p->dinv.p, M};
   cudaFuncSetAttribute(k_part_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
   cudaFuncSetAttribute(k_part_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
   cudaFuncSetAttribute(k_part_forward<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
@@ -356,7 +345,7 @@ int launch_part_solve(const Dev& d, PartPlan* p, cudaStream_t s) {
   d2.st = d.st;
   k_part_assemble<<<std::min(148, d2.n + 1), 64, 0, s>>>(d, p->pd, d2, p->s2_len);
   launch_chol_banded(d2, p->bw2, p->nb, p->smem_red, s);
-  k_part_backward<<<p->pd.P, 256, p->smem_bwd, s>>>(d, p->pd, p->y2);
+  k_part_backward<<<p->pd.P, 256, p->smem_bwd, s>>>(d, p->pd, p->y2.p);
   return 4;
 }
 

@@ -10,15 +10,14 @@ namespace lfba {
 
 namespace {
 
-struct Temp {
+struct Temp {  // CUB scratch
+  DevBuf<unsigned char> buf;
   void* p = nullptr;
   size_t bytes = 0;
-  ~Temp() { if (p) cudaFreeAsync(p, alloc_stream()); }
   void reserve(size_t b) {
     if (b > bytes) {
-      if (p) cudaFreeAsync(p, alloc_stream());
-      p = nullptr;
-      LFBA_CUDA(cudaMallocAsync(&p, b, alloc_stream()));
+      buf.alloc(b);
+      p = buf.p;
       bytes = b;
     }
   }
@@ -293,6 +292,7 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
   ix.F = F;
   Temp tmp;
   int64_t nl = 0;
+  bool pending_copy_in = false;
   const bool dbg = std::getenv("LFBA_DEBUG") != nullptr;
   double tp = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   auto phase = [&](const char* name) {
@@ -303,44 +303,76 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
     tp = t;
   };
 
-  // raw input (input order); the ox/oy/mx/my staging buffers live only until the indexed copies exist
+  // raw input (input order); the ox/oy/mx/my staging buffers live only until the indexed copies exist.
+  // The six host arrays go up on a SEPARATE copy stream in the order the indexing consumes them — lens centres first,
+  // indices next, observed points last — one cudaMemcpyAsync per array with an event behind each group, so that the lens
+  // table, the sortedness check and the track tables are built while the remaining arrays are still crossing PCIe
+  // (4.5 GB at the 1M x 1000 scene: the upload IS the end-to-end time, everything else hides behind it).
+  auto hnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double th0 = hnow();
   DevBuf<double> ox(N), oy(N), mx(N), my(N);
   ix.point_in.alloc(N);
   ix.frame_in.alloc(N);
-  ox.upload(pb.obs_x, N, s);
-  oy.upload(pb.obs_y, N, s);
-  mx.upload(pb.ml_x, N, s);
-  my.upload(pb.ml_y, N, s);
-  ix.point_in.upload(pb.point_idx, N, s);
-  ix.frame_in.upload(pb.frame_idx, N, s);
   ix.obs_in.alloc(N);
   ix.lens_id_in.alloc(N);
-
   ix.pt_trk_begin.alloc((size_t)P + 1);
   ix.frm_begin.alloc((size_t)F + 1);
   DevBuf<int32_t> pt_count((size_t)P + 1), fr_count((size_t)F + 1);
   pt_count.zero(s);
   fr_count.zero(s);
-  phase("alloc+H2D");
+  struct CopyLane {  // copy stream + events, released on every exit path
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ready = nullptr, e_ml = nullptr, e_idx = nullptr, e_obs = nullptr, t0 = nullptr, t1 = nullptr;
+    ~CopyLane() {
+      if (cs) cudaStreamSynchronize(cs);
+      for (cudaEvent_t e : {ready, e_ml, e_idx, e_obs, t0, t1})
+        if (e) cudaEventDestroy(e);
+      if (cs) cudaStreamDestroy(cs);
+    }
+  } lane;
+  const double th1 = hnow();
+  LFBA_CUDA(cudaStreamCreateWithFlags(&lane.cs, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&lane.ready, &lane.e_ml, &lane.e_idx, &lane.e_obs})
+    LFBA_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  LFBA_CUDA(cudaEventCreate(&lane.t0));
+  LFBA_CUDA(cudaEventCreate(&lane.t1));
+  LFBA_CUDA(cudaEventRecord(lane.ready, s));  // the stream-ordered allocations above exist from here on
+  LFBA_CUDA(cudaStreamWaitEvent(lane.cs, lane.ready, 0));
+  LFBA_CUDA(cudaEventRecord(lane.t0, lane.cs));
+  const double th2 = hnow();
+  mx.upload(pb.ml_x, N, lane.cs);
+  my.upload(pb.ml_y, N, lane.cs);
+  LFBA_CUDA(cudaEventRecord(lane.e_ml, lane.cs));
+  ix.point_in.upload(pb.point_idx, N, lane.cs);
+  ix.frame_in.upload(pb.frame_idx, N, lane.cs);
+  LFBA_CUDA(cudaEventRecord(lane.e_idx, lane.cs));
+  ox.upload(pb.obs_x, N, lane.cs);
+  oy.upload(pb.obs_y, N, lane.cs);
+  LFBA_CUDA(cudaEventRecord(lane.e_obs, lane.cs));
+  LFBA_CUDA(cudaEventRecord(lane.t1, lane.cs));
+  ix.h2d_bytes = 40 * N;
+  if (dbg)
+    std::fprintf(stderr, "[lfba dbg]   host: allocations %.2f ms, copy stream + events %.2f ms, six memcpy enqueues %.2f ms\n",
+                 1e3 * (th1 - th0), 1e3 * (th2 - th1), 1e3 * (hnow() - th2));
+  phase("alloc+H2D enqueue");
   if (N > 0) {
-    k_copy_in<<<grid_for(N), 256, 0, s>>>(ox.p, oy.p, ix.obs_in.p, N);
-    ox.release();
-    oy.release();
-    // ---- index validation + "is the input already sorted by (point, frame)?" in one pass ----
-    DevBuf<int> flags2(3);
-    flags2.zero(s);
-    k_check_sorted<<<grid_for(N), 256, 0, s>>>(ix.point_in.p, ix.frame_in.p, flags2.p, flags2.p + 1, P, F, N);
     // ---- distinct lenses: exact hash table on the (mx, my) bit patterns ----
     int cap = 1 << 16;
     while (cap < (1 << 24) && (int64_t)cap < 4 * std::min<int64_t>(N, (int64_t)1 << 22)) cap <<= 1;
     DevBuf<unsigned long long> keyA(cap), keyB(cap);
     DevBuf<int32_t> slot_of(N), occ((size_t)cap + 1), oid((size_t)cap + 1);
+    DevBuf<int> flags2(3);
+    flags2.zero(s);
     LFBA_CUDA(cudaMemsetAsync(keyA.p, 0xff, (size_t)cap * 8, s));
     LFBA_CUDA(cudaMemsetAsync(keyB.p, 0xff, (size_t)cap * 8, s));
     occ.zero(s);
+    LFBA_CUDA(cudaStreamWaitEvent(s, lane.e_ml, 0));
     k_lens_insert<<<grid_for(N), 256, 0, s>>>(mx.p, my.p, keyA.p, keyB.p, (uint32_t)(cap - 1), slot_of.p, flags2.p + 2, N);
     k_lens_mark<<<grid_for(cap), 256, 0, s>>>(keyA.p, keyB.p, occ.p, cap);
     exclusive_sum(tmp, occ.p, oid.p, (size_t)cap + 1, s);
+    // ---- index validation + "is the input already sorted by (point, frame)?" in one pass ----
+    LFBA_CUDA(cudaStreamWaitEvent(s, lane.e_idx, 0));
+    k_check_sorted<<<grid_for(N), 256, 0, s>>>(ix.point_in.p, ix.frame_in.p, flags2.p, flags2.p + 1, P, F, N);
     int h_flags[3] = {0, 0, 0};
     int32_t h_nl = 0;
     flags2.download(h_flags, 3, s);
@@ -352,12 +384,11 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
     ix.lens_xy.alloc((size_t)2 * std::max(1, ix.NL));
     k_lens_table<<<grid_for(cap), 256, 0, s>>>(keyA.p, keyB.p, occ.p, oid.p, ix.lens_xy.p, cap);
     k_lens_assign<<<grid_for(N), 256, 0, s>>>(slot_of.p, oid.p, ix.lens_id_in.p, N);
-    mx.release();
-    my.release();
     nl += 8;
-    phase("lenses (hash)");
+    phase("lenses (hash) + sortedness");
     // ---- order by (point, frame) ----
     DevBuf<uint64_t> k1(N);
+    bool copied_in = false;
     ix.presorted = h_flags[0] == 0;
     if (ix.presorted) {
       // the caller's order is already (point, frame)-major: no sort, no copy — the sorted view IS the input view
@@ -366,6 +397,10 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
       ix.lens_id_sorted = ix.lens_id_in.p;
       nl += 1;
     } else {
+      // the gather below reads the observed points: they are the last arrays to arrive
+      LFBA_CUDA(cudaStreamWaitEvent(s, lane.e_obs, 0));
+      k_copy_in<<<grid_for(N), 256, 0, s>>>(ox.p, oy.p, ix.obs_in.p, N);
+      copied_in = true;
       // radix sort is stable, so observations keep their input order inside a track
       DevBuf<uint64_t> k0(N);
       DevBuf<int32_t> v0(N);
@@ -401,6 +436,9 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
     LFBA_CUDA(cudaMemcpyAsync(ix.trk_begin.p + T, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
     nl += 3;
     phase("tracks");
+    // CSR / orders / pairs below do not touch the observed points; they are interleaved into obs_in at the very end
+    // (see the end of this function), when their upload — the last one — has landed.
+    pending_copy_in = !copied_in;
   } else {
     ix.T = 0;
     ix.NL = 0;
@@ -475,8 +513,22 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
       nl += 8;
     }
   }
+  if (N > 0) {
+    if (pending_copy_in) {
+      LFBA_CUDA(cudaStreamWaitEvent(s, lane.e_obs, 0));
+      k_copy_in<<<grid_for(N), 256, 0, s>>>(ox.p, oy.p, ix.obs_in.p, N);
+      nl += 1;
+    }
+    // the staging buffers are freed stream-ordered on s: s must be behind the copy stream first
+    LFBA_CUDA(cudaStreamWaitEvent(s, lane.e_obs, 0));
+  }
   LFBA_CUDA(cudaStreamSynchronize(s));
-  phase("pairs");
+  LFBA_CUDA(cudaStreamSynchronize(lane.cs));
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, lane.t0, lane.t1) == cudaSuccess) ix.h2d_ms = ms;
+  }
+  phase("pairs + last upload");
   if (launches) *launches += nl;
 }
 

@@ -158,6 +158,21 @@ struct Solver {
   bool ev_made = false;
   bool prof = false;
   LmState h_state{};
+  double t_dbg = 0;
+  void dbg_phase(const char* name) {  // LFBA_DEBUG: host wall time of the set-up phases (with a stream drain each)
+    if (!std::getenv("LFBA_DEBUG")) return;
+    cudaStreamSynchronize(stream);
+    const double t = now_s();
+    cudaMemPool_t pool;
+    unsigned long long res = 0, used = 0, thr = 0;
+    cudaDeviceGetDefaultMemPool(&pool, device);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    std::fprintf(stderr, "[lfba dbg] setup %-28s %8.2f ms   pool reserved %.2f GB used %.2f GB threshold %.3g\n", name,
+                 1e3 * (t - (t_dbg > 0 ? t_dbg : t_create0)), res / 1e9, used / 1e9, (double)thr);
+    t_dbg = t;
+  }
 
   ~Solver() {
     cudaSetDevice(device);
@@ -191,10 +206,10 @@ struct Solver {
       throw CudaError("no CUDA device: the LF-BA path has no CPU fallback", LFBA_NO_DEVICE);
     if (o.device >= 0) device = o.device; else LFBA_CUDA(cudaGetDevice(&device));
     LFBA_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    LFBA_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) throw CudaError("device is not sm_100-class: kernels are built for sm_100a only", LFBA_NO_DEVICE);
-    sms = prop.multiProcessorCount;
+    int cc_major = 0;  // attribute queries: cudaGetDeviceProperties costs milliseconds per call
+    LFBA_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    if (cc_major < 10) throw CudaError("device is not sm_100-class: kernels are built for sm_100a only", LFBA_NO_DEVICE);
+    LFBA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     if (shared_stream) {
       stream = shared_stream;
       sh.owned = false;
@@ -211,7 +226,9 @@ struct Solver {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
       }
     }
+    dbg_phase("device+stream");
     build_index(pb, ix, stream, &launches);
+    dbg_phase("build_index");
     const int P = ix.P, F = ix.F;
     const bool recalib = calib_type == LFBA_RECALIBRATION;
     const bool use_constraints = rpoints && !recalib && pb.n_constraints > 0;  // :916
@@ -255,6 +272,7 @@ struct Solver {
     for (int f = 0; f < F; ++f) h_fa[f] = ix.h_frame_count[f] > 0 ? 1 : 0;
     h_fa[F] = ix.bandwidth;
     LFBA_CUDA(cudaStreamSynchronize(stream));  // the host vectors above go out of scope
+    dbg_phase("coupled points + flags");
   }
 
   // ---- set-up, step 2: with the frame flags / bandwidth / observation count of ALL shards known ----
@@ -311,6 +329,7 @@ struct Solver {
     tile_first.alloc(n_tiles);
     tile_first.upload(h_tf.data(), n_tiles, stream);
 
+    dbg_phase("layout");
     // ---- buffers ----
     red_len = S_len + 3 * (size_t)n + SS_COUNT + (size_t)nranks;
     es_len = ES_COUNT + (size_t)nranks;
@@ -367,7 +386,9 @@ struct Solver {
       d.grid_eval = std::max(1, (int)std::min<int64_t>(2 * sms, (rounds + 3) / 4));
     }
     part_eval.alloc((size_t)d.grid_eval * 64);
+    dbg_phase("buffers");
     build_stream(ix, lanes, stream, &launches);
+    dbg_phase("packed stream");
     {
       // frames that have tracks ON THIS SHARD: a shard of a multi-GPU solve touches F / nranks of them, and one CTA per
       // frame would leave most SMs idle — split the frames' track lists over several CTAs then
@@ -419,9 +440,11 @@ struct Solver {
     ev_made = true;
     prepare_device_kernels();
     prepare_eval_kernels();
+    dbg_phase("events + kernel attributes");
     part_plan = part_plan_create(d, band_frames, stream);
     LFBA_CUDA(cudaStreamSynchronize(stream));
     LFBA_CUDA(cudaGetLastError());
+    dbg_phase("partition plan");
     setup_time = now_s() - t_create0;
   }
 
@@ -586,7 +609,6 @@ struct Group {
     if (!sh.empty()) cudaSetDevice(sh[0]->device);
     if (ev_made)
       for (auto& e : ev_round) cudaEventDestroy(e);
-    if (h_done) cudaFreeHost(h_done);
     while (!sh.empty()) sh.pop_back();  // reverse order: shard 0 owns the stream the emulated shards share
     if (comm && own_comm && !(comm_aborted && comm_aborted->load())) Nccl::get().CommDestroy(comm);
   }
@@ -674,9 +696,16 @@ struct Group {
       n_all = (int64_t)(h_n + 0.5);
     }
     for (auto& s : sh) s->create_finish(fa, n_all);
-    LFBA_CUDA(cudaMallocHost(&h_done, 4 * sizeof(int)));
+    h_done = pinned_flags();
     for (auto& e : ev_round) LFBA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ev_made = true;
+  }
+  // four pinned ints per host thread for the `done` polling, allocated once (cudaMallocHost costs about a millisecond);
+  // a Group only uses them inside run(), which blocks its thread
+  static int* pinned_flags() {
+    static thread_local int* p = nullptr;
+    if (!p) LFBA_CUDA(cudaMallocHost(&p, 4 * sizeof(int)));
+    return p;
   }
 
   void set_parameters(const double* c, const double* v, const double* p) {
@@ -785,6 +814,10 @@ struct Group {
       sum->num_lenses = a.ix.NL;
       for (size_t r = 0; r < sh.size(); ++r) sum->gpu_launches += sh[r]->launches - launches0[r];
       sum->setup_time_s = a.setup_time;
+      for (auto& q : sh) {
+        sum->h2d_bytes += q->ix.h2d_bytes;
+        sum->h2d_ms = std::max(sum->h2d_ms, q->ix.h2d_ms);
+      }
       sum->solve_time_s = now_s() - t0;
       sum->solve_gpu_ms = run_ms;
       for (int k = 0; k < LFBA_NUM_KERNEL_TIMERS; ++k) {
@@ -872,11 +905,12 @@ int lfba_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   int ok = 0;
   for (int i = 0; i < n; ++i) {
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major >= 10) ++ok;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major >= 10) ++ok;
   }
   return ok;
 }
+void lfba_trim_cache(void) { BlockCache::get().trim(); }
 int lfba_comm_unique_id(char out[128]) {
   Nccl& n = Nccl::get();
   if (!n.ok) {
@@ -1199,7 +1233,7 @@ int lfba_solve(const lfba_problem* pb, const lfba_options* opt_in, double* cam, 
           LFBA_CUDA(cudaStreamSynchronize(s.stream));
           s.create_finish(fa, (int64_t)(h_n + 0.5));
         }
-        LFBA_CUDA(cudaMallocHost(&g.h_done, 4 * sizeof(int)));
+        g.h_done = Group::pinned_flags();
         for (auto& e : g.ev_round) LFBA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         g.ev_made = true;
         g.set_parameters(cam, views, points);
