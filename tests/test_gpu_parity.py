@@ -346,12 +346,32 @@ def test_recalib_projected_line_search_contracts_like_the_oracle(gpu, case):
     cam0[1] = sc.camera_true[1] / 1.3 * 0.9999
     init = (cam0, sc.views_init, sc.points_init)
     cam, vw, pt, s = api.solve(sc.problem, *init)
-    spread, (ocam, ovw, opt_, os_) = _oracle_spread(sc.problem, init)
-    ls_o = [r["line_search_iterations"] for r in os_["iterations"]]
-    ls_g = [r["line_search_iterations"] for r in s["iterations"]]
-    assert max(ls_o) >= 2 and sum(1 for v in ls_o if v > 0) >= 2, ls_o  # the scene does exercise the contraction
+    # the oracle twice (1 thread / all threads): near convergence the Armijo decisions of this scene hang on cost differences
+    # of 1e-13 relative, where the reference algorithm itself depends on its summation order; rows are compared as far as
+    # the oracle agrees with itself
+    o1 = ob.solve(sc.problem, *init, threads=1)
+    oN = ob.solve(sc.problem, *init, threads=max(2, ob.max_threads()))
+    spread = [np.abs(x - y) for x, y in zip(o1[:3], oN[:3])]
+    ocam, ovw, opt_, os_ = oN
+    key = lambda r: (r["line_search_iterations"], r["step_is_successful"])
+    stable = 0
+    for ra, rb in zip(o1[3]["iterations"], oN[3]["iterations"]):
+        if key(ra) != key(rb):
+            break
+        stable += 1
+    ls_o = [r["line_search_iterations"] for r in os_["iterations"]][:stable]
+    ls_g = [r["line_search_iterations"] for r in s["iterations"]][:stable]
+    assert stable >= 4 and max(ls_o) >= 2, (stable, ls_o)  # the scene does exercise the contraction
     assert ls_g == ls_o, (ls_g, ls_o)
-    _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread, name=f"recalib_ls:{case}")
+    for r, o in list(zip(s["iterations"], os_["iterations"]))[:stable]:
+        assert r["step_is_successful"] == o["step_is_successful"]
+        assert abs(r["cost"] - o["cost"]) <= REL * o["cost"], (r["iteration"], r["cost"], o["cost"])
+        assert abs(r["trust_region_radius"] - o["trust_region_radius"]) <= 1e-6 * o["trust_region_radius"]
+    if stable == o1[3]["num_iterations"] == oN[3]["num_iterations"]:
+        _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread, name=f"recalib_ls:{case}")
+    else:
+        _strict_report(f"recalib_ls:{case}", s, (cam, vw, pt), os_, (ocam, ovw, opt_), {"oracle_self_consistent_rows": stable})
+        assert abs(s["final_cost"] - os_["final_cost"]) <= 1e-7 * os_["final_cost"]
     assert cam[0] == cam0[0] and cam[2] == cam0[2]
     assert cam[1] <= 1.3 * cam0[1] * (1 + 1e-15) and abs(cam[1] - 1.3 * cam0[1]) <= 1e-9 * cam[1]  # ends ON the bound
 
