@@ -238,6 +238,38 @@ int lfba_eval(const lfba_problem* problem, const lfba_options* options, const do
               double* jac_view, double* jac_point, double* cost, lfba_reproj_stats* stats,
               double inlier_threshold);
 
+/* ---- the step before the solve: observation generation ----
+ * What CameraCalibration::projectPointsToRawImage (src/CameraCalibration.cpp:640-769) reads from the MicroLensGrid
+ * (src/MicroLensGrid/MicroLensGrid.h:48-73, maps built by defineMlMaps :338-421), flattened. Host memory. */
+typedef struct lfba_lens_grid {
+  int32_t raw_width, raw_height;   /* rawWidth, rawHeight */
+  int32_t scale;                   /* depth_to_raw_im_scale */
+  float lens_diameter;             /* mlGrid->lensDiameter (px) */
+  float lens_validity_radius_2;    /* mlGrid->lensValidityRadius_2 */
+  float rotation;                  /* mlGrid->rotation (rad), used for the epipolar web when rotation_on_grid */
+  int32_t rotation_on_grid;        /* mlGrid->isRotationOnGrid() */
+  int32_t n_lenses;
+  const float* lens_cx;            /* MicroLens::centerX of mlLensList[i] */
+  const float* lens_cy;
+  const int32_t* map_next;         /* [raw_width * raw_height] index of mapNextMl[pixel] in mlLensList, -1 = NULL */
+  const int32_t* map_ml;           /* [raw_width * raw_height] index of mapMlPointer[pixel], -1 = NULL */
+} lfba_lens_grid;
+
+/* Drop-in for the loops of projectPointsToRawImage: features are given frame-major like the reference walks them
+ * (frames[i].imageCoordinates[p] -> feat_x/y, virtualDepthValues[i][p] -> vdepth, i -> frame_idx,
+ * index of frames[i].objectCoordinatesByID[p] in p3d_w -> point_idx); the outputs are the concatenation over frames of
+ * rawImageCoordinates / microLensCenter / objectCoordinatesByRawID in the reference's order — exactly the observation
+ * arrays of lfba_problem. float32 arithmetic as in the reference: lens selection bit-exact, coordinates float32-exact.
+ * Two-call pattern: capacity = 0 only counts (*n_obs); features must lie inside the total-focus image. */
+int lfba_project_to_raw(const lfba_lens_grid* grid, int64_t n_features, const double* feat_x, const double* feat_y,
+                        const double* vdepth, const int32_t* frame_idx, const int32_t* point_idx, int64_t capacity,
+                        double* obs_x, double* obs_y, double* ml_x, double* ml_y, int32_t* out_point_idx,
+                        int32_t* out_frame_idx, int64_t* n_obs, int32_t device);
+/* The web of epipolar lines of CameraCalibration::defineEpiPolarLines (:521-634), host-side: lines3 [n][3] = (ex, ey,
+ * base-line length) grouped by float-equal length in ascending order, group_begin [n_groups + 1]. NULL arrays: count only. */
+int lfba_epipolar_web(float lens_diameter, float rotation, int32_t rotation_on_grid, int32_t* n_lines, int32_t* n_groups,
+                      double* lines3, int32_t* group_begin);
+
 /* ---- device-resident session API (what lfba_solve / lfba_eval are built from) ---- */
 int lfba_comm_unique_id(char out[128]);
 /* Persistent NCCL communicator for this rank (collective: every rank calls it). Pass it in lfba_comm.handle so that

@@ -22,7 +22,7 @@ _lib = None
 _EXPORTS = ["lfba_version", "lfba_last_error", "lfba_status_string", "lfba_options_init", "lfba_device_count", "lfba_trim_cache",
             "lfba_solve", "lfba_eval", "lfba_comm_unique_id", "lfba_comm_create", "lfba_comm_destroy", "lfba_solver_create", "lfba_solver_set_parameters",
             "lfba_solver_get_parameters", "lfba_solver_run", "lfba_solver_time_eval", "lfba_solver_track_blocks",
-            "lfba_measure_fp64_peak", "lfba_solver_destroy"]
+            "lfba_measure_fp64_peak", "lfba_solver_destroy", "lfba_project_to_raw", "lfba_epipolar_web"]
 
 
 def load():
@@ -60,6 +60,10 @@ def load():
     L.lfba_solver_track_blocks.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), dp, dp, ip, ip]
     L.lfba_measure_fp64_peak.argtypes = [C.c_int, dp]
     L.lfba_solver_destroy.argtypes = [C.c_void_p]
+    i64p = C.POINTER(C.c_int64)
+    L.lfba_project_to_raw.argtypes = [C.POINTER(capi.LensGridStruct), C.c_int64, dp, dp, dp, ip, ip, C.c_int64, dp, dp, dp, dp,
+                                      ip, ip, i64p, C.c_int32]
+    L.lfba_epipolar_web.argtypes = [C.c_float, C.c_float, C.c_int32, ip, ip, dp, ip]
     _lib = L
     return L
 
@@ -132,6 +136,44 @@ def evaluate(pa: capi.ProblemArrays, camera, views, points, jacobians=True, opti
     return {"residuals": res.reshape(n, 2), "jac_camera": jc, "jac_view": jv, "jac_point": jp, "cost": cost.value,
             "stats": {"std_x": st.std_x, "std_y": st.std_y, "mae_x": st.mae_x, "mae_y": st.mae_y,
                       "num_points": st.num_points, "num_inliers": st.num_inliers}}
+
+
+def project_to_raw(grid: "capi.LensGrid", feat_x, feat_y, vdepth, frame_idx=None, point_idx=None, device=-1):
+    """lfba_project_to_raw: the observation arrays projectPointsToRawImage (src/CameraCalibration.cpp:640-769) produces
+    for a frame-major feature list, in the reference's order. Returns a dict of NumPy arrays."""
+    L = load()
+    fx = np.ascontiguousarray(feat_x, np.float64)
+    fy = np.ascontiguousarray(feat_y, np.float64)
+    vd = np.ascontiguousarray(vdepth, np.float64)
+    m = fx.size
+    fi = None if frame_idx is None else np.ascontiguousarray(frame_idx, np.int32)
+    pi = None if point_idx is None else np.ascontiguousarray(point_idx, np.int32)
+    g = grid.as_struct()
+    n = C.c_int64(0)
+    _check(L.lfba_project_to_raw(C.byref(g), m, capi._dp(fx), capi._dp(fy), capi._dp(vd), capi._ip(fi), capi._ip(pi), 0, None,
+                                 None, None, None, None, None, C.byref(n), device), "lfba_project_to_raw")
+    k = n.value
+    out = {"obs_x": np.zeros(k), "obs_y": np.zeros(k), "ml_x": np.zeros(k), "ml_y": np.zeros(k),
+           "point_idx": np.zeros(k, np.int32), "frame_idx": np.zeros(k, np.int32)}
+    if k:
+        _check(L.lfba_project_to_raw(C.byref(g), m, capi._dp(fx), capi._dp(fy), capi._dp(vd), capi._ip(fi), capi._ip(pi), k,
+                                     capi._dp(out["obs_x"]), capi._dp(out["obs_y"]), capi._dp(out["ml_x"]),
+                                     capi._dp(out["ml_y"]), capi._ip(out["point_idx"]), capi._ip(out["frame_idx"]),
+                                     C.byref(n), device), "lfba_project_to_raw")
+    return out
+
+
+def epipolar_web(lens_diameter, rotation=0.0, rotation_on_grid=False):
+    """lfba_epipolar_web (host): (lines [n, 3] = ex, ey, base-line length; group_begin [n_groups + 1])."""
+    L = load()
+    nl, ng = C.c_int32(0), C.c_int32(0)
+    _check(L.lfba_epipolar_web(float(lens_diameter), float(rotation), int(bool(rotation_on_grid)), C.byref(nl), C.byref(ng),
+                               None, None), "lfba_epipolar_web")
+    lines = np.zeros((nl.value, 3))
+    gb = np.zeros(ng.value + 1, np.int32)
+    _check(L.lfba_epipolar_web(float(lens_diameter), float(rotation), int(bool(rotation_on_grid)), C.byref(nl), C.byref(ng),
+                               capi._dp(lines), capi._ip(gb)), "lfba_epipolar_web")
+    return lines, gb
 
 
 def comm_unique_id() -> bytes:

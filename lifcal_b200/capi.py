@@ -102,6 +102,43 @@ class Comm(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_char * 128), ("handle", C.c_void_p)]
 
 
+c_float_p = C.POINTER(C.c_float)
+
+
+class LensGridStruct(C.Structure):
+    _fields_ = [("raw_width", C.c_int32), ("raw_height", C.c_int32), ("scale", C.c_int32),
+                ("lens_diameter", C.c_float), ("lens_validity_radius_2", C.c_float), ("rotation", C.c_float),
+                ("rotation_on_grid", C.c_int32), ("n_lenses", C.c_int32),
+                ("lens_cx", c_float_p), ("lens_cy", c_float_p), ("map_next", c_int32_p), ("map_ml", c_int32_p)]
+
+
+class LensGrid:
+    """NumPy-owning mirror of lfba_lens_grid: what projectPointsToRawImage reads from the reference's MicroLensGrid."""
+
+    def __init__(self, raw_width, raw_height, scale, lens_diameter, rotation, rotation_on_grid, lens_cx, lens_cy,
+                 map_next, map_ml, lens_border=1.0):
+        self.raw_width, self.raw_height, self.scale = int(raw_width), int(raw_height), int(scale)
+        self.lens_diameter = np.float32(lens_diameter)
+        r = np.float32(self.lens_diameter * np.float32(0.5) - np.float32(lens_border))  # MicroLensGrid.cpp:110-111
+        self.lens_validity_radius_2 = np.float32(r * r)
+        self.rotation, self.rotation_on_grid = np.float32(rotation), int(bool(rotation_on_grid))
+        self.lens_cx = np.ascontiguousarray(lens_cx, np.float32)
+        self.lens_cy = np.ascontiguousarray(lens_cy, np.float32)
+        self.map_next = np.ascontiguousarray(map_next, np.int32).ravel()
+        self.map_ml = np.ascontiguousarray(map_ml, np.int32).ravel()
+        assert self.map_next.size == self.raw_width * self.raw_height == self.map_ml.size
+
+    def as_struct(self) -> LensGridStruct:
+        g = LensGridStruct()
+        g.raw_width, g.raw_height, g.scale = self.raw_width, self.raw_height, self.scale
+        g.lens_diameter, g.lens_validity_radius_2 = float(self.lens_diameter), float(self.lens_validity_radius_2)
+        g.rotation, g.rotation_on_grid, g.n_lenses = float(self.rotation), self.rotation_on_grid, int(self.lens_cx.size)
+        g.lens_cx = self.lens_cx.ctypes.data_as(c_float_p)
+        g.lens_cy = self.lens_cy.ctypes.data_as(c_float_p)
+        g.map_next, g.map_ml = _ip(self.map_next), _ip(self.map_ml)
+        return g
+
+
 class SceneSpec(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64), ("n_points", C.c_int32), ("n_frames", C.c_int32), ("window", C.c_int32),

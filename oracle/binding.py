@@ -40,6 +40,14 @@ def lib():
         L.oracle_time_eval.argtypes = [C.POINTER(capi.Problem), c_double_p, c_double_p, c_double_p, C.c_int,
                                        C.c_int, c_double_p]
         L.oracle_max_threads.restype = C.c_int
+        i32p, f32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int64)
+        L.oracle_epi_web.argtypes = [C.c_float, C.c_float, C.c_int, i32p, i32p, c_double_p, i32p]
+        L.oracle_epi_make.argtypes = [C.c_double, C.c_double, C.c_double, c_double_p]
+        L.oracle_epi_add.argtypes = [c_double_p, c_double_p, c_double_p]
+        L.oracle_project_to_raw.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int32,
+                                            f32p, f32p, i32p, i32p, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_int64,
+                                            c_double_p, c_double_p, c_double_p, c_double_p, i64p]
+        L.oracle_project_to_raw.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -62,6 +70,9 @@ def ref_lib():
                                         c_double_p, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int,
                                         c_double_p]
         R.ref_pose_matrix.argtypes = [c_double_p, c_double_p]
+        if hasattr(R, "ref_epi_make"):
+            R.ref_epi_make.argtypes = [C.c_double, C.c_double, C.c_double, c_double_p]
+            R.ref_epi_add.argtypes = [c_double_p, c_double_p, c_double_p]
         _ref = R
     return _ref
 
@@ -158,3 +169,36 @@ def time_eval(pa: capi.ProblemArrays, camera, views, points, reps=1, threads=0) 
 
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
+
+
+# ---- N2: epipolar web + projection of total-focus features into the micro images (oracle/project_raw.hpp) ----
+def epi_web(lens_diameter, rotation=0.0, rotation_on_grid=False):
+    L = lib()
+    nl, ng = C.c_int32(0), C.c_int32(0)
+    L.oracle_epi_web(float(lens_diameter), float(rotation), int(bool(rotation_on_grid)), C.byref(nl), C.byref(ng), None, None)
+    lines = np.zeros((nl.value, 3))
+    gb = np.zeros(ng.value + 1, np.int32)
+    L.oracle_epi_web(float(lens_diameter), float(rotation), int(bool(rotation_on_grid)), C.byref(nl), C.byref(ng),
+                     capi._dp(lines), capi._ip(gb))
+    return lines, gb
+
+
+def project_to_raw(grid: "capi.LensGrid", feat_x, feat_y, vdepth):
+    """Returns obs_x, obs_y, ml_x, ml_y and the feature index of every observation, in the reference's order."""
+    L = lib()
+    fx = np.ascontiguousarray(feat_x, np.float64)
+    fy = np.ascontiguousarray(feat_y, np.float64)
+    vd = np.ascontiguousarray(vdepth, np.float64)
+    f32p, i32p, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    args = [grid.raw_width, grid.raw_height, grid.scale, float(grid.lens_diameter), float(grid.lens_validity_radius_2),
+            float(grid.rotation), grid.rotation_on_grid, int(grid.lens_cx.size), grid.lens_cx.ctypes.data_as(f32p),
+            grid.lens_cy.ctypes.data_as(f32p), capi._ip(grid.map_next), capi._ip(grid.map_ml), fx.size, capi._dp(fx),
+            capi._dp(fy), capi._dp(vd)]
+    n = L.oracle_project_to_raw(*args, 0, None, None, None, None, None)
+    out = {k: np.zeros(n) for k in ("obs_x", "obs_y", "ml_x", "ml_y")}
+    feat = np.zeros(n, np.int64)
+    if n:
+        L.oracle_project_to_raw(*args, n, capi._dp(out["obs_x"]), capi._dp(out["obs_y"]), capi._dp(out["ml_x"]),
+                                capi._dp(out["ml_y"]), feat.ctypes.data_as(i64p))
+    out["feature"] = feat
+    return out

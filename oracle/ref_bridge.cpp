@@ -13,6 +13,8 @@
 #include <cstdint>
 
 #include "BundleAdjustment/BundleAdjustment.h"
+// the reference's own EpiPolarLine class, compiled in place (no dependencies): pins the web primitives of the N2 oracle
+#include "MicroLensGrid/EpiPolarLine.cpp"
 
 extern "C" {
 
@@ -99,5 +101,23 @@ void ref_pose_matrix(const double* view, double* rt16) {
   Eigen::Matrix<double, 4, 4> RT = RigidBody::getTransformationMatrix<double>(a, t);
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) rt16[4 * i + j] = RT(i, j);
+}
+
+// EpiPolarLine::EpiPolarLine / EpiPolarLine::add of the reference (src/MicroLensGrid/EpiPolarLine.cpp:16-46)
+void ref_epi_make(double x, double y, double dist, double out[3]) {
+  EpiPolarLine e(x, y, dist, 2.0f);
+  out[0] = e.epiLine[0];
+  out[1] = e.epiLine[1];
+  out[2] = e.baseLineDist;
+}
+void ref_epi_add(const double a[3], const double b[3], double out[3]) {
+  EpiPolarLine ea(1, 0, 1, 2.0f), eb(1, 0, 1, 2.0f);
+  ea.epiLine[0] = a[0]; ea.epiLine[1] = a[1]; ea.baseLineDist = a[2];
+  eb.epiLine[0] = b[0]; eb.epiLine[1] = b[1]; eb.baseLineDist = b[2];
+  EpiPolarLine* r = ea.add(eb);
+  out[0] = r->epiLine[0];
+  out[1] = r->epiLine[1];
+  out[2] = r->baseLineDist;
+  delete r;
 }
 }

@@ -65,3 +65,27 @@ def random_blocks(rng, config, n, signs=False):
         pts[i] = R.T @ (pc[i] - views[i, 3:])
     obs = np.float32(ml + 8 * (rng.random((n, 2)) - 0.5)).astype(np.float64)
     return dict(spx=spx, spy=spx, scale=scale, cams=cams, views=views, points=pts, ml=ml, obs=obs)
+
+
+def make_lens_grid(raw=512, diameter=23.0, rotation=0.003, scale=2, seed=0):
+    """A Raytrix-like hexagonal micro-lens grid with the two pixel maps projectPointsToRawImage reads
+    (MicroLensGrid::createGrid / defineMlMaps, src/MicroLensGrid/MicroLensGrid.cpp:186-270, 338-421): float32 centres;
+    map_ml = lens whose valid micro image (radius D/2 - 1) covers the pixel, map_next = nearest lens. The maps are INPUTS of
+    the component under test, so a KD-tree stands in for the reference's ring search."""
+    from scipy.spatial import cKDTree
+    D = np.float32(diameter)
+    hy = np.float32(np.sqrt(0.75)) * D
+    ca, sa = np.float32(np.cos(rotation)), np.float32(np.sin(rotation))
+    n = int(raw / diameter) + 4
+    cs = []
+    for j in range(-2, int(raw / float(hy)) + 3):
+        for i in range(-2, n):
+            x = np.float32(i) * D + (np.float32(0.5) * D if j % 2 else np.float32(0))
+            y = np.float32(j) * hy
+            cs.append((np.float32(11.3) + x * ca - y * sa, np.float32(7.9) + x * sa + y * ca))
+    c = np.array(cs, np.float32)
+    yy, xx = np.mgrid[0:raw, 0:raw]
+    d, idx = cKDTree(c.astype(np.float64)).query(np.stack([xx.ravel(), yy.ravel()], 1).astype(np.float64))
+    g = capi.LensGrid(raw, raw, scale, D, rotation, True, c[:, 0], c[:, 1], idx.astype(np.int32), idx.astype(np.int32))
+    g.map_ml = np.where(d * d <= float(g.lens_validity_radius_2), idx, -1).astype(np.int32)
+    return g
