@@ -265,6 +265,15 @@ int lfba_project_to_raw(const lfba_lens_grid* grid, int64_t n_features, const do
                         const double* vdepth, const int32_t* frame_idx, const int32_t* point_idx, int64_t capacity,
                         double* obs_x, double* obs_y, double* ml_x, double* ml_y, int32_t* out_point_idx,
                         int32_t* out_frame_idx, int64_t* n_obs, int32_t device);
+/* Drop-in for CameraCalibration::initPlenopticParameters (src/CameraCalibration.cpp:456-498): fL_init = fph_init *
+ * pixel_size_totfoc, then the least-squares fit of bL = v B + bL0 over all (frame, feature) pairs k: v = vdepth[k]
+ * (virtualDepthValues), bL = fL Z / (Z - fL) with Z the camera-frame depth of point point_idx[k] in frame frame_idx[k]
+ * (views = Euler angles + translation of worldToCam as in lfba_solve); rows with v < 2 or bL < 0 do not count (:483-488).
+ * LFBA_FAILURE when fewer than two distinct valid virtual depths are left. */
+int lfba_init_plenoptic(double fph_init, double pixel_size_totfoc, int64_t n_pairs, const double* vdepth,
+                        const int32_t* frame_idx, const int32_t* point_idx, int32_t n_frames, const double* views6F,
+                        int32_t n_points, const double* points3P, double* fL_init, double* B_init, double* bL0_init,
+                        int32_t device);
 /* The web of epipolar lines of CameraCalibration::defineEpiPolarLines (:521-634), host-side: lines3 [n][3] = (ex, ey,
  * base-line length) grouped by float-equal length in ascending order, group_begin [n_groups + 1]. NULL arrays: count only. */
 int lfba_epipolar_web(float lens_diameter, float rotation, int32_t rotation_on_grid, int32_t* n_lines, int32_t* n_groups,

@@ -22,7 +22,7 @@ _lib = None
 _EXPORTS = ["lfba_version", "lfba_last_error", "lfba_status_string", "lfba_options_init", "lfba_device_count", "lfba_trim_cache",
             "lfba_solve", "lfba_eval", "lfba_comm_unique_id", "lfba_comm_create", "lfba_comm_destroy", "lfba_solver_create", "lfba_solver_set_parameters",
             "lfba_solver_get_parameters", "lfba_solver_run", "lfba_solver_time_eval", "lfba_solver_track_blocks",
-            "lfba_measure_fp64_peak", "lfba_solver_destroy", "lfba_project_to_raw", "lfba_epipolar_web"]
+            "lfba_measure_fp64_peak", "lfba_solver_destroy", "lfba_project_to_raw", "lfba_epipolar_web", "lfba_init_plenoptic"]
 
 
 def load():
@@ -64,6 +64,8 @@ def load():
     L.lfba_project_to_raw.argtypes = [C.POINTER(capi.LensGridStruct), C.c_int64, dp, dp, dp, ip, ip, C.c_int64, dp, dp, dp, dp,
                                       ip, ip, i64p, C.c_int32]
     L.lfba_epipolar_web.argtypes = [C.c_float, C.c_float, C.c_int32, ip, ip, dp, ip]
+    L.lfba_init_plenoptic.argtypes = [C.c_double, C.c_double, C.c_int64, dp, ip, ip, C.c_int32, dp, C.c_int32, dp, dp, dp, dp,
+                                      C.c_int32]
     _lib = L
     return L
 
@@ -161,6 +163,21 @@ def project_to_raw(grid: "capi.LensGrid", feat_x, feat_y, vdepth, frame_idx=None
                                      capi._dp(out["ml_y"]), capi._ip(out["point_idx"]), capi._ip(out["frame_idx"]),
                                      C.byref(n), device), "lfba_project_to_raw")
     return out
+
+
+def init_plenoptic(fph_init, pixel_size_totfoc, vdepth, frame_idx, point_idx, views, points, device=-1):
+    """lfba_init_plenoptic: (fL_init, B_init, bL0_init) of CameraCalibration::initPlenopticParameters (:456-498)."""
+    L = load()
+    vd = np.ascontiguousarray(vdepth, np.float64)
+    fi = np.ascontiguousarray(frame_idx, np.int32)
+    pi = np.ascontiguousarray(point_idx, np.int32)
+    vw = np.ascontiguousarray(views, np.float64).ravel()
+    pt = np.ascontiguousarray(points, np.float64).ravel()
+    fL, B, bL0 = C.c_double(0), C.c_double(0), C.c_double(0)
+    _check(L.lfba_init_plenoptic(float(fph_init), float(pixel_size_totfoc), vd.size, capi._dp(vd), capi._ip(fi), capi._ip(pi),
+                                 vw.size // 6, capi._dp(vw), pt.size // 3, capi._dp(pt), C.byref(fL), C.byref(B),
+                                 C.byref(bL0), device), "lfba_init_plenoptic")
+    return fL.value, B.value, bL0.value
 
 
 def epipolar_web(lens_diameter, rotation=0.0, rotation_on_grid=False):

@@ -14,6 +14,8 @@
 #include <cstring>
 #include <vector>
 
+#include <algorithm>
+
 #include "lfba_setup.cuh"
 
 namespace lfba {
@@ -257,6 +259,122 @@ extern "C" int lfba_project_to_raw(const lfba_lens_grid* grid, int64_t n_feature
         }
       }
     }  // device buffers are released (stream-ordered) before the stream goes away
+    return rc;
+  } catch (const CudaError& e) {
+    return e.code;
+  } catch (const std::exception&) {
+    return LFBA_CUDA_ERROR;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// N4: CameraCalibration::initPlenopticParameters (src/CameraCalibration.cpp:456-498) — fL_init = fPH_init * pixelSize,
+// then the linear model bL = v B + bL0 over all (frame, feature) pairs, bL = fL Z / (Z - fL) from the camera-frame depth
+// of the feature's 3-D point; rows with v < 2 or bL < 0 are zeroed (:483-488). The reference solves the N x 2 system by
+// a thin Jacobi SVD; for a full-rank two-column system the minimiser is the centred regression, computed here in two
+// fixed-order device passes (means, then centred second moments): no squared condition number, no atomics.
+// ------------------------------------------------------------------------------------------------------------------
+namespace lfba {
+namespace {
+__device__ __forceinline__ bool init_row(const double* views, const double* points, const double* vd, const int32_t* fi,
+                                         const int32_t* pi, int64_t k, double fL, double& v, double& b) {
+  double fe[kFrameStride];
+  frame_entry(views + 6 * (size_t)fi[k], fe);
+  double pc[3];
+  track_point(fe, points + 3 * (size_t)pi[k], pc);
+  v = vd[k];
+  b = (fL * pc[2]) / (pc[2] - fL);
+  return !(v < 2.0 || b < 0.0);
+}
+// pass 0: n, sum v, sum b over the valid rows; pass 1: sum (v - vm)^2, sum (v - vm)(b - bm). One partial per CTA.
+__global__ void __launch_bounds__(256) k_init_sums(const double* views, const double* points, const double* vd,
+                                                   const int32_t* fi, const int32_t* pi, int64_t n, double fL, int pass,
+                                                   double vm, double bm, double* part) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    double v, b;
+    if (!init_row(views, points, vd, fi, pi, k, fL, v, b)) continue;
+    if (pass == 0) {
+      a0 += 1.0;
+      a1 += v;
+      a2 += b;
+    } else {
+      a0 += (v - vm) * (v - vm);
+      a1 += (v - vm) * (b - bm);
+    }
+  }
+  __shared__ double red[8][3];
+  double vals[3] = {a0, a1, a2};
+  for (int q = 0; q < 3; ++q) {
+    double x = vals[q];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double x = 0.0;
+    for (int w = 0; w < 8; ++w) x += red[w][threadIdx.x];
+    part[3 * blockIdx.x + threadIdx.x] = x;
+  }
+}
+}  // namespace
+}  // namespace lfba
+
+extern "C" int lfba_init_plenoptic(double fph_init, double pixel_size_totfoc, int64_t n_pairs, const double* vdepth,
+                                   const int32_t* frame_idx, const int32_t* point_idx, int32_t n_frames, const double* views6F,
+                                   int32_t n_points, const double* points3P, double* fL_init, double* B_init, double* bL0_init,
+                                   int32_t device) {
+  if (n_pairs <= 0 || !vdepth || !frame_idx || !point_idx || !views6F || !points3P || !fL_init || !B_init || !bL0_init ||
+      n_frames <= 0 || n_points <= 0)
+    return LFBA_INVALID_ARGUMENT;
+  for (int64_t k = 0; k < n_pairs; ++k)
+    if (frame_idx[k] < 0 || frame_idx[k] >= n_frames || point_idx[k] < 0 || point_idx[k] >= n_points) return LFBA_INVALID_ARGUMENT;
+  try {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return LFBA_NO_DEVICE;
+    if (device >= 0) LFBA_CUDA(cudaSetDevice(device));
+    cudaStream_t s;
+    LFBA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    struct SG { cudaStream_t s; ~SG() { cudaStreamSynchronize(s); cudaStreamDestroy(s); } } sg{s};
+    alloc_stream() = s;
+    const double fL = fph_init * pixel_size_totfoc;  // :460
+    int rc = LFBA_OK;
+    {
+      const size_t n = (size_t)n_pairs;
+      const int grid = (int)std::min<size_t>(592, (n + 255) / 256);
+      DevBuf<double> vd(n), vw((size_t)6 * n_frames), pt((size_t)3 * n_points), part((size_t)3 * grid);
+      DevBuf<int32_t> fi(n), pi(n);
+      vd.upload(vdepth, n, s);
+      fi.upload(frame_idx, n, s);
+      pi.upload(point_idx, n, s);
+      vw.upload(views6F, (size_t)6 * n_frames, s);
+      pt.upload(points3P, (size_t)3 * n_points, s);
+      std::vector<double> h((size_t)3 * grid);
+      auto pass = [&](int which, double vm, double bm, double out[3]) {
+        k_init_sums<<<grid, 256, 0, s>>>(vw.p, pt.p, vd.p, fi.p, pi.p, n_pairs, fL, which, vm, bm, part.p);
+        LFBA_CUDA(cudaGetLastError());
+        part.download(h.data(), h.size(), s);
+        LFBA_CUDA(cudaStreamSynchronize(s));
+        out[0] = out[1] = out[2] = 0.0;
+        for (int b = 0; b < grid; ++b)  // fixed order
+          for (int q = 0; q < 3; ++q) out[q] += h[3 * (size_t)b + q];
+      };
+      double m[3], c[3];
+      pass(0, 0.0, 0.0, m);
+      if (!(m[0] >= 2.0)) {
+        rc = LFBA_FAILURE;  // fewer than two valid rows: the reference's SVD would return a rank-deficient minimum-norm answer
+      } else {
+        const double vm = m[1] / m[0], bm = m[2] / m[0];
+        pass(1, vm, bm, c);
+        if (!(c[0] > 0.0)) {
+          rc = LFBA_FAILURE;
+        } else {
+          *fL_init = fL;
+          *B_init = c[1] / c[0];
+          *bL0_init = bm - *B_init * vm;
+        }
+      }
+    }
     return rc;
   } catch (const CudaError& e) {
     return e.code;

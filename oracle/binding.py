@@ -202,3 +202,27 @@ def project_to_raw(grid: "capi.LensGrid", feat_x, feat_y, vdepth):
                                 capi._dp(out["ml_y"]), feat.ctypes.data_as(i64p))
     out["feature"] = feat
     return out
+
+
+# ---- N4: linear initialisation (numpy restatement of src/CameraCalibration.cpp:456-498) ----
+def init_plenoptic(fph_init, pixel_size_totfoc, vdepth, frame_idx, point_idx, views, points):
+    """a = [v 1] (N x 2), b = bL = fL Z / (Z - fL) with Z = (worldToCam X).z; rows with v < 2 or bL < 0 are zeroed in a AND
+    b (:483-488); x = thin-SVD least squares (:492, numpy lstsq is SVD-based). Returns (fL_init, B_init, bL0_init)."""
+    fL = float(fph_init) * float(pixel_size_totfoc)                     # :460
+    vw = np.asarray(views, np.float64).reshape(-1, 6)
+    pt = np.asarray(points, np.float64).reshape(-1, 3)
+    v = np.asarray(vdepth, np.float64)
+    z = np.zeros(v.size)
+    for f in np.unique(frame_idx):
+        a0, a1, a2 = vw[f, :3]
+        cx, sx, cy, sy, cz, sz = np.cos(a0), np.sin(a0), np.cos(a1), np.sin(a1), np.cos(a2), np.sin(a2)
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        sel = np.asarray(frame_idx) == f
+        z[sel] = (pt[np.asarray(point_idx)[sel]] @ (Rx @ Ry @ Rz).T + vw[f, 3:])[:, 2]
+    b = (fL * z) / (z - fL)                                              # :480
+    bad = (v < 2) | (b < 0)                                              # :483
+    a = np.stack([np.where(bad, 0.0, v), np.where(bad, 0.0, 1.0)], 1)
+    x, *_ = np.linalg.lstsq(a, np.where(bad, 0.0, b), rcond=None)       # :492
+    return fL, float(x[0]), float(x[1])

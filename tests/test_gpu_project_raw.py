@@ -96,3 +96,27 @@ def helpers_rot(a):
     Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
     Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
     return Rx @ Ry @ Rz
+
+
+def test_linear_initialisation_on_the_device_matches_the_svd_oracle(gpu):
+    # SURVEY.md 8(f) N4, src/CameraCalibration.cpp:456-498: bL = v B + bL0 over all (frame, feature) pairs
+    from lifcal_b200 import init_params as ip
+    sc = capi.make_scene(None, n_points=3000, n_frames=12, seed=9)
+    cam, views, pts = sc.camera_true, sc.views_true.reshape(-1, 6), sc.points_true.reshape(-1, 3)
+    fL, bL0, B = cam[0], cam[1], cam[2]
+    rng = np.random.default_rng(2)
+    fi = np.repeat(np.arange(12, dtype=np.int32), 3000)
+    pi = np.tile(np.arange(3000, dtype=np.int32), 12)
+    z = np.zeros(fi.size)
+    for f in range(12):
+        z[fi == f] = (pts @ helpers_rot(views[f, :3]).T + views[f, 3:])[:, 2]
+    v = (fL * z / (z - fL) - bL0) / B + 2e-3 * rng.standard_normal(z.size)
+    v[:40] = 1.7                                   # rejected rows: v < 2
+    pts2 = pts.copy()
+    pts2[5] = -views[0, 3:] @ helpers_rot(views[0, :3]) + np.array([0, 0, 10.0]) @ helpers_rot(views[0, :3])  # Z = 10 < fL: bL < 0
+    sp = sc.problem.spx
+    got = ip.init_plenoptic_parameters(fL / sp, sp, v, fi, pi, views, pts2)
+    ref = ob.init_plenoptic(fL / sp, sp, v, fi, pi, views, pts2)
+    assert got[0] == ref[0]
+    assert abs(got[1] - ref[1]) <= 1e-11 * abs(ref[1]) and abs(got[2] - ref[2]) <= 1e-11 * abs(ref[2])
+    assert abs(got[1] - B) < 2e-2 and abs(got[2] - bL0) < 2e-1  # recovers the camera it was rendered from
