@@ -36,7 +36,8 @@ struct BandArgs {
   int prof;                // LFBA_DEBUG: block 0 prints the cycles spent per phase of the step
 };
 
-constexpr int kBandPref = 5;  // prefetch registers per thread: 6 W <= kBandPref * 224 (seven of the eight warps prefetch)
+constexpr int kBandThreads = 512;  // CTA size of the sweep kernels: 15 working warps + the factorisation warp
+constexpr int kBandPref = 2;       // prefetch registers per thread: 6 W <= kBandPref * 480
 
 // Skyline offsets in closed form (no dependent index loads on the latency chain). The solver lays the reduced system out
 // as: pose row r = 6 f + i starts at column 6 max(0, f - bw); border rows (coupled points, camera, rhs) start at column 0.
@@ -67,19 +68,29 @@ __device__ __forceinline__ long long band_border_row(const BandArgs& g, int b) {
   return m.border_row(b);
 }
 
-// shared memory needed by band_sweep: A [W][LDW], X [W][6], L_kk (21) + 1/diag (6), padded
-__host__ __device__ inline size_t band_smem_doubles(int W) {
-  const size_t LDW = (size_t)W | 1;
-  size_t a = (size_t)W * LDW;
-  a += a & 1;  // X must be 16-byte aligned
-  return a + (size_t)W * 6 + 56;
-}
+
+// Geometry of the window in shared memory: rows padded to a multiple of 8 (tensor tiles), odd leading dimension.
+struct BandGeom {
+  int W, W8, LDW, NBAND;
+  __host__ __device__ explicit BandGeom(int bw, int border_rows) {
+    NBAND = 6 * (bw + 1);
+    W = NBAND + border_rows;
+    W8 = (W + 7) & ~7;
+    LDW = W8 | 1;
+  }
+  __host__ __device__ size_t x_offset() const {  // X [W8][6] behind A, 16-byte aligned
+    size_t a = (size_t)W8 * LDW;
+    return a + (a & 1);
+  }
+  __host__ __device__ size_t doubles() const { return x_offset() + (size_t)W8 * 6 + 2 * 28 + 24 + 8; }
+};
 
 // Initial window: frames fa .. fa + bw (those that exist) and their border columns.
 __device__ inline void band_load_initial(const BandArgs& g, double* A) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int bw1 = g.bw + 1, NBAND = 6 * bw1, W = NBAND + g.ns + g.nb, LDW = W | 1;
-  for (int e = tid; e < W * LDW; e += nt) A[e] = 0.0;
+  const BandGeom geo(g.bw, g.ns + g.nb);
+  const int bw1 = g.bw + 1, NBAND = geo.NBAND, LDW = geo.LDW;
+  for (int e = tid; e < (int)(geo.x_offset() + (size_t)geo.W8 * 6); e += nt) A[e] = 0.0;  // window and X (padding rows stay zero)
   __syncthreads();
   for (int f = g.fa; f <= min(g.fa + g.bw, g.hi); ++f) {
     int c0;
@@ -141,64 +152,72 @@ __device__ __forceinline__ bool band_factor6(double* a, double* out, double* din
   return bad;
 }
 
-// The sweep. NPASS = ceil(W / 32). 256 threads: warp 7 is the factorisation warp (its lane 0 runs the 6x6 Cholesky of the
-// NEXT pivot — look-ahead — while warps 0..6 do the trailing update of the current one), warps 0..6 own the panel rows,
-// the trailing update, the write-back of L and the refill of the freed slot. Two CTA barriers per pivot.
-// On return the window holds the Schur complement on the frames fb..hi and the border rows (slot space, [max][min]).
-template <int NPASS>
+// D (8x8) += A (8x4) * B (4x8) on the FP64 tensor path (DMMA): one warp instruction for 256 fused multiply-adds. The
+// trailing update of a pivot is X X^T with K = 6: per 8x8 tile of the window two of these replace 64 x 6 scalar DFMAs and,
+// more importantly, about 25 instructions per entry of predicate / address / load / store overhead — the sweep was bound by
+// instruction issue (ncu: 8900 warp instructions per pivot, 46% issue utilisation with 16 warps), not by arithmetic.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// The sweep. kBandThreads threads: the last warp is the factorisation warp (its lanes update and its lane 0 factorises
+// the NEXT pivot block — look-ahead — while the other warps do the trailing update of the current one); the other warps
+// own the panel rows, the tensor-tile trailing update, the write-back of L and the refill of the freed slot.
+// Three CTA barriers per pivot. On return the window holds the Schur complement on the frames fb..hi and the border rows
+// (slot space, [max][min]).
 __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const int bw = g.bw, bw1 = bw + 1, NBAND = 6 * bw1, Bn = g.ns + g.nb, W = NBAND + Bn, LDW = W | 1;
-  size_t aoff = (size_t)W * LDW;
-  aoff += aoff & 1;
-  double* Xs = A + aoff;              // [W][6], 16-byte aligned rows of 48 bytes
-  double* Lsm = Xs + (size_t)W * 6;   // 2 x 28: L_kk lower (21) + 1 / diag (6) of the current / next pivot
-  const int FT = nt - 32;             // the factorising thread (lane 0 of the last warp)
-  const int nww = (nt >> 5) - 1;      // working warps
+  const int bw = g.bw, bw1 = bw + 1;
+  const BandGeom geo(bw, g.ns + g.nb);
+  const int NBAND = geo.NBAND, W = geo.W, W8 = geo.W8, LDW = geo.LDW;
+  double* Xs = A + geo.x_offset();      // [W8][6], rows of 48 bytes, 16-byte aligned; rows >= W stay zero
+  double* Lsm = Xs + (size_t)W8 * 6;    // 2 x 28: L_kk lower (21) + 1 / diag (6) of the current / next pivot
+  double* snap = Lsm + 2 * 28;          // 21: the next pivot block as it was before this step's update
+  const int FT = nt - 32;               // the factorising thread (lane 0 of the last warp)
+  const int nww = (nt >> 5) - 1;        // working warps
   const SkyMap sky{bw, g.np6};
+  const int nT = W8 >> 3, n_tiles = nT * (nT + 1) / 2;
 
   // this thread's entries of the pivot-slot region (row r of the window, column i of the pivot block): static decode
   const int npf = nt - 32;
   int er[kBandPref], ei[kBandPref];
+  long long estat[kBandPref];  // static part of the entry's skyline offset
 #pragma unroll
   for (int q = 0; q < kBandPref; ++q) {
     const int e = tid + q * npf;
-    er[q] = (tid < npf && e < 6 * W) ? e / 6 : -1;
-    ei[q] = e - 6 * (e / 6);
+    const bool live = tid < npf && e < 6 * W;
+    const int r = live ? e / 6 : -1, i = e - 6 * (e / 6);
+    er[q] = (r >= NBAND && r < NBAND + g.ns) ? -2 : r;  // previous-separator rows: always zero for an entering frame
+    ei[q] = i;
+    if (r >= NBAND + g.ns) estat[q] = sky.border_row(r - NBAND - g.ns) + i;       // + 6 fn
+    else estat[q] = (long long)i * (6 * bw + 1) + (i * (i - 1)) / 2;              // + row0(fn) + column (entering frames have a full band)
   }
   const int prow = tid < W ? tid : -1;  // this thread's panel row (W <= 160: warps 0..4)
   const int prow_js = prow >= 0 && prow < NBAND ? prow / 6 : -1, prow_i = prow >= 0 ? prow - 6 * (prow / 6) : 0;
 
-  long long pc[4] = {0, 0, 0, 0}, tl = 0;
-  const bool prof = g.prof && blockIdx.x == 0 && (tid == FT || tid == 0);
-  if (prof) tl = clock64();
-#define BAND_TICK(i) if (prof) { const long long tn_ = clock64(); pc[i] += tn_ - tl; tl = tn_; }
-
   // global loads of the region entries for the frame that enters when pivot k retires (issued one step ahead)
   double pv[kBandPref];
+  long long row0 = sky.frame_off(g.fa + bw1);  // skyline offset of the entering frame's first row; frames > bw: constant stride
+  const int fstride = 36 * bw + 21;
   auto prefetch = [&](int k, int kmod) {
     const int fn = k + bw1;
     const bool enter = fn <= g.hi && k < g.fb;
-    const long long row0 = enter ? sky.row(fn, 0) : 0;
-    const int c0n = sky.c0(fn), len0 = 6 * fn - c0n + 1;
 #pragma unroll
     for (int q = 0; q < kBandPref; ++q) {
       pv[q] = 0.0;
       const int r = er[q], i = ei[q];
       if (!enter || r < 0) continue;
-      const long long rowi = row0 + (long long)i * len0 + (i * (i - 1)) / 2;
       if (r < NBAND) {
         const int js = r / 6, jj = r - 6 * js;
-        if (js == kmod) {
-          if (jj <= i) pv[q] = g.S[rowi + (6 * fn + jj - c0n)];
-        } else {
-          int dd = js - kmod;
-          dd += dd < 0 ? bw1 : 0;
-          const int fg = k + dd;  // frame living in that slot: k+1 .. k+bw
-          if (fg <= g.hi) pv[q] = g.S[rowi + (6 * fg + jj - c0n)];
+        int dd = js - kmod;
+        dd += dd < 0 ? bw1 : 0;        // 0: the entering frame's own block; 1..bw: the frame k + dd living in that slot
+        if (dd == 0) {
+          if (jj <= i) pv[q] = g.S[row0 + estat[q] + (6 * bw + jj)];
+        } else if (k + dd <= g.hi) {
+          pv[q] = g.S[row0 + estat[q] + (6 * (dd - 1) + jj)];
         }
-      } else if (r >= NBAND + g.ns) {
-        pv[q] = g.S[sky.border_row(r - NBAND - g.ns) + 6 * fn + i];
+      } else {
+        pv[q] = g.S[estat[q] + 6 * fn];
       }
     }
   };
@@ -221,114 +240,92 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
     const double* Lc = Lsm + 28 * ((k - g.fa) & 1);
     double* Ln = Lsm + 28 * (((k - g.fa) & 1) ^ 1);
     const bool ahead = k + 1 < g.fb;
-    // ---- panel: X_r = A(r, pivot columns) L_kk^-T for every other row of the window (empty rows give zeros) ----
+    // ---- panel: X_r = A(r, pivot columns) L_kk^-T for every other row of the window (empty rows give zeros);
+    //      the pivot's own rows get X = 0 so that the tile update below needs no exclusions ----
     double x[6] = {0, 0, 0, 0, 0, 0};
     const bool prow_on = prow >= 0 && (prow < s || prow >= s + 6);
-    if (prow_on) {
+    if (prow >= 0) {
       const int r = prow;
-      if (r > s) {
+      if (prow_on) {
+        if (r > s) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) x[c] = A[r * LDW + s + c];
-      } else {
+          for (int c = 0; c < 6; ++c) x[c] = A[r * LDW + s + c];
+        } else {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) x[c] = A[(s + c) * LDW + r];
-      }
-      double l[21], di[6];
+          for (int c = 0; c < 6; ++c) x[c] = A[(s + c) * LDW + r];
+        }
+        double l[21], di[6];
 #pragma unroll
-      for (int e = 0; e < 21; ++e) l[e] = Lc[e];
+        for (int e = 0; e < 21; ++e) l[e] = Lc[e];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) di[c] = Lc[21 + c];
+        for (int c = 0; c < 6; ++c) di[c] = Lc[21 + c];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double acc = x[c];
+        for (int c = 0; c < 6; ++c) {
+          double acc = x[c];
 #pragma unroll
-        for (int j = 0; j < c; ++j) acc = fma(-x[j], l[c * (c + 1) / 2 + j], acc);
-        x[c] = acc * di[c];
+          for (int j = 0; j < c; ++j) acc = fma(-x[j], l[c * (c + 1) / 2 + j], acc);
+          x[c] = acc * di[c];
+        }
       }
       double2* xd = reinterpret_cast<double2*>(Xs + (size_t)r * 6);
       xd[0] = make_double2(x[0], x[1]);
       xd[1] = make_double2(x[2], x[3]);
       xd[2] = make_double2(x[4], x[5]);
-    } else if (tid >= nt - 21) {  // L_kk itself goes back to HBM (lanes 11..31 of the factorisation warp)
-      const int e = tid - (nt - 21);
-      int i = 0, j = e;
-      while (j > i) { j -= i + 1; ++i; }
-      g.S[sky.row(k, i) + (6 * k + j - sky.c0(k))] = Lc[e];
+    } else if (warp == nww) {
+      if (lane < 21 && ahead) {  // snapshot of the next pivot block (the tile update will also touch it)
+        int i = 0, j = lane;
+        while (j > i) { j -= i + 1; ++i; }
+        snap[lane] = A[(s1 + i) * LDW + s1 + j];
+      }
+      if (lane >= 11) {  // L_kk itself goes back to HBM
+        const int e = lane - 11;
+        int i = 0, j = e;
+        while (j > i) { j -= i + 1; ++i; }
+        g.S[sky.row(k, i) + (6 * k + j - sky.c0(k))] = Lc[e];
+      }
     }
-    BAND_TICK(0)
     __syncthreads();
-    BAND_TICK(1)
     if (warp == nww) {
-      // ---- look-ahead: the next pivot block gets its update from this step and is factorised right away ----
-      if (tid == FT && ahead) {
-        double a[21], xr[36];
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = A[(s1 + i) * LDW + s1 + j];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const double2* xd = reinterpret_cast<const double2*>(Xs + (size_t)(s1 + i) * 6);
-          const double2 v0 = xd[0], v1 = xd[1], v2 = xd[2];
-          xr[6 * i] = v0.x; xr[6 * i + 1] = v0.y; xr[6 * i + 2] = v1.x; xr[6 * i + 3] = v1.y; xr[6 * i + 4] = v2.x; xr[6 * i + 5] = v2.y;
+      // ---- look-ahead: the next pivot block gets its update from this step and is factorised right away. Lanes 0..20
+      //      update one entry each (two 3-term chains), lane 0 collects them through shared memory and runs the chain ----
+      if (ahead) {
+        double* scratch = Ln;  // the next pivot's L slot doubles as the exchange buffer (overwritten by the factorisation)
+        if (lane < 21) {
+          int i = 0, j = lane;
+          while (j > i) { j -= i + 1; ++i; }
+          const double2* xi = reinterpret_cast<const double2*>(Xs + (size_t)(s1 + i) * 6);
+          const double2* xj = reinterpret_cast<const double2*>(Xs + (size_t)(s1 + j) * 6);
+          const double2 a0 = xi[0], a1 = xi[1], a2 = xi[2], b0 = xj[0], b1 = xj[1], b2 = xj[2];
+          const double d0 = fma(a0.x, b0.x, fma(a0.y, b0.y, a1.x * b1.x));
+          const double d1 = fma(a1.y, b1.y, fma(a2.x, b2.x, a2.y * b2.y));
+          scratch[lane] = snap[lane] - (d0 + d1);
         }
+        __syncwarp();
+        if (lane == 0) {
+          double a[21];
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j <= i; ++j) {
-            const double d0 = fma(xr[6 * i], xr[6 * j], fma(xr[6 * i + 1], xr[6 * j + 1], xr[6 * i + 2] * xr[6 * j + 2]));
-            const double d1 = fma(xr[6 * i + 3], xr[6 * j + 3], fma(xr[6 * i + 4], xr[6 * j + 4], xr[6 * i + 5] * xr[6 * j + 5]));
-            a[i * (i + 1) / 2 + j] -= d0 + d1;
-          }
-        if (band_factor6(a, Ln, g.dinv_out + 6 * (k + 1))) *s_fail = 1;
+          for (int e = 0; e < 21; ++e) a[e] = scratch[e];
+          if (band_factor6(a, Ln, g.dinv_out + 6 * (k + 1))) *s_fail = 1;
+        }
       }
     } else {
-      // ---- trailing update of every entry outside the pivot slot (and outside the block the look-ahead owns):
-      //      A(a, b) -= X_a . X_b, a >= b in slot order; rows in groups of four per warp for instruction-level parallelism
-      double xb[NPASS][6];
-#pragma unroll
-      for (int p = 0; p < NPASS; ++p) {
-        const int b = lane + 32 * p;
-        if (b < W) {
-          const double2* xd = reinterpret_cast<const double2*>(Xs + (size_t)b * 6);
-          const double2 v0 = xd[0], v1 = xd[1], v2 = xd[2];
-          xb[p][0] = v0.x; xb[p][1] = v0.y; xb[p][2] = v1.x; xb[p][3] = v1.y; xb[p][4] = v2.x; xb[p][5] = v2.y;
-        } else {
-#pragma unroll
-          for (int c = 0; c < 6; ++c) xb[p][c] = 0.0;
-        }
-      }
-      for (int a0 = warp; a0 < W; a0 += 4 * nww) {
-        double xa[4][6], acc[4][NPASS];
-        bool on[4][NPASS];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int a = a0 + u * nww;
-          const bool row_on = a < W && (a < s || a >= s + 6);
-          const bool in_next = ahead && a >= s1 && a < s1 + 6;
-          const double2* xd = reinterpret_cast<const double2*>(Xs + (size_t)(row_on ? a : 0) * 6);  // broadcast loads
-          const double2 v0 = xd[0], v1 = xd[1], v2 = xd[2];
-          xa[u][0] = v0.x; xa[u][1] = v0.y; xa[u][2] = v1.x; xa[u][3] = v1.y; xa[u][4] = v2.x; xa[u][5] = v2.y;
-#pragma unroll
-          for (int p = 0; p < NPASS; ++p) {
-            const int b = lane + 32 * p;
-            on[u][p] = row_on && b <= a && (b < s || b >= s + 6) && !(in_next && b >= s1);
-            acc[u][p] = on[u][p] ? A[(size_t)a * LDW + b] : 0.0;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int p = 0; p < NPASS; ++p) {
-            const double d0 = fma(xa[u][0], xb[p][0], fma(xa[u][1], xb[p][1], xa[u][2] * xb[p][2]));
-            const double d1 = fma(xa[u][3], xb[p][3], fma(xa[u][4], xb[p][4], xa[u][5] * xb[p][5]));
-            acc[u][p] -= d0 + d1;
-          }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int p = 0; p < NPASS; ++p)
-            if (on[u][p]) A[(size_t)(a0 + u * nww) * LDW + lane + 32 * p] = acc[u][p];
+      // ---- trailing update, A(a, b) -= X_a . X_b for a >= b in slot order, as 8x8 tensor tiles (two m8n8k4 DMMAs each;
+      //      K = 6 padded to 8 with zeros). Diagonal tiles also write their (unused) upper half; rows of the pivot slot and
+      //      the padding rows have X = 0 ----
+      const int lr = lane >> 2, lc = lane & 3;
+      for (int t = warp; t < n_tiles; t += nww) {
+        int I = 0, J = t;
+        while (J > I) { J -= I + 1; ++I; }
+        const double* xi = Xs + (size_t)(8 * I + lr) * 6;
+        const double* xj = Xs + (size_t)(8 * J + lr) * 6;
+        const double a0 = -xi[lc], a1 = lc < 2 ? -xi[4 + lc] : 0.0;
+        const double b0 = xj[lc], b1 = lc < 2 ? xj[4 + lc] : 0.0;
+        double* cp = A + (size_t)(8 * I + lr) * LDW + 8 * J + 2 * lc;
+        double c0 = cp[0], c1 = cp[1];
+        dmma884(c0, c1, a0, b0);
+        dmma884(c0, c1, a1, b1);
+        cp[0] = c0;
+        cp[1] = c1;
       }
       // ---- column block k of L goes back to HBM (backward substitution reads it there) ----
       if (prow_on) {
@@ -349,10 +346,13 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
           for (int c = 0; c < 6; ++c) dst[c] = x[c];
         }
       }
-      // ---- the freed slot takes frame k + bw + 1 (or zeros): every entry of the region is written by its one owner ----
+    }
+    __syncthreads();
+    // ---- the freed slot takes frame k + bw + 1 (or zeros): every entry of the region is written by its one owner ----
+    if (warp < nww) {
 #pragma unroll
       for (int q = 0; q < kBandPref; ++q) {
-        const int r = er[q], i = ei[q];
+        const int r = er[q] == -2 ? (tid + q * npf) / 6 : er[q], i = ei[q];
         if (r < 0) continue;
         if (r >= s && r < s + 6) {
           const int jj = r - s;
@@ -362,26 +362,12 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
           A[max(r, b) * LDW + min(r, b)] = pv[q];
         }
       }
+      row0 += fstride;
       prefetch(k + 1, kmod1);  // in flight during the whole next step
     }
-    BAND_TICK(2)
     __syncthreads();
-    BAND_TICK(3)
     kmod = kmod1;
   }
-  if (prof)
-    printf("[lfba dbg] band sweep W=%d pivots=%d thread %d: cycles panel %lld | wait %lld | %s %lld | wait %lld\n", W, g.fb - g.fa,
-           tid, pc[0], pc[1], tid == FT ? "look-ahead factor" : "trailing+store+refill+prefetch", pc[2], pc[3]);
-#undef BAND_TICK
 }
-
-#define LFBA_BAND_DISPATCH(W_, CALL)                              \
-  switch (((W_) + 31) / 32) {                                     \
-    case 1: { constexpr int NPASS = 1; CALL; } break;             \
-    case 2: { constexpr int NPASS = 2; CALL; } break;             \
-    case 3: { constexpr int NPASS = 3; CALL; } break;             \
-    case 4: { constexpr int NPASS = 4; CALL; } break;             \
-    default: { constexpr int NPASS = 5; CALL; } break;            \
-  }
 
 }  // namespace lfba

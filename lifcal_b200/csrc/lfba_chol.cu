@@ -200,18 +200,17 @@ __global__ void __launch_bounds__(256) k_backsolve(Dev d) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int bslot(int f, int bw1) { return 6 * (f % bw1); }
 
-template <int NPASS>
-__global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
+__global__ void __launch_bounds__(kBandThreads) k_chol_banded(Dev d, int bw, int nb) {
   LmState* st = d.st;
   if (linear_phase_idle(st) || !st->solve_ok) return;
   extern __shared__ __align__(16) double sm[];
   const int F = d.np6 / 6;
   const int bw1 = bw + 1;
   const int NBAND = 6 * bw1;
-  const int W = NBAND + nb;
-  const int LDW = W | 1;
+  const BandGeom geo(bw, nb);
+  const int LDW = geo.LDW;
   double* A = sm;                                                   // window + X + L_kk (band_sweep's layout)
-  double* ys = sm + band_smem_doubles(W);                           // n
+  double* ys = sm + geo.doubles();                                  // n
   double* dinv_all = ys + d.n;                                      // n: 1 / L_cc of the pose pivots
   __shared__ double tvec[6];
   __shared__ double Lkk[21];
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
   }
   __syncthreads();
 #define CHOL_TICK(i)
-  band_sweep<NPASS>(g, A, &s_fail);
+  band_sweep(g, A, &s_fail);
   CHOL_TICK(5)
   // ---- dense Cholesky of the border block (coupled points + camera); the rhs row is not a pivot ----
   for (int c = 0; c < npiv; ++c) {
@@ -333,28 +332,21 @@ __global__ void __launch_bounds__(256) k_chol_banded(Dev d, int bw, int nb) {
 // per-device opt-in to > 48 KB of dynamic shared memory (call once per device with that device current)
 void prepare_device_kernels() {
   cudaFuncSetAttribute(k_chol_column, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * TS * LD * sizeof(double)));
-  cudaFuncSetAttribute(k_chol_banded<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
-  cudaFuncSetAttribute(k_chol_banded<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
-  cudaFuncSetAttribute(k_chol_banded<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
-  cudaFuncSetAttribute(k_chol_banded<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
-  cudaFuncSetAttribute(k_chol_banded<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
+  cudaFuncSetAttribute(k_chol_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandedSmemMax);
 }
 
 // shared memory needed by k_chol_banded, or 0 when the banded path does not apply / does not fit
 size_t banded_smem_bytes(const Dev& d, int bw, int nb) {
   if (d.np6 == 0) return 0;
-  const size_t NBAND = 6 * (size_t)(bw + 1), W = NBAND + nb;
-  const size_t F = d.np6 / 6;
-  if (6 * W > (size_t)kBandPref * 224 || W > 160) return 0;   // prefetch registers / column passes of band_sweep
+  const BandGeom geo(bw, nb);
+  if (6 * geo.W > kBandPref * 480 || geo.W > 160) return 0;   // prefetch registers / panel rows of band_sweep
   if (6 * (size_t)bw + nb > 32 * 8) return 0;                 // backward-substitution lanes
-  const size_t bytes = (band_smem_doubles((int)W) + 2 * (size_t)d.n + 8) * sizeof(double);
-  (void)F;
+  const size_t bytes = (geo.doubles() + 2 * (size_t)d.n + 8) * sizeof(double);
   return bytes <= (size_t)kBandedSmemMax ? bytes : 0;
 }
 
 void launch_chol_banded(const Dev& d, int bw, int nb, size_t smem, cudaStream_t s) {
-  const int W = 6 * (bw + 1) + nb;
-  LFBA_BAND_DISPATCH(W, (k_chol_banded<NPASS><<<1, 256, smem, s>>>(d, bw, nb)));
+  k_chol_banded<<<1, kBandThreads, smem, s>>>(d, bw, nb);
 }
 
 int launch_reduced_solve(const Dev& d, int n_tiles, const int* d_tile_first, int bw, cudaStream_t s, PartPlan* plan) {

@@ -43,8 +43,7 @@ __device__ __forceinline__ int pslot(int f, int bw1) { return 6 * (f % bw1); }
 // ---------------------------------------------------------------------------------------------------------------
 // phase 1
 // ---------------------------------------------------------------------------------------------------------------
-template <int NPASS>
-__global__ void __launch_bounds__(256) k_part_forward(Dev d, PartDev pd) {
+__global__ void __launch_bounds__(kBandThreads) k_part_forward(Dev d, PartDev pd) {
   LmState* st = d.st;
   if (linear_phase_idle(st) || !st->solve_ok) return;
   extern __shared__ __align__(16) double sm[];
@@ -56,14 +55,15 @@ __global__ void __launch_bounds__(256) k_part_forward(Dev d, PartDev pd) {
   const int ns = j > 0 ? 6 * bw : 0;                    // rows of the previous separator
   const int nb = pd.npiv + 1;                           // global border rows incl. the rhs row
   const int B = ns + nb;
-  const int NBAND = 6 * bw1, W = NBAND + B, LDW = W | 1;
+  const BandGeom geo(bw, B);
+  const int NBAND = geo.NBAND, LDW = geo.LDW;
   double* A = sm;
   __shared__ int s_fail;
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) s_fail = 0;
   BandArgs g{d.S, d.row_off, d.np6, bw, fa, fb, hi, ns, fa - bw, nb, pd.Lsep, pd.dinv, d.debug};
   band_load_initial(g, A);
-  band_sweep<NPASS>(g, A, &s_fail);
+  band_sweep(g, A, &s_fail);
   if (tid == 0 && s_fail) st->solve_ok = 0;
   // ---- what is left: Schur complement on [this separator | previous separator | border] (slot space, [max][min]) ----
   const int nsep = last ? 0 : 6 * bw;
@@ -273,16 +273,15 @@ PartPlan* part_plan_create(const Dev& d, int bw, cudaStream_t s) {
   P = std::min(P, F / (2 * bw + 2));
   P = std::min(P, 64);
   if (P < 3) return p;
-  {
-    const int Wf = 6 * (bw + 1) + 6 * bw + nb;
-    if (6 * Wf > kBandPref * 224 || Wf > 160) return p;  // prefetch registers / column passes of band_sweep
-  }
+  const BandGeom geo_f(bw, 6 * bw + nb);
+  if (6 * geo_f.W > kBandPref * 480 || geo_f.W > 160) return p;  // prefetch registers / panel rows of band_sweep
   if (6 * bw + 6 * bw + npiv > 32 * 8) return p;   // backward-substitution lanes
   std::vector<int> hb((size_t)P + 1);
   for (int j = 0; j <= P; ++j) hb[j] = (int)((long long)F * j / P);
   const int B = 6 * bw + nb, NBAND = 6 * (bw + 1), W = NBAND + B, LDW = W | 1;
-  p->smem_fwd = band_smem_doubles(W) * sizeof(double);
+  p->smem_fwd = geo_f.doubles() * sizeof(double);
   (void)LDW;
+  (void)W;
   int max_len = 0;
   for (int j = 0; j < P; ++j) max_len = std::max(max_len, hb[j + 1] - hb[j]);
   p->smem_bwd = (size_t)(6 * max_len + 6 * bw + npiv + 8) * sizeof(double);
@@ -323,11 +322,7 @@ PartPlan* part_plan_create(const Dev& d, int bw, cudaStream_t s) {
   d2.y = p->y2.p;
   p->d2 = d2;
   p->pd = PartDev{P, bw, F, npiv, p->bounds.p, p->Lsep.p, p->X.p, p->dinv.p, M};
-  cudaFuncSetAttribute(k_part_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
-  cudaFuncSetAttribute(k_part_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
-  cudaFuncSetAttribute(k_part_forward<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
-  cudaFuncSetAttribute(k_part_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
-  cudaFuncSetAttribute(k_part_forward<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
+  cudaFuncSetAttribute(k_part_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_fwd);
   cudaFuncSetAttribute(k_part_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bwd);
   p->active = true;
   return p;
@@ -337,10 +332,7 @@ bool part_plan_active(const PartPlan* p) { return p && p->active; }
 
 // the three phases on stream s; returns the number of kernels launched
 int launch_part_solve(const Dev& d, PartPlan* p, cudaStream_t s) {
-  {
-    const int Wf = 6 * (p->pd.bw + 1) + 6 * p->pd.bw + p->pd.npiv + 1;
-    LFBA_BAND_DISPATCH(Wf, (k_part_forward<NPASS><<<p->pd.P, 256, p->smem_fwd, s>>>(d, p->pd)));
-  }
+  k_part_forward<<<p->pd.P, kBandThreads, p->smem_fwd, s>>>(d, p->pd);
   Dev d2 = p->d2;
   d2.st = d.st;
   k_part_assemble<<<std::min(148, d2.n + 1), 64, 0, s>>>(d, p->pd, d2, p->s2_len);
