@@ -39,25 +39,6 @@ struct BandArgs {
 constexpr int kBandThreads = 512;  // CTA size of the sweep kernels: 15 working warps + the factorisation warp
 constexpr int kBandPref = 2;       // prefetch registers per thread: 6 W <= kBandPref * 480
 
-// Skyline offsets in closed form (no dependent index loads on the latency chain). The solver lays the reduced system out
-// as: pose row r = 6 f + i starts at column 6 max(0, f - bw); border rows (coupled points, camera, rhs) start at column 0.
-// So frame f's six rows hold 36 min(f, bw) + 21 entries, and everything before frame f is a polynomial in f.
-struct SkyMap {
-  int bw, np6;
-  __host__ __device__ long long frame_off(int f) const {
-    return f <= bw ? 18ll * f * (f - 1) + 21ll * f
-                   : 18ll * bw * (bw - 1) + 21ll * bw + (long long)(f - bw) * (36 * bw + 21);
-  }
-  __host__ __device__ int c0(int f) const { return 6 * (f > bw ? f - bw : 0); }
-  __host__ __device__ long long row(int f, int i) const {  // offset of entry (6 f + i, c0(f))
-    const int len0 = 6 * f - c0(f) + 1;
-    return frame_off(f) + (long long)i * len0 + (i * (i - 1)) / 2;
-  }
-  __host__ __device__ long long border_row(int b) const {  // offset of entry (np6 + b, 0)
-    return frame_off(np6 / 6) + (long long)b * (np6 + 1) + ((long long)b * (b - 1)) / 2;
-  }
-};
-
 __device__ __forceinline__ long long band_sky_row(const BandArgs& g, int f, int i, int& c0) {
   const SkyMap m{g.bw, g.np6};
   c0 = m.c0(f);

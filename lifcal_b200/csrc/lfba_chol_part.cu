@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_part_backward(Dev d, PartDev pd, const 
   double* ysp = ys + 6 * (hi - fa + 1);     // [ns] y of the previous separator
   double* yb = ysp + 6 * bw;                // [npiv] y of the border
   __shared__ double tvec[6];
-  __shared__ double Lkk[21];
+  __shared__ double Lkk[27];
   const SkyMap sky{bw, d.np6};
   // known parts of the solution (phase 2); every CTA also publishes what it owns into d.y
   if (!last)
@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(256) k_part_backward(Dev d, PartDev pd, const 
       int i = 0, c = lane;
       while (c > i) { c -= i + 1; ++i; }
       lkk = d.S[sky.row(k, i) + (6 * k + c - sky.c0(k))];
+    } else if (warp == 6 && lane < 27) {
+      lkk = pd.dinv[6 * k + (lane - 21)];  // 1 / L_cc: fetched one step ahead with the rest, not inside the solve chain
     }
   };
   if (fb > fa) fetch_col(fb - 1);
@@ -215,18 +217,21 @@ __global__ void __launch_bounds__(256) k_part_backward(Dev d, PartDev pd, const 
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) tvec[warp] = zk - acc;
-    } else if (warp == 6 && lane < 21) {
-      Lkk[lane] = lkk;
+    } else if (warp == 6 && lane < 27) {
+      Lkk[lane] = lkk;  // 21 entries of L_kk, then the six 1 / L_cc
     }
     if (k > fa) fetch_col(k - 1);
     __syncthreads();
     if (tid == 0) {
-      double t[6];
+      double t[6], dv[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) t[c] = tvec[c];
+      for (int c = 0; c < 6; ++c) {
+        t[c] = tvec[c];
+        dv[c] = Lkk[21 + c];
+      }
 #pragma unroll
       for (int c = 5; c >= 0; --c) {
-        const double yc = t[c] * pd.dinv[6 * k + c];
+        const double yc = t[c] * dv[c];
         ys[6 * (k - fa) + c] = yc;
 #pragma unroll
         for (int c2 = 0; c2 < c; ++c2) t[c2] = fma(-Lkk[c * (c + 1) / 2 + c2], yc, t[c2]);
@@ -298,6 +303,7 @@ PartPlan* part_plan_create(const Dev& d, int bw, cudaStream_t s) {
   p->nb = nb;
   Dev d2 = d;
   d2.np6 = 6 * F2;
+  d2.band = bw2;
   d2.n = n2;
   p->smem_red = banded_smem_bytes(d2, bw2, nb);
   if (p->smem_red == 0) return p;

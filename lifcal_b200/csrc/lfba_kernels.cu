@@ -48,8 +48,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// entry (r, c), c <= r, of the skyline: closed form (SkyMap), no index loads
 __device__ __forceinline__ double* S_at(const Dev& d, int r, int c) {
-  return d.S + d.row_off[r] + (c - d.row_c0[r]);
+  const SkyMap m{d.band, d.np6};
+  if (r < d.np6) {
+    const int f = r / 6;
+    return d.S + m.row(f, r - 6 * f) + (c - m.c0(f));
+  }
+  return d.S + m.border_row(r - d.np6) + c;
 }
 
 // Sum NV per-thread values over the CTA (fixed order: lanes by butterfly, warps ascending), result to out[0..NV).
@@ -114,14 +120,21 @@ __global__ void __launch_bounds__(1024) k_reduce_eval(Dev d) {
   __shared__ double sls[2];
   const int v = threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 32 warps; a warp sums one value over the CTAs
-  for (int q = warp; q < 64; q += 32) {                        // (lanes stride over the CTAs, then a butterfly: fixed order)
-    double s_ = 0.0;
-    if (q < NV && !st->eval_skip)
-      for (int b = lane; b < d.grid_eval; b += 32) s_ += d.part_eval[(size_t)b * 64 + q];
-    s_ = warp_sum(s_);
-    if (lane == 0) {
-      sh[q] = s_;
-      if (q < NV) d.camsum[cand][q] = s_;
+  {  // lane = value (coalesced rows of the CTA partials), warps stride over the CTAs, warp partials added in warp order
+    __shared__ double wp[32][64];
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int q = lane + 32 * h2;
+      double s_ = 0.0;
+      if (q < NV && !st->eval_skip)
+        for (int b = warp; b < d.grid_eval; b += 32) s_ += d.part_eval[(size_t)b * 64 + q];
+      wp[warp][q] = s_;
+    }
+    __syncthreads();
+    if (v < 64) {
+      double s_ = 0.0;
+      for (int w = 0; w < 32; ++w) s_ += wp[w][v];
+      sh[v] = s_;
+      if (v < NV) d.camsum[cand][v] = s_;
     }
   }
   if (warp < 8) {
@@ -1049,18 +1062,28 @@ __global__ void __launch_bounds__(1024) k_add_camera(Dev d) {
   __shared__ double sp[64];
   const int v = threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int q = warp; q < 64; q += 32) {  // a warp reduces one value over the CTAs of k_points (fixed order)
-    double s_ = 0.0;
-    if (d.refine_points) {
-      if (q == 63) {
-        for (int b = lane; b < d.grid_pts; b += 32) s_ = fmax(s_, d.part_pts[(size_t)b * 64 + 63]);
-        s_ = warp_max(s_);
-      } else {
-        for (int b = lane; b < d.grid_pts; b += 32) s_ += d.part_pts[(size_t)b * 64 + q];
-        s_ = warp_sum(s_);
+  // 64 values per CTA of k_points, summed over the CTAs: lane = value (coalesced 256-byte rows), warps stride over the
+  // CTAs, then the 32 warp partials are added in warp order (fixed order: deterministic)
+  {
+    __shared__ double wp[32][64];
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int q = lane + 32 * h2;
+      double s_ = 0.0;
+      if (d.refine_points) {
+        if (q == 63) {
+          for (int b = warp; b < d.grid_pts; b += 32) s_ = fmax(s_, d.part_pts[(size_t)b * 64 + q]);
+        } else {
+          for (int b = warp; b < d.grid_pts; b += 32) s_ += d.part_pts[(size_t)b * 64 + q];
+        }
       }
+      wp[warp][q] = s_;
     }
-    if (lane == 0) sp[q] = s_;
+    __syncthreads();
+    if (v < 64) {
+      double s_ = 0.0;
+      for (int w = 0; w < 32; ++w) s_ = v == 63 ? fmax(s_, wp[w][v]) : s_ + wp[w][v];
+      sp[v] = s_;
+    }
   }
   __syncthreads();
   if (v < NH) {
@@ -1262,11 +1285,11 @@ __global__ void __launch_bounds__(128) k_point_step(Dev d) {
 
 // Back substitution output y (reduced) -> candidate camera (SubsetManifold + box bounds), poses, coupled points;
 // reduced-part scalars. One CTA.
-__global__ void __launch_bounds__(256) k_reduced_step(Dev d) {
+__global__ void __launch_bounds__(1024) k_reduced_step(Dev d) {
   LmState* st = d.st;
   if (linear_phase_idle(st)) return;
   const int cur = st->cur, cand = 1 - cur;
-  __shared__ double red[8 * 8];
+  __shared__ double red[32 * 8];
   __shared__ double out[8];
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (st->solve_ok) {
@@ -1449,7 +1472,7 @@ int launch_steps(const Dev& d, cudaStream_t s) {
     LFBA_DISPATCH_NC(d.NC, (k_point_step<NC><<<d.grid_pts, 128, 0, s>>>(d)));
     ++launches;
   }
-  k_reduced_step<<<1, 256, 0, s>>>(d);
+  k_reduced_step<<<1, 1024, 0, s>>>(d);
   return launches;
 }
 void launch_init_norms(const Dev& d, cudaStream_t s) { k_init_norms<<<d.grid_pts, 128, 0, s>>>(d); }

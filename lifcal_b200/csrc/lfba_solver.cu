@@ -294,6 +294,7 @@ struct Solver {
     // ---- reduced system layout [poses | coupled points | camera | rhs] and its skyline profile ----
     std::memset(&d, 0, sizeof(d));
     d.np6 = rposes ? 6 * F : 0;
+    d.band = bw;
     d.Pc = Pc;
     int ncr = 0;
     for (int c = 0; c < kMaxNC; ++c) d.cam_red[c] = -1;
