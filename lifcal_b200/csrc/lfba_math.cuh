@@ -179,35 +179,6 @@ LFBA_HD void lens_entry(const CamModel& m, double mx, double my, double* e) {
   for (int k = 0; k < 8; ++k) e[8 + k] = E[k];
 }
 
-// Derivatives of the undistorted lens centre from u alone, by the implicit-function theorem at the fixed point
-// u = cd - shift(u):  du/dcd = (I + A(u))^-1,  du/dtheta = -(I + A(u))^-1 dshift/dtheta(u).
-// The reference differentiates the TRUNCATED ten-step iteration (lens_entry carries that exact recurrence); the two
-// agree to O(|A|^10), i.e. to rounding for |A| <~ 0.03. k_tables measures the actual deviation over all lenses of the
-// problem at every evaluation; the evaluation kernels may use this form (1 instead of 8 gathered 16-byte chunks per
-// observation) while that deviation is below a tolerance (opt-in: on B200 it measured slower than the table gather).
-// out[0..11] has the layout of lens-entry slots [4..15].
-LFBA_HD void lens_implicit_derivs(const CamModel& m, double ux, double uy, double* out) {
-  if (!m.any_dist) {
-    out[0] = -m.dcrx * m.sx; out[1] = 0.0; out[2] = 0.0; out[3] = -m.dcry * m.sy;
-    for (int k = 4; k < 12; ++k) out[k] = 0.0;
-    return;
-  }
-  double dx, dy, A[4], d[8];
-  dist_shift_jac(m, ux, uy, dx, dy, A, d + 0, d + 2, d + 4, d + 6);
-  const double a = 1.0 + A[0], b = A[1], c = A[2], e = 1.0 + A[3];
-  const double idet = 1.0 / (a * e - b * c);
-  const double B00 = e * idet, B01 = -b * idet, B10 = -c * idet, B11 = a * idet;
-  const double fx = -m.dcrx * m.sx, fy = -m.dcry * m.sy;
-  out[0] = B00 * fx;
-  out[1] = B10 * fx;
-  out[2] = B01 * fy;
-  out[3] = B11 * fy;
-  for (int k = 0; k < 4; ++k) {
-    out[4 + 2 * k] = -(B00 * d[2 * k] + B01 * d[2 * k + 1]);
-    out[5 + 2 * k] = -(B10 * d[2 * k] + B11 * d[2 * k + 1]);
-  }
-}
-
 // R = Rx(a0) Ry(a1) Rz(a2) (row-major) and dR/da_k; f[36..38] = translation.
 LFBA_HD void frame_entry(const double* v, double* f) {
   const double c0 = cos(v[0]), s0 = sin(v[0]);
@@ -306,7 +277,8 @@ LFBA_HD void track_setup(const CamModel& m, const double Pc[3], TrackCtx& t) {
   t.bB = m.sg[2] * bB;
 }
 
-// residual only (candidate-cost evaluation, reprojection statistics)
+// residual only. Not called by a kernel: the CPU harness (tests/cpu_harness) uses it as the value-only form the analytic
+// Jacobian path must agree with bit for bit
 LFBA_HD void obs_residual(const CamModel& m, const TrackCtx& t, const double* e, double ox, double oy,
                           double r[2]) {
   const double cux = e[2] * m.gamma, cuy = e[3] * m.gamma;
@@ -434,7 +406,8 @@ struct FeatDims {
   static constexpr int NG = NQ + NF;            // + h(a) = sum f_a . r
 };
 
-// residual and features; F[a] = x component, F[NF + a] = y component of feature a
+// residual and features; F[a] = x component, F[NF + a] = y component of feature a. The fused kernel uses the reduced set
+// (obs_features9 + gram9_expand); this full set is the form the CPU harness checks the expansion against.
 template <int NC, int NRAD, class LensEntry>
 LFBA_HD void obs_features(const CamModel& m, const TrackCtx& t, const LensEntry& e, double ox, double oy, double r[2],
                           double* F) {

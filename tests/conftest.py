@@ -12,19 +12,6 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def _have_gpu():
-    try:
-        from lifcal_b200 import api
-        return api.device_count() > 0
-    except Exception:
-        return False
-
-
-def pytest_collection_modifyitems(config, items):
-    # -m gpu on a box without a GPU must fail loudly, not skip: the product has no CPU fallback.
-    pass
-
-
 @pytest.fixture(scope="session")
 def built():
     """Build everything once per session (no-op when the .so files are fresh)."""
