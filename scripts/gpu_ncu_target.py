@@ -14,5 +14,6 @@ ds.set_parameters(sc.camera_init, sc.views_init, sc.points_init)
 s = ds.run()
 print(name, "rows", s["num_iterations"], "cost", s["final_cost"], "gpu_ms", s["solve_gpu_ms"], "launches", s["gpu_launches"])
 if len(sys.argv) > 3:
-    print("eval-only ms", ds.time_eval(1, True))
+    print("eval-only ms (Ceres layout)", ds.time_eval(1, 1))
+    print("eval-only ms (live camera columns)", ds.time_eval(1, 2))
 ds.close()
