@@ -58,7 +58,9 @@ constexpr int kVWStride = 36;     // vw: V(18: 6x3 row-major) W(18)
 constexpr int kMaxLog = 1024;
 constexpr int kTile = 64;         // Cholesky tile
 
-__host__ __device__ inline int rec_stride(int nc) { return 9 + 3 * nc; }
+// doubles per track record: A (6) b (3) C (3 NC), padded to a multiple of 4 so that a record is a whole number of 32-byte
+// sectors for every model variant (NC = 8: 33 -> 36) and the 256-bit per-lane loads / stores always apply
+__host__ __device__ constexpr int rec_stride(int nc) { return (9 + 3 * nc + 3) & ~3; }
 
 // Skyline offsets in closed form (no dependent index loads on the latency chain). The solver lays the reduced system out
 // as: pose row r = 6 f + i starts at column 6 max(0, f - bw); border rows (coupled points, camera, rhs) start at column 0.

@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(128) k_points(Dev d) {
   const int cur = st->cur;
   constexpr int NH = NC * (NC + 1) / 2;
   constexpr int NV = NH + NC + 3;  // Schur cam-cam (NH), Schur cam gradient (NC), |g|^2, fail count, (max separately)
-  constexpr int RS = 9 + 3 * NC;
+  constexpr int RS = rec_stride(NC);
   __shared__ double red[4 * NV];
   __shared__ double redmax[4];
   double acc[NV];
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
   if (linear_phase_idle(st)) return;
   const int cur = st->cur;
   const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
-  constexpr int RS = 9 + 3 * NC;
+  constexpr int RS = rec_stride(NC);
   constexpr int NP = 21 + 6 + 6 + 6;  // S_ff (lower 21), reduced gradient, full gradient, diag(F^T F)
   constexpr int NV = NP + 6 * NC;     // + camera-pose block
   __shared__ double fe[kFrameStride];
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
 #pragma unroll
         for (int k = 3; k < RS / 4; ++k) ldg256(rcp + 4 * k, tmp + 4 * (k - 3));
 #pragma unroll
-        for (int k = 12; k < RS; ++k) cc[k - 9] = tmp[k - 12];
+        for (int k = 12; k < 9 + 3 * NC; ++k) cc[k - 9] = tmp[k - 12];
       } else if (RS % 2 == 0) {
 #pragma unroll
         for (int k = 5; k < RS / 2; ++k) {
@@ -960,7 +960,7 @@ __global__ void k_coupled(Dev d) {
   LmState* st = d.st;
   if (linear_phase_idle(st)) return;
   const int cur = st->cur;
-  constexpr int RS = 9 + 3 * NC;
+  constexpr int RS = rec_stride(NC);
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= d.Pc) return;
   const int p = d.coupled_pts[ci];

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   constexpr int NH = NC * (NC + 1) / 2;
   constexpr int NV = NH + NC + 1;
   constexpr int NVL = L == 1 ? 0 : (NV + L - 1) / L;  // L > 1: camera-block totals a lane owns (entries v with v % L == lane % L)
-  constexpr int RS = 9 + 3 * NC;
+  constexpr int RS = rec_stride(NC);  // padded to a multiple of 4: whole 32-byte sectors
   constexpr int NF9 = Feat9Dims<NC>::NF, NQ9 = Feat9Dims<NC>::NQ, NG9 = Feat9Dims<NC>::NG;
   constexpr int NQ = FeatDims<NC>::NQ, NG = FeatDims<NC>::NG;
   typedef GramMap<NC> GM;
@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
         // one lane owns the whole record: 256-bit (or 128-bit) stores instead of 8-byte ones, which reached L2 as 4.6 GB of
         // partially filled sectors for 1.15 GB of records (ncu l1tex__m_l1tex2xbar_write_bytes); measured -10% kernel time
         double rec_[RS];
+#pragma unroll
+        for (int k = 9 + 3 * NC; k < RS; ++k) rec_[k] = 0.0;  // padding
         int v = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
