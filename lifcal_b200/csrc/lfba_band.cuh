@@ -63,7 +63,10 @@ struct BandGeom {
     size_t a = (size_t)W8 * LDW;
     return a + (a & 1);
   }
-  __host__ __device__ size_t doubles() const { return x_offset() + (size_t)W8 * 6 + 2 * 28 + 24 + 8; }
+  __host__ __device__ size_t doubles() const {  // + L slots (2 x 28), snapshot (24), tile list (2 bytes each), private X (36)
+    const size_t nT = W8 >> 3, n_tiles = nT * (nT + 1) / 2;
+    return x_offset() + (size_t)W8 * 6 + 2 * 28 + 24 + ((n_tiles + 3) >> 2) + 36 + 24 + 8;
+  }
 };
 
 // Initial window: frames fa .. fa + bw (those that exist) and their border columns.
@@ -203,31 +206,57 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
     }
   };
 
+  // tile list of the trailing update (lower triangle of 8x8 tiles), decoded once
+  unsigned short* tile_ij = reinterpret_cast<unsigned short*>(snap + 24);  // [n_tiles] (I << 8) | J, behind the snapshot
+  for (int t = tid; t < n_tiles; t += nt) {
+    int I = 0, J = t;
+    while (J > I) { J -= I + 1; ++I; }
+    tile_ij[t] = (unsigned short)((I << 8) | J);
+  }
+  double* fx = snap + 24 + ((n_tiles + 3) >> 2);  // 36 + 24: the factorisation warp's own X rows of the next slot, and its copy of the snapshot
+
   int kmod = g.fa % bw1;
   if (warp < nww) prefetch(g.fa, kmod);
-  if (tid == FT && g.fa < g.fb) {  // first pivot: nothing to look ahead from
+  if (warp == nww && g.fa < g.fb) {  // first pivot: nothing to look ahead from
     const int s = 6 * kmod;
-    double a[21];
+    if (lane == 0) {
+      double a[21];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = A[(s + i) * LDW + s + j];
-    if (band_factor6(a, Lsm, g.dinv_out + 6 * g.fa)) *s_fail = 1;
+        for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = A[(s + i) * LDW + s + j];
+      if (band_factor6(a, Lsm, g.dinv_out + 6 * g.fa)) *s_fail = 1;
+    }
+    __syncwarp();
+    if (lane < 21) {
+      int i = 0, j = lane;
+      while (j > i) { j -= i + 1; ++i; }
+      g.S[sky.row(g.fa, i) + (6 * g.fa + j - sky.c0(g.fa))] = Lsm[lane];
+      if (g.fa + 1 < g.fb) {  // the second pivot block as it is now: input of the first look-ahead
+        const int s1 = 6 * (kmod + 1 == bw1 ? 0 : kmod + 1);
+        snap[lane] = A[(s1 + i) * LDW + s1 + j];
+      }
+    }
   }
   __syncthreads();
+  // Per pivot k the two groups run side by side and meet at the end of the step:
+  //   working warps   panel(k) with L_k | bar A | tensor-tile trailing update, L column block k -> HBM | bar B |
+  //                   refill of slot k, snapshot of pivot block k+2, prefetch
+  //   last warp       its own X rows of slot k+1 (6 rows), block (k+1) = snapshot - X X^T, Cholesky -> L_{k+1}
+  // so the 6x6 factorisation chain (the latency that cannot be parallelised) overlaps the panel AND the trailing update
+  // of the same step instead of following the panel. bar A also counts the last warp (arrive only): it has read the
+  // pivot-column entries of slot k+1 by then, which the refill behind bar B overwrites.
   for (int k = g.fa; k < g.fb; ++k) {
     const int s = 6 * kmod;
     const int kmod1 = kmod + 1 == bw1 ? 0 : kmod + 1, s1 = 6 * kmod1;
+    const int kmod2 = kmod1 + 1 == bw1 ? 0 : kmod1 + 1, s2 = 6 * kmod2;
     const double* Lc = Lsm + 28 * ((k - g.fa) & 1);
     double* Ln = Lsm + 28 * (((k - g.fa) & 1) ^ 1);
     const bool ahead = k + 1 < g.fb;
-    // ---- panel: X_r = A(r, pivot columns) L_kk^-T for every other row of the window (empty rows give zeros);
-    //      the pivot's own rows get X = 0 so that the tile update below needs no exclusions ----
-    double x[6] = {0, 0, 0, 0, 0, 0};
-    const bool prow_on = prow >= 0 && (prow < s || prow >= s + 6);
-    if (prow >= 0) {
-      const int r = prow;
-      if (prow_on) {
+    if (warp == nww) {
+      if (ahead && lane < 6) {
+        const int r = s1 + lane;
+        double x[6];
         if (r > s) {
 #pragma unroll
           for (int c = 0; c < 6; ++c) x[c] = A[r * LDW + s + c];
@@ -235,51 +264,29 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
 #pragma unroll
           for (int c = 0; c < 6; ++c) x[c] = A[(s + c) * LDW + r];
         }
-        double l[21], di[6];
-#pragma unroll
-        for (int e = 0; e < 21; ++e) l[e] = Lc[e];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) di[c] = Lc[21 + c];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           double acc = x[c];
 #pragma unroll
-          for (int j = 0; j < c; ++j) acc = fma(-x[j], l[c * (c + 1) / 2 + j], acc);
-          x[c] = acc * di[c];
+          for (int j = 0; j < c; ++j) acc = fma(-x[j], Lc[c * (c + 1) / 2 + j], acc);
+          x[c] = acc * Lc[21 + c];
         }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) fx[6 * lane + c] = x[c];
       }
-      double2* xd = reinterpret_cast<double2*>(Xs + (size_t)r * 6);
-      xd[0] = make_double2(x[0], x[1]);
-      xd[1] = make_double2(x[2], x[3]);
-      xd[2] = make_double2(x[4], x[5]);
-    } else if (warp == nww) {
-      if (lane < 21 && ahead) {  // snapshot of the next pivot block (the tile update will also touch it)
-        int i = 0, j = lane;
-        while (j > i) { j -= i + 1; ++i; }
-        snap[lane] = A[(s1 + i) * LDW + s1 + j];
-      }
-      if (lane >= 11) {  // L_kk itself goes back to HBM
-        const int e = lane - 11;
-        int i = 0, j = e;
-        while (j > i) { j -= i + 1; ++i; }
-        g.S[sky.row(k, i) + (6 * k + j - sky.c0(k))] = Lc[e];
-      }
-    }
-    __syncthreads();
-    if (warp == nww) {
-      // ---- look-ahead: the next pivot block gets its update from this step and is factorised right away. Lanes 0..20
-      //      update one entry each (two 3-term chains), lane 0 collects them through shared memory and runs the chain ----
+      if (ahead && lane < 21) fx[36 + lane] = snap[lane];  // private copy: the workers rewrite the snapshot behind bar B
+      __syncwarp();
+      asm volatile("bar.arrive 1, %0;" ::"r"(nt) : "memory");
       if (ahead) {
         double* scratch = Ln;  // the next pivot's L slot doubles as the exchange buffer (overwritten by the factorisation)
         if (lane < 21) {
           int i = 0, j = lane;
           while (j > i) { j -= i + 1; ++i; }
-          const double2* xi = reinterpret_cast<const double2*>(Xs + (size_t)(s1 + i) * 6);
-          const double2* xj = reinterpret_cast<const double2*>(Xs + (size_t)(s1 + j) * 6);
-          const double2 a0 = xi[0], a1 = xi[1], a2 = xi[2], b0 = xj[0], b1 = xj[1], b2 = xj[2];
-          const double d0 = fma(a0.x, b0.x, fma(a0.y, b0.y, a1.x * b1.x));
-          const double d1 = fma(a1.y, b1.y, fma(a2.x, b2.x, a2.y * b2.y));
-          scratch[lane] = snap[lane] - (d0 + d1);
+          const double* xi = fx + 6 * i;
+          const double* xj = fx + 6 * j;
+          const double d0 = fma(xi[0], xj[0], fma(xi[1], xj[1], xi[2] * xj[2]));
+          const double d1 = fma(xi[3], xj[3], fma(xi[4], xj[4], xi[5] * xj[5]));
+          scratch[lane] = fx[36 + lane] - (d0 + d1);
         }
         __syncwarp();
         if (lane == 0) {
@@ -288,15 +295,53 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
           for (int e = 0; e < 21; ++e) a[e] = scratch[e];
           if (band_factor6(a, Ln, g.dinv_out + 6 * (k + 1))) *s_fail = 1;
         }
+        __syncwarp();
+        if (lane < 21) {  // L_{k+1,k+1} itself goes back to HBM
+          int i = 0, j = lane;
+          while (j > i) { j -= i + 1; ++i; }
+          g.S[sky.row(k + 1, i) + (6 * (k + 1) + j - sky.c0(k + 1))] = Ln[lane];
+        }
       }
     } else {
+      // ---- panel: X_r = A(r, pivot columns) L_kk^-T for every other row of the window (empty rows give zeros);
+      //      the pivot's own rows get X = 0 so that the tile update below needs no exclusions ----
+      double x[6] = {0, 0, 0, 0, 0, 0};
+      const bool prow_on = prow >= 0 && (prow < s || prow >= s + 6);
+      if (prow >= 0) {
+        const int r = prow;
+        if (prow_on) {
+          if (r > s) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) x[c] = A[r * LDW + s + c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) x[c] = A[(s + c) * LDW + r];
+          }
+          double l[21], di[6];
+#pragma unroll
+          for (int e = 0; e < 21; ++e) l[e] = Lc[e];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) di[c] = Lc[21 + c];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            double acc = x[c];
+#pragma unroll
+            for (int j = 0; j < c; ++j) acc = fma(-x[j], l[c * (c + 1) / 2 + j], acc);
+            x[c] = acc * di[c];
+          }
+        }
+        double2* xd = reinterpret_cast<double2*>(Xs + (size_t)r * 6);
+        xd[0] = make_double2(x[0], x[1]);
+        xd[1] = make_double2(x[2], x[3]);
+        xd[2] = make_double2(x[4], x[5]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
       // ---- trailing update, A(a, b) -= X_a . X_b for a >= b in slot order, as 8x8 tensor tiles (two m8n8k4 DMMAs each;
       //      K = 6 padded to 8 with zeros). Diagonal tiles also write their (unused) upper half; rows of the pivot slot and
       //      the padding rows have X = 0 ----
       const int lr = lane >> 2, lc = lane & 3;
       for (int t = warp; t < n_tiles; t += nww) {
-        int I = 0, J = t;
-        while (J > I) { J -= I + 1; ++I; }
+        const int ij = tile_ij[t], I = ij >> 8, J = ij & 255;
         const double* xi = Xs + (size_t)(8 * I + lr) * 6;
         const double* xj = Xs + (size_t)(8 * J + lr) * 6;
         const double a0 = -xi[lc], a1 = lc < 2 ? -xi[4 + lc] : 0.0;
@@ -327,10 +372,8 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
           for (int c = 0; c < 6; ++c) dst[c] = x[c];
         }
       }
-    }
-    __syncthreads();
-    // ---- the freed slot takes frame k + bw + 1 (or zeros): every entry of the region is written by its one owner ----
-    if (warp < nww) {
+      asm volatile("bar.sync 2, %0;" ::"r"(nt - 32) : "memory");
+      // ---- the freed slot takes frame k + bw + 1 (or zeros): every entry of the region is written by its one owner ----
 #pragma unroll
       for (int q = 0; q < kBandPref; ++q) {
         const int r = er[q] == -2 ? (tid + q * npf) / 6 : er[q], i = ei[q];
@@ -342,6 +385,11 @@ __device__ inline void band_sweep(const BandArgs& g, double* A, int* s_fail) {
           const int b = s + i;
           A[max(r, b) * LDW + min(r, b)] = pv[q];
         }
+      }
+      if (tid < 21 && k + 2 < g.fb) {  // pivot block k + 2 after this step's update: input of the next look-ahead
+        int i = 0, j = tid;
+        while (j > i) { j -= i + 1; ++i; }
+        snap[tid] = A[(s2 + i) * LDW + s2 + j];
       }
       row0 += fstride;
       prefetch(k + 1, kmod1);  // in flight during the whole next step
