@@ -48,6 +48,7 @@ struct CamModel {
   double dcrx, dcry;    // d c_raw / d camera[3], camera[4]
   double sx, sy, isx, isy;  // raw pixel size (mm) and reciprocal
   double k0, k1, t0, t1;
+  double k0x2, k1x4, t0x2, t1x2, t0x6, t1x6;  // multiples used by dist_shift_jac
   double invD, alpha, zC0, gB, inv_fL, gamma;
   double dalpha_dfL, dalpha_dbL0, dz_dfL, dz_dbL0, dgB_dfL, dgB_dbL0, dgB_dB, dgamma_dbL0, dgamma_dB;
   double loss_b, loss_c;  // Cauchy: b = a^2, c = 1/b
@@ -78,6 +79,12 @@ LFBA_HD void cam_model_init(CamModel& m, const double* c, uint32_t config, doubl
   m.k1 = m.n_radial > 1 ? c[6] : 0.0;
   m.t0 = m.tangential ? c[5 + m.n_radial] : 0.0;
   m.t1 = m.tangential ? c[6 + m.n_radial] : 0.0;
+  m.k0x2 = 2.0 * m.k0;
+  m.k1x4 = 4.0 * m.k1;
+  m.t0x2 = 2.0 * m.t0;
+  m.t1x2 = 2.0 * m.t1;
+  m.t0x6 = 6.0 * m.t0;
+  m.t1x6 = 6.0 * m.t1;
   const double D = m.fL - m.bL0;
   m.invD = 1.0 / D;
   m.alpha = m.fL * m.invD;
@@ -110,33 +117,38 @@ LFBA_HD void cam_model_init(CamModel& m, const double* c, uint32_t config, doubl
 LFBA_HD void dist_shift(const CamModel& m, double x, double y, double& dx, double& dy) {
   // same expression tree as dist_shift_jac so both paths round identically
   const double xx = x * x, yy = y * y, xy = x * y;
-  const double r2 = xx + yy, r4 = r2 * r2;
-  const double dr = m.k0 * r2 + m.k1 * r4;
-  dx = x * dr + m.t0 * (r2 + 2.0 * xx) + 2.0 * m.t1 * xy;
-  dy = y * dr + m.t1 * (r2 + 2.0 * yy) + 2.0 * m.t0 * xy;
+  const double r2 = xx + yy;
+  const double dr = r2 * fma(m.k1, r2, m.k0);
+  const double ax = fma(2.0, xx, r2), ay = fma(2.0, yy, r2), xy2 = xy + xy;
+  dx = fma(x, dr, fma(m.t0, ax, m.t1 * xy2));
+  dy = fma(y, dr, fma(m.t1, ay, m.t0 * xy2));
 }
 
-// shift, its 2x2 Jacobian A = d(shift)/d(x,y) (row-major) and d(shift)/d(k0,k1,t0,t1) (each a 2-vector)
-LFBA_HD void dist_shift_jac(const CamModel& m, double x, double y, double& dx, double& dy, double A[4],
+// shift, its 2x2 Jacobian A = d(shift)/d(x,y) and d(shift)/d(k0,k1,t0,t1) (each a 2-vector). A is symmetric:
+// A[0] = d dx/dx, A[1] = d dx/dy = d dy/dx, A[2] = d dy/dy. 30 FP64 instructions (multiples of the coefficients are
+// model constants): this runs once per observation inside the fused evaluation kernel.
+//   dr = k0 r2 + k1 r2^2,  dr' = k0 + 2 k1 r2
+//   dx = x dr + t0 (r2 + 2 x^2) + 2 t1 x y,   dy = y dr + t1 (r2 + 2 y^2) + 2 t0 x y
+LFBA_HD void dist_shift_jac(const CamModel& m, double x, double y, double& dx, double& dy, double A[3],
                             double dk0[2], double dk1[2], double dt0[2], double dt1[2]) {
   const double xx = x * x, yy = y * y, xy = x * y;
   const double r2 = xx + yy, r4 = r2 * r2;
-  const double dr = m.k0 * r2 + m.k1 * r4;
-  const double ddr = m.k0 + 2.0 * m.k1 * r2;  // d(dr)/d(r2)
-  dx = x * dr + m.t0 * (r2 + 2.0 * xx) + 2.0 * m.t1 * xy;
-  dy = y * dr + m.t1 * (r2 + 2.0 * yy) + 2.0 * m.t0 * xy;
-  A[0] = dr + 2.0 * xx * ddr + 6.0 * m.t0 * x + 2.0 * m.t1 * y;
-  A[1] = 2.0 * xy * ddr + 2.0 * m.t0 * y + 2.0 * m.t1 * x;
-  A[2] = 2.0 * xy * ddr + 2.0 * m.t1 * x + 2.0 * m.t0 * y;
-  A[3] = dr + 2.0 * yy * ddr + 6.0 * m.t1 * y + 2.0 * m.t0 * x;
+  const double dr = r2 * fma(m.k1, r2, m.k0);
+  const double ddr2 = fma(m.k1x4, r2, m.k0x2);  // 2 dr'
+  const double ax = fma(2.0, xx, r2), ay = fma(2.0, yy, r2), xy2 = xy + xy;
+  dx = fma(x, dr, fma(m.t0, ax, m.t1 * xy2));
+  dy = fma(y, dr, fma(m.t1, ay, m.t0 * xy2));
+  A[0] = fma(m.t1x2, y, fma(m.t0x6, x, fma(xx, ddr2, dr)));
+  A[1] = fma(xy, ddr2, fma(m.t0x2, y, m.t1x2 * x));
+  A[2] = fma(m.t0x2, x, fma(m.t1x6, y, fma(yy, ddr2, dr)));
   dk0[0] = x * r2;
   dk0[1] = y * r2;
   dk1[0] = x * r4;
   dk1[1] = y * r4;
-  dt0[0] = r2 + 2.0 * xx;
-  dt0[1] = 2.0 * xy;
-  dt1[0] = 2.0 * xy;
-  dt1[1] = r2 + 2.0 * yy;
+  dt0[0] = ax;
+  dt0[1] = xy2;
+  dt1[0] = xy2;
+  dt1[1] = ay;
 }
 
 // One lens-table entry: u_0 = cd, u_i = cd - shift(u_{i-1}), i = 1..10 (exactly ten steps, src/CameraModel.h:109),
@@ -149,10 +161,10 @@ LFBA_HD void lens_entry(const CamModel& m, double mx, double my, double* e) {
   double E[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // E[2*k + row], k = k0,k1,t0,t1
   if (m.any_dist) {
     for (int it = 0; it < 10; ++it) {
-      double dx, dy, A[4], d[8];
+      double dx, dy, A[3], d[8];
       dist_shift_jac(m, ux, uy, dx, dy, A, d + 0, d + 2, d + 4, d + 6);
       const double n0 = 1.0 - (A[0] * U[0] + A[1] * U[2]), n1 = -(A[0] * U[1] + A[1] * U[3]);
-      const double n2 = -(A[2] * U[0] + A[3] * U[2]), n3 = 1.0 - (A[2] * U[1] + A[3] * U[3]);
+      const double n2 = -(A[1] * U[0] + A[2] * U[2]), n3 = 1.0 - (A[1] * U[1] + A[2] * U[3]);
       U[0] = n0;
       U[1] = n1;
       U[2] = n2;
@@ -160,7 +172,7 @@ LFBA_HD void lens_entry(const CamModel& m, double mx, double my, double* e) {
       for (int k = 0; k < 4; ++k) {
         const double ex = E[2 * k], ey = E[2 * k + 1];
         E[2 * k] = -(A[0] * ex + A[1] * ey) - d[2 * k];
-        E[2 * k + 1] = -(A[2] * ex + A[3] * ey) - d[2 * k + 1];
+        E[2 * k + 1] = -(A[1] * ex + A[2] * ey) - d[2 * k + 1];
       }
       ux = (cdx - dx);
       uy = (cdy - dy);
@@ -245,6 +257,7 @@ LFBA_HD void track_point(const double* fe, const double* X, double Pc[3]) {
 }
 
 struct TrackCtx {
+  double wpx, wpy; // gB * P_c.xy / q_z: the part of the projected point that does not depend on the micro lens
   double Px, Py;   // P_c.xy / q_z
   double a1;       // alpha / q_z
   double g1;       // gB / q_z
@@ -258,6 +271,8 @@ LFBA_HD void track_setup(const CamModel& m, const double Pc[3], TrackCtx& t) {
   t.Py = Pc[1] * iq;
   t.a1 = m.alpha * iq;
   t.g1 = m.gB * iq;
+  t.wpx = t.g1 * Pc[0];
+  t.wpy = t.g1 * Pc[1];
   const double kappa = m.gB * (t.a1 - m.inv_fL);  // d pm / d cu
   const double k1 = m.ml_adjust ? kappa + 1.0 : kappa;
   t.kl = k1 * m.gamma;
@@ -277,17 +292,51 @@ LFBA_HD void track_setup(const CamModel& m, const double Pc[3], TrackCtx& t) {
   t.bB = m.sg[2] * bB;
 }
 
+// ---- one observation ------------------------------------------------------------------------------------------
+// Projection of src/CameraModel.h:127-195 at fixed (camera, pose, point), as a function of the micro lens:
+//   q  = P + a1 gamma u,   pm = gB (q - gamma u / fL) = gB P + kappa gamma u,   w0 = pm + gamma u  (mlAdj)
+// i.e. w0 = wp + kl u with the per-TRACK wp = gB P and kl (track_setup): two FMAs per observation.
+//   mlAdj:  w = w0 + shift(w0)                r = w / s + c_raw - o      M = d r / d w0 = diag(1/s) (I + A(w0))
+//   else :  w = w0 + (m - c_raw) s            (no forward distortion)   M = diag(1/s)
+// dk = d shift / d(k0,k1,t0,t1) at w0 (the direct term of the forward distortion), zero unless mlAdj with distortion.
+// Every form below (value only, Jacobian, features) goes through this one function: they agree bit for bit.
+// ml_adjust / any_dist are passed beside the model so that a caller that knows them at compile time (the fused kernel)
+// gets straight-line code.
+template <class LensEntry>
+LFBA_HD void obs_core(const CamModel& m, const TrackCtx& t, const LensEntry& e, double ox, double oy, double r[2],
+                      double M[4], double dk[8], const bool ml_adjust, const bool any_dist) {
+  double wx = fma(t.kl, e[2], t.wpx), wy = fma(t.kl, e[3], t.wpy);
+  M[0] = m.isx;
+  M[1] = 0.0;
+  M[2] = 0.0;
+  M[3] = m.isy;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dk[k] = 0.0;
+  if (ml_adjust) {
+    if (any_dist) {
+      double dx, dy, A[3];
+      dist_shift_jac(m, wx, wy, dx, dy, A, dk + 0, dk + 2, dk + 4, dk + 6);
+      wx += dx;
+      wy += dy;
+      M[0] = fma(m.isx, A[0], m.isx);
+      M[1] = m.isx * A[1];
+      M[2] = m.isy * A[1];
+      M[3] = fma(m.isy, A[2], m.isy);
+    }
+  } else {
+    wx = fma(e[0] - m.crx, m.sx, wx);
+    wy = fma(e[1] - m.cry, m.sy, wy);
+  }
+  r[0] = fma(wx, m.isx, m.crx) - ox;
+  r[1] = fma(wy, m.isy, m.cry) - oy;
+}
+
 // residual only. Not called by a kernel: the CPU harness (tests/cpu_harness) uses it as the value-only form the analytic
 // Jacobian path must agree with bit for bit
 LFBA_HD void obs_residual(const CamModel& m, const TrackCtx& t, const double* e, double ox, double oy,
                           double r[2]) {
-  const double cux = e[2] * m.gamma, cuy = e[3] * m.gamma;
-  const double qx = t.Px + t.a1 * cux, qy = t.Py + t.a1 * cuy;
-  const double pmx = (qx - cux * m.inv_fL) * m.gB, pmy = (qy - cuy * m.inv_fL) * m.gB;
-  double wx, wy;
+  double wx = fma(t.kl, e[2], t.wpx), wy = fma(t.kl, e[3], t.wpy);
   if (m.ml_adjust) {
-    wx = pmx + cux;
-    wy = pmy + cuy;
     if (m.any_dist) {
       double dx, dy;
       dist_shift(m, wx, wy, dx, dy);
@@ -295,11 +344,48 @@ LFBA_HD void obs_residual(const CamModel& m, const TrackCtx& t, const double* e,
       wy += dy;
     }
   } else {
-    wx = pmx + (e[0] - m.crx) * m.sx;
-    wy = pmy + (e[1] - m.cry) * m.sy;
+    wx = fma(e[0] - m.crx, m.sx, wx);
+    wy = fma(e[1] - m.cry, m.sy, wy);
   }
-  r[0] = (wx * m.isx + m.crx) - ox;
-  r[1] = (wy * m.isy + m.cry) - oy;
+  r[0] = fma(wx, m.isx, m.crx) - ox;
+  r[1] = fma(wy, m.isy, m.cry) - oy;
+}
+
+// Columns of d r / d(cx, cy, k0.., t0, t1) — what every form shares: through u (lens table, scaled by the per-track
+// kl: Mk = kl M), through (m - c_raw) when !mlAdj, the additive + c_raw of the output, and the direct term of the
+// forward distortion. out_x[c], out_y[c] for c = 0 .. NC-4 (cx, cy, then the live distortion parameters).
+template <int NC, int NRAD, class LensEntry>
+LFBA_HD void obs_lens_columns(const CamModel& m, const TrackCtx& t, const LensEntry& e, const double M[4],
+                              const double dk[8], double* out_x, double* out_y, const bool ml_adjust,
+                              const bool any_dist) {
+  constexpr int TAN = (NC - 5 - NRAD) / 2;
+  const double K00 = t.kl * M[0], K01 = t.kl * M[1], K10 = t.kl * M[2], K11 = t.kl * M[3];
+  double c3x = m.dcrx, c3y = 0.0, c4x = 0.0, c4y = m.dcry;
+  if (!ml_adjust) {
+    const double d3 = -m.dcrx * m.sx, d4 = -m.dcry * m.sy;
+    c3x = fma(M[0], d3, c3x);
+    c3y = M[2] * d3;
+    c4x = M[1] * d4;
+    c4y = fma(M[3], d4, c4y);
+  }
+  out_x[0] = fma(K00, e[4], fma(K01, e[5], c3x));
+  out_y[0] = fma(K10, e[4], fma(K11, e[5], c3y));
+  out_x[1] = fma(K00, e[6], fma(K01, e[7], c4x));
+  out_y[1] = fma(K10, e[6], fma(K11, e[7], c4y));
+  const bool fwd = ml_adjust && any_dist;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool live = (k == 0 && NRAD > 0) || (k == 1 && NRAD > 1) || (k >= 2 && TAN);
+    if (!live) continue;
+    const int col = 2 + (k < 2 ? k : NRAD + (k - 2));  // compile-time after unrolling
+    double jx = K01 * e[9 + 2 * k], jy = K11 * e[9 + 2 * k];
+    if (fwd) {
+      jx = fma(dk[2 * k], m.isx, jx);
+      jy = fma(dk[2 * k + 1], m.isy, jy);
+    }
+    out_x[col] = fma(K00, e[8 + 2 * k], jx);
+    out_y[col] = fma(K10, e[8 + 2 * k], jy);
+  }
 }
 
 // residual + analytic Jacobian. G: 2x3 row-major d r / d P_c.  Jc: 2 x NC row-major, columns in camera-block
@@ -312,40 +398,18 @@ LFBA_HD void obs_eval(const CamModel& m, const TrackCtx& t, const LensEntry& e, 
                       double G[6], double* Jc) {
   constexpr int TAN = (NC - 5 - NRAD) / 2;
   static_assert(5 + NRAD + 2 * TAN == NC && NRAD >= 0 && NRAD <= 2 && (TAN == 0 || TAN == 1), "NC / NRAD mismatch");
+  double M[4], dk[8];
+  obs_core(m, t, e, ox, oy, r, M, dk, m.ml_adjust != 0, m.any_dist != 0);
   const double ux = e[2], uy = e[3];
-  const double cux = ux * m.gamma, cuy = uy * m.gamma;
-  const double qx = t.Px + t.a1 * cux, qy = t.Py + t.a1 * cuy;
-  const double pmx = (qx - cux * m.inv_fL) * m.gB, pmy = (qy - cuy * m.inv_fL) * m.gB;
-  double wx, wy;
-  double M00 = m.isx, M01 = 0.0, M10 = 0.0, M11 = m.isy;  // diag(1/s) (I + A)
-  double dk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool fwd = m.ml_adjust && m.any_dist;
-  if (m.ml_adjust) {
-    wx = pmx + cux;
-    wy = pmy + cuy;
-    if (m.any_dist) {
-      double dx, dy, A[4];
-      dist_shift_jac(m, wx, wy, dx, dy, A, dk + 0, dk + 2, dk + 4, dk + 6);
-      wx += dx;
-      wy += dy;
-      M00 = m.isx * (1.0 + A[0]);
-      M01 = m.isx * A[1];
-      M10 = m.isy * A[2];
-      M11 = m.isy * (1.0 + A[3]);
-    }
-  } else {
-    wx = pmx + (e[0] - m.crx) * m.sx;
-    wy = pmy + (e[1] - m.cry) * m.sy;
-  }
-  r[0] = (wx * m.isx + m.crx) - ox;
-  r[1] = (wy * m.isy + m.cry) - oy;
+  const double ca = t.a1 * m.gamma;
+  const double qx = fma(ca, ux, t.Px), qy = fma(ca, uy, t.Py);
 
   // d r / d P_c = M * g1 * [I | -q]
-  G[0] = M00 * t.g1;
-  G[1] = M01 * t.g1;
+  G[0] = M[0] * t.g1;
+  G[1] = M[1] * t.g1;
   G[2] = -(G[0] * qx + G[1] * qy);
-  G[3] = M10 * t.g1;
-  G[4] = M11 * t.g1;
+  G[3] = M[2] * t.g1;
+  G[4] = M[3] * t.g1;
   G[5] = -(G[3] * qx + G[4] * qy);
 
   // fL, bL0, B
@@ -353,47 +417,20 @@ LFBA_HD void obs_eval(const CamModel& m, const TrackCtx& t, const LensEntry& e, 
     const double dfx = ux * t.af + qx * t.bf, dfy = uy * t.af + qy * t.bf;
     const double dbx = ux * t.ab + qx * t.bb, dby = uy * t.ab + qy * t.bb;
     const double dBx = ux * t.aB + qx * t.bB, dBy = uy * t.aB + qy * t.bB;
-    Jc[0] = M00 * dfx + M01 * dfy;
-    Jc[NC + 0] = M10 * dfx + M11 * dfy;
-    Jc[1] = M00 * dbx + M01 * dby;
-    Jc[NC + 1] = M10 * dbx + M11 * dby;
-    Jc[2] = M00 * dBx + M01 * dBy;
-    Jc[NC + 2] = M10 * dBx + M11 * dBy;
+    Jc[0] = M[0] * dfx + M[1] * dfy;
+    Jc[NC + 0] = M[2] * dfx + M[3] * dfy;
+    Jc[1] = M[0] * dbx + M[1] * dby;
+    Jc[NC + 1] = M[2] * dbx + M[3] * dby;
+    Jc[2] = M[0] * dBx + M[1] * dBy;
+    Jc[NC + 2] = M[2] * dBx + M[3] * dBy;
   }
-  // cx, cy: through u (lens table), through cd when !mlAdj, and the additive + c_raw of the output
-  {
-    double d3x = t.kl * e[4], d3y = t.kl * e[5];
-    double d4x = t.kl * e[6], d4y = t.kl * e[7];
-    if (!m.ml_adjust) {
-      d3x += -m.dcrx * m.sx;
-      d4y += -m.dcry * m.sy;
-    }
-    Jc[3] = M00 * d3x + M01 * d3y + m.dcrx;
-    Jc[NC + 3] = M10 * d3x + M11 * d3y;
-    Jc[4] = M00 * d4x + M01 * d4y;
-    Jc[NC + 4] = M10 * d4x + M11 * d4y + m.dcry;
-  }
-  // distortion parameters: through u, plus the direct term of the forward distortion (mlAdj only)
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool live = (k == 0 && NRAD > 0) || (k == 1 && NRAD > 1) || (k >= 2 && TAN);
-    if (!live) continue;
-    const int col = 5 + (k < 2 ? k : NRAD + (k - 2));  // compile-time after unrolling
-    const double dx = t.kl * e[8 + 2 * k], dy = t.kl * e[9 + 2 * k];
-    double jx = M00 * dx + M01 * dy, jy = M10 * dx + M11 * dy;
-    if (fwd) {
-      jx += dk[2 * k] * m.isx;
-      jy += dk[2 * k + 1] * m.isy;
-    }
-    Jc[col] = jx;
-    Jc[NC + col] = jy;
-  }
+  obs_lens_columns<NC, NRAD>(m, t, e, M, dk, Jc + 3, Jc + NC + 3, m.ml_adjust != 0, m.any_dist != 0);
 }
 
 // ---- feature form of the per-observation Jacobian ---------------------------------------------------------
 // Inside one track every Jacobian column of an observation is a combination, with per-TRACK coefficients, of a few
-// per-observation 2-vectors ("features"). With Ms = diag(1/s)(I + A) (2x2), q and u as in obs_eval:
-//     f0 = Ms[:,0]   f1 = Ms[:,1]   f2 = Ms q   f3 = Ms u   f(4+j) = d r / d camera[3+j]   (j = 0 .. NC-4)
+// per-observation 2-vectors ("features"). With M (2x2), q and u as above:
+//     f0 = M[:,0]   f1 = M[:,1]   f2 = M q   f3 = M u   f(4+j) = d r / d camera[3+j]   (j = 0 .. NC-4)
 //     d r/d P_c   = g1 [ f0 | f1 | -f2 ]
 //     d r/d fL    = af f3 + bf f2,   d r/d bL0 = ab f3 + bb f2,   d r/d B = aB f3 + bB f2
 // so the normal-equation blocks of a track follow from the Gram matrix of NF = NC + 1 features (+ their products with
@@ -414,71 +451,24 @@ LFBA_HD void obs_features(const CamModel& m, const TrackCtx& t, const LensEntry&
   constexpr int NF = NC + 1;
   constexpr int TAN = (NC - 5 - NRAD) / 2;
   static_assert(5 + NRAD + 2 * TAN == NC && NRAD >= 0 && NRAD <= 2 && (TAN == 0 || TAN == 1), "NC / NRAD mismatch");
+  double M[4], dk[8];
+  obs_core(m, t, e, ox, oy, r, M, dk, m.ml_adjust != 0, m.any_dist != 0);
   const double ux = e[2], uy = e[3];
-  const double cux = ux * m.gamma, cuy = uy * m.gamma;
-  const double qx = t.Px + t.a1 * cux, qy = t.Py + t.a1 * cuy;
-  const double pmx = (qx - cux * m.inv_fL) * m.gB, pmy = (qy - cuy * m.inv_fL) * m.gB;
-  double wx, wy;
-  double M00 = m.isx, M01 = 0.0, M10 = 0.0, M11 = m.isy;
-  double dk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool fwd = m.ml_adjust && m.any_dist;
-  if (m.ml_adjust) {
-    wx = pmx + cux;
-    wy = pmy + cuy;
-    if (m.any_dist) {
-      double dx, dy, A[4];
-      dist_shift_jac(m, wx, wy, dx, dy, A, dk + 0, dk + 2, dk + 4, dk + 6);
-      wx += dx;
-      wy += dy;
-      M00 = m.isx * (1.0 + A[0]);
-      M01 = m.isx * A[1];
-      M10 = m.isy * A[2];
-      M11 = m.isy * (1.0 + A[3]);
-    }
-  } else {
-    wx = pmx + (e[0] - m.crx) * m.sx;
-    wy = pmy + (e[1] - m.cry) * m.sy;
-  }
-  r[0] = (wx * m.isx + m.crx) - ox;
-  r[1] = (wy * m.isy + m.cry) - oy;
-  F[0] = M00;
-  F[NF + 0] = M10;
-  F[1] = M01;
-  F[NF + 1] = M11;
-  F[2] = M00 * qx + M01 * qy;
-  F[NF + 2] = M10 * qx + M11 * qy;
-  F[3] = M00 * ux + M01 * uy;
-  F[NF + 3] = M10 * ux + M11 * uy;
-  {
-    double d3x = t.kl * e[4], d3y = t.kl * e[5];
-    double d4x = t.kl * e[6], d4y = t.kl * e[7];
-    if (!m.ml_adjust) {
-      d3x += -m.dcrx * m.sx;
-      d4y += -m.dcry * m.sy;
-    }
-    F[4] = M00 * d3x + M01 * d3y + m.dcrx;
-    F[NF + 4] = M10 * d3x + M11 * d3y;
-    F[5] = M00 * d4x + M01 * d4y;
-    F[NF + 5] = M10 * d4x + M11 * d4y + m.dcry;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool live = (k == 0 && NRAD > 0) || (k == 1 && NRAD > 1) || (k >= 2 && TAN);
-    if (!live) continue;
-    const int col = 5 + (k < 2 ? k : NRAD + (k - 2));  // compile-time after unrolling
-    const double dx = t.kl * e[8 + 2 * k], dy = t.kl * e[9 + 2 * k];
-    double jx = M00 * dx + M01 * dy, jy = M10 * dx + M11 * dy;
-    if (fwd) {
-      jx += dk[2 * k] * m.isx;
-      jy += dk[2 * k + 1] * m.isy;
-    }
-    F[col + 1] = jx;
-    F[NF + col + 1] = jy;
-  }
+  const double ca = t.a1 * m.gamma;
+  const double qx = fma(ca, ux, t.Px), qy = fma(ca, uy, t.Py);
+  F[0] = M[0];
+  F[NF + 0] = M[2];
+  F[1] = M[1];
+  F[NF + 1] = M[3];
+  F[2] = M[0] * qx + M[1] * qy;
+  F[NF + 2] = M[2] * qx + M[3] * qy;
+  F[3] = M[0] * ux + M[1] * uy;
+  F[NF + 3] = M[2] * ux + M[3] * uy;
+  obs_lens_columns<NC, NRAD>(m, t, e, M, dk, F + 4, F + NF + 4, m.ml_adjust != 0, m.any_dist != 0);
 }
 
 // ---- reduced feature set (NC + 0 features) --------------------------------------------------------------------
-// f2 = Ms q is not independent: q = P + (a1 gamma) u with per-TRACK P and a1, so f2 = Px f0 + Py f1 + (a1 gamma) f3.
+// f2 = M q is not independent: q = P + (a1 gamma) u with per-TRACK P and a1, so f2 = Px f0 + Py f1 + (a1 gamma) f3.
 // Dropping it leaves NF9 = NC features [f0, f1, f3, f4, ...] and 54 instead of 65 running sums for NC = 9; the
 // sums that involve f2 are rebuilt once per track (gram9_expand) — the same algebra, 22 fewer DFMA per observation.
 template <int NC>
@@ -490,71 +480,22 @@ struct Feat9Dims {
 
 // residual and the NC features; F[a] = x component, F[NC + a] = y component.
 // New index -> old index (obs_features): 0 -> 0, 1 -> 1, a >= 2 -> a + 1.
+// For NC = 9 with mlAdj and distortion: 42 (obs_core) + 4 + 36 FP64 instructions; only wp, kl of the track are read.
 template <int NC, int NRAD, class LensEntry>
 LFBA_HD void obs_features9(const CamModel& m, const TrackCtx& t, const LensEntry& e, double ox, double oy, double r[2],
-                           double* F) {
+                           double* F, const bool ml_adjust, const bool any_dist) {
   constexpr int NF = NC;
   constexpr int TAN = (NC - 5 - NRAD) / 2;
   static_assert(5 + NRAD + 2 * TAN == NC && NRAD >= 0 && NRAD <= 2 && (TAN == 0 || TAN == 1), "NC / NRAD mismatch");
-  const double ux = e[2], uy = e[3];
-  const double cux = ux * m.gamma, cuy = uy * m.gamma;
-  const double qx = t.Px + t.a1 * cux, qy = t.Py + t.a1 * cuy;
-  const double pmx = (qx - cux * m.inv_fL) * m.gB, pmy = (qy - cuy * m.inv_fL) * m.gB;
-  double wx, wy;
-  double M00 = m.isx, M01 = 0.0, M10 = 0.0, M11 = m.isy;
-  double dk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool fwd = m.ml_adjust && m.any_dist;
-  if (m.ml_adjust) {
-    wx = pmx + cux;
-    wy = pmy + cuy;
-    if (m.any_dist) {
-      double dx, dy, A[4];
-      dist_shift_jac(m, wx, wy, dx, dy, A, dk + 0, dk + 2, dk + 4, dk + 6);
-      wx += dx;
-      wy += dy;
-      M00 = m.isx * (1.0 + A[0]);
-      M01 = m.isx * A[1];
-      M10 = m.isy * A[2];
-      M11 = m.isy * (1.0 + A[3]);
-    }
-  } else {
-    wx = pmx + (e[0] - m.crx) * m.sx;
-    wy = pmy + (e[1] - m.cry) * m.sy;
-  }
-  r[0] = (wx * m.isx + m.crx) - ox;
-  r[1] = (wy * m.isy + m.cry) - oy;
-  F[0] = M00;
-  F[NF + 0] = M10;
-  F[1] = M01;
-  F[NF + 1] = M11;
-  F[2] = M00 * ux + M01 * uy;
-  F[NF + 2] = M10 * ux + M11 * uy;
-  {
-    double d3x = t.kl * e[4], d3y = t.kl * e[5];
-    double d4x = t.kl * e[6], d4y = t.kl * e[7];
-    if (!m.ml_adjust) {
-      d3x += -m.dcrx * m.sx;
-      d4y += -m.dcry * m.sy;
-    }
-    F[3] = M00 * d3x + M01 * d3y + m.dcrx;
-    F[NF + 3] = M10 * d3x + M11 * d3y;
-    F[4] = M00 * d4x + M01 * d4y;
-    F[NF + 4] = M10 * d4x + M11 * d4y + m.dcry;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool live = (k == 0 && NRAD > 0) || (k == 1 && NRAD > 1) || (k >= 2 && TAN);
-    if (!live) continue;
-    const int col = 5 + (k < 2 ? k : NRAD + (k - 2));  // compile-time after unrolling
-    const double dx = t.kl * e[8 + 2 * k], dy = t.kl * e[9 + 2 * k];
-    double jx = M00 * dx + M01 * dy, jy = M10 * dx + M11 * dy;
-    if (fwd) {
-      jx += dk[2 * k] * m.isx;
-      jy += dk[2 * k + 1] * m.isy;
-    }
-    F[col] = jx;
-    F[NF + col] = jy;
-  }
+  double M[4], dk[8];
+  obs_core(m, t, e, ox, oy, r, M, dk, ml_adjust, any_dist);
+  F[0] = M[0];
+  F[NF + 0] = M[2];
+  F[1] = M[1];
+  F[NF + 1] = M[3];
+  F[2] = fma(M[0], e[2], M[1] * e[3]);
+  F[NF + 2] = fma(M[2], e[2], M[3] * e[3]);
+  obs_lens_columns<NC, NRAD>(m, t, e, M, dk, F + 3, F + NF + 3, ml_adjust, any_dist);
 }
 
 // Rebuild the NC+1-feature Gram sums (layout of FeatDims<NC>: Q lower triangle row-major, then h) from the NC-feature

@@ -68,6 +68,19 @@ __device__ __forceinline__ void block_reduce_store_rows(double* vals, double* ou
   __syncthreads();
 }
 
+constexpr int kFlushRows = 8;  // rows between two checks of the running product of the Cauchy sums
+
+// 1 / x for finite x >= 1 (the Cauchy sum 1 + s / a^2): hardware seed (2^-20 or better) + two Newton steps, no range
+// checks and no slow path, i.e. no branch inside the evaluation step. Within 1 ulp of the correctly rounded quotient.
+__device__ __forceinline__ double rcp_ge1(double x) {
+  double y;
+  asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // volatile: stays where it is called (not sunk into a branch)
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 // first round whose first row is >= row
 __device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ step_base, int R, int64_t row) {
   int lo = 0, hi = R;  // answer in [0, R]
@@ -78,7 +91,9 @@ __device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ ste
   return lo;
 }
 
-template <int NC, int NRAD, int L>
+// FLAGS: -1 = the model flags are read at run time (L > 1: small problems); else bit 0 = micro-lens adjustment, bit 1 =
+// robust loss, compiled in (L = 1: the evaluation step becomes one basic block).
+template <int NC, int NRAD, int L, int FLAGS>
 __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   const LmState* st = d.st;
   if (st->done || st->eval_skip) return;
@@ -98,8 +113,11 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   double2* tiles = reinterpret_cast<double2*>(dyn + NVL * 128);    // [4 warps][2][8][kLensRow]
   double2* ring_o = tiles + 4 * 2 * 8 * kLensRow;                  // [4 warps][3][32] observations of rows s, s+1, s+2
   int32_t* ring_l = reinterpret_cast<int32_t*>(ring_o + 4 * 3 * 32);  // [4 warps][3][32] their lens ids
+  double* tc_save = reinterpret_cast<double*>(ring_l + 4 * 3 * 32);    // [10][128] per-thread track coefficients
 #pragma unroll
   for (int v = 0; v < NVL; ++v) pers[v * 128 + threadIdx.x] = 0.0;
+  for (int i = threadIdx.x; i < 4 * 2 * 8 * kLensRow; i += 128) tiles[i] = make_double2(0.0, 0.0);  // padding lanes read it
+  for (int i = threadIdx.x; i < 4 * 3 * 32; i += 128) ring_l[i] = -1;  // no row yet
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,7 +132,9 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   const int32_t* __restrict__ s_lid = d.s_lid;
   const int32_t* __restrict__ step_base = d.step_base;
   double* __restrict__ recs = d.rec[cand];
-  const bool robust = cm.robust != 0;
+  const bool robust = FLAGS >= 0 ? (FLAGS & 2) != 0 : cm.robust != 0;
+  const bool ml_adjust = FLAGS >= 0 ? (FLAGS & 1) != 0 : cm.ml_adjust != 0;
+  constexpr bool any_dist = NC > 5;
   const double loss_c = cm.loss_c, half_b = 0.5 * cm.loss_b;
   double cost = 0.0;
   double camacc[2] = {0.0, 0.0};  // L == 1: this lane's two entries of the camera block (see the end of a round)
@@ -127,16 +147,17 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   int row = R > 0 ? step_base[r_begin] : 0;
   const int row_end = R > 0 ? step_base[r_end] : 0;
 
-  // cooperative gather of the lens entries of one row: 8 consecutive lanes fetch the 8 chunks of one entry
+  // cooperative gather of the lens entries of one row: 8 consecutive lanes fetch the 8 chunks of one entry. The lens ids
+  // of the 8 lanes come straight from the ring slot (two broadcast LDS.128); a slot holds -1 until its row has landed.
   const int chunk = lane & 7, lane8 = lane & ~7;
-  auto gather_row = [&](int lid, double2* buf) {
+  auto gather_row = [&](const int32_t* slot_ids /* the warp's 32 ids of that row */, double2* buf) {
+    const int4 a = *reinterpret_cast<const int4*>(slot_ids + lane8), b = *reinterpret_cast<const int4*>(slot_ids + lane8 + 4);
+    const int ids[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int src = lane8 + k;
-      const int lk = __shfl_sync(0xffffffffu, lid, src);
-      if (lk >= 0) cp_async_ca16(buf + chunk * kLensRow + src, lens2 + (size_t)lk * 8 + chunk);
-    }
+    for (int k = 0; k < 8; ++k)
+      if (ids[k] >= 0) cp_async_ca16(buf + chunk * kLensRow + lane8 + k, lens2 + (size_t)ids[k] * 8 + chunk);
   };
+  int32_t* warp_l = ring_l + warp * (3 * 32);
 
   // Software pipeline, all through cp.async (no register rotation: the compiler turns rotated load targets into moves
   // right behind the loads, which puts the full memory latency back on the critical path):
@@ -148,12 +169,18 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
       __pipeline_memcpy_async(my_l + (rw % 3) * 32, s_lid + (size_t)rw * 32 + lane, 4);
     }
   };
+  // inside the row loop (row_end >= 1): no branch, the rows behind the warp's last one re-fetch that one
+  auto fetch_row_clamped = [&](int rw) {
+    const int src = min(rw, row_end - 1);
+    __pipeline_memcpy_async(my_o + (rw % 3) * 32, s_obs + (size_t)src * 32 + lane, 16);
+    __pipeline_memcpy_async(my_l + (rw % 3) * 32, s_lid + (size_t)src * 32 + lane, 4);
+  };
   fetch_row(row);
   fetch_row(row + 1);
   __pipeline_commit();
   __pipeline_wait_prior(0);
   __syncwarp();
-  gather_row(row < row_end ? my_l[(row % 3) * 32] : -1, tile + (row & 1) * (8 * kLensRow));
+  gather_row(warp_l + (row % 3) * 32, tile + (row & 1) * (8 * kLensRow));
   __pipeline_commit();
 
   for (int r = r_begin; r < r_end; ++r) {
@@ -165,21 +192,33 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
 #pragma unroll
     for (int v = 0; v < NG9; ++v) g[v] = 0.0;
     double prod = 1.0;
-    TrackCtx tc;
+    // Only (wp, kl) of the track context are read per observation; the ten coefficients of the expansion wait in shared
+    // memory until the end of the track instead of occupying twenty registers through the row loop.
+    double t_wpx, t_wpy, t_kl;
     {
+      TrackCtx tc0;
       const int p = d.trk_point[t], f = d.trk_frame[t];
       double Pc[3];
       track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
-      track_setup(cm, Pc, tc);
+      track_setup(cm, Pc, tc0);
+      t_wpx = tc0.wpx;
+      t_wpy = tc0.wpy;
+      t_kl = tc0.kl;
+      double* sv = tc_save + threadIdx.x;
+      sv[0 * 128] = tc0.Px; sv[1 * 128] = tc0.Py; sv[2 * 128] = tc0.a1; sv[3 * 128] = tc0.g1;
+      sv[4 * 128] = tc0.af; sv[5 * 128] = tc0.bf; sv[6 * 128] = tc0.ab; sv[7 * 128] = tc0.bb;
+      sv[8 * 128] = tc0.aB; sv[9 * 128] = tc0.bB;
     }
-    for (int m = 0; m < nsteps; ++m) {
+    // One row: wait for its copies, read it from shared memory, queue the copies of the rows behind it, and turn it into
+    // (features, residual, weight). Straight-line: a padding lane (lens id -1) reads a stale but finite tile entry (the
+    // tile starts zeroed) and gets weight 0.
+    auto row_features = [&](double* F, double* rr, double& w) {
       __pipeline_wait_prior(0);  // this lane's copies for rows row (lens) and row + 1 (observation) have landed ...
       __syncwarp();              // ... and so have everybody else's; nobody still reads what is refilled next
       // Read everything this step needs from shared memory BEFORE queueing the next copies: the load/store unit is in
       // order, an LDS issued behind the ten LDGSTS below would wait for all of them (measured: 10% of the kernel on
       // the first use of lid_c).
       const int lid_c = my_l[(row % 3) * 32];
-      const int lid_next = row + 1 < row_end ? my_l[((row + 1) % 3) * 32] : -1;
       const double2 o_c = my_o[(row % 3) * 32];
       double e[kLensStride];
       {
@@ -191,38 +230,70 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
           e[2 * k + 1] = v2.y;
         }
       }
-      gather_row(lid_next, tile + ((row + 1) & 1) * (8 * kLensRow));
-      fetch_row(row + 2);
+      gather_row(warp_l + ((row + 1) % 3) * 32, tile + ((row + 1) & 1) * (8 * kLensRow));
+      fetch_row_clamped(row + 2);
       __pipeline_commit();
-      if (lid_c >= 0) {
-        double rr[2], F[2 * NF9];
-        obs_features9<NC, NRAD>(cm, tc, e, o_c.x, o_c.y, rr, F);
-        const double s = rr[0] * rr[0] + rr[1] * rr[1];
-        double w = 1.0;
-        if (robust) {
-          const double sum = 1.0 + s * loss_c;
-          w = 1.0 / sum;  // rho'
-          prod *= sum;
-          if (prod > 1e200) {  // keep the running product finite whatever the residuals are
-            cost += half_b * log(prod);
-            prod = 1.0;
-          }
-        } else {
-          cost += 0.5 * s;
-        }
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < NF9; ++a) {
-          const double wx = w * F[a], wy = w * F[NF9 + a];  // row a of the weighted features, live for this row only
-#pragma unroll
-          for (int b = 0; b <= a; ++b) {
-            g[q] = fma(wx, F[b], fma(wy, F[NF9 + b], g[q]));
-            ++q;
-          }
-          g[NQ9 + a] = fma(wx, rr[0], fma(wy, rr[1], g[NQ9 + a]));
-        }
+      // The copies must be ISSUED here, a whole row of arithmetic ahead of their wait. Nothing below depends on them, so
+      // inside one basic block the assembler's scheduler is free to sink them to the end of the step (measured: 42% of all
+      // stall samples on the wait at the top); a warp-level barrier is a point it does not move memory operations across.
+      __syncwarp();
+      TrackCtx tc;
+      tc.wpx = t_wpx;
+      tc.wpy = t_wpy;
+      tc.kl = t_kl;
+      obs_features9<NC, NRAD>(cm, tc, e, o_c.x, o_c.y, rr, F, ml_adjust, any_dist);
+      const bool live = lid_c >= 0;
+      const double s = rr[0] * rr[0] + rr[1] * rr[1];
+      if (robust) {
+        const double sum = live ? fma(s, loss_c, 1.0) : 1.0;
+        prod *= sum;
+        const double w0 = rcp_ge1(sum);  // rho'
+        w = live ? w0 : 0.0;
+      } else {
+        w = live ? 1.0 : 0.0;
+        cost = fma(0.5 * w, s, cost);
       }
       ++row;
+    };
+    auto gram = [&](const double* F, const double* rr, double w) {
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < NF9; ++a) {
+        const double wx = w * F[a], wy = w * F[NF9 + a];  // row a of the weighted features, live for this row only
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          g[q] = fma(wx, F[b], fma(wy, F[NF9 + b], g[q]));
+          ++q;
+        }
+        g[NQ9 + a] = fma(wx, rr[0], fma(wy, rr[1], g[NQ9 + a]));
+      }
+    };
+    // Software pipeline over the rows of the round: the Gram update of row m (54 independent chains) and the feature
+    // chain of row m + 1 (long and narrow) sit in ONE basic block, so each hides the other's latency.
+    double Fc[2 * NF9], rc[2], wc;
+    row_features(Fc, rc, wc);
+    for (int m = 1; m < nsteps; ++m) {
+      double Fn[2 * NF9], rn[2], wn;
+      row_features(Fn, rn, wn);
+      gram(Fc, rc, wc);
+#pragma unroll
+      for (int k = 0; k < 2 * NF9; ++k) Fc[k] = Fn[k];
+      rc[0] = rn[0];
+      rc[1] = rn[1];
+      wc = wn;
+      // keep the running product finite: kFlushRows factors of at most 1 + |r|^2 / a^2 each
+      if (robust && (m % kFlushRows) == 0 && prod > 1e100) {
+        cost += half_b * log(prod);
+        prod = 1.0;
+      }
+    }
+    gram(Fc, rc, wc);
+    TrackCtx tc;
+    {
+      const double* sv = tc_save + threadIdx.x;
+      tc.Px = sv[0 * 128]; tc.Py = sv[1 * 128]; tc.a1 = sv[2 * 128]; tc.g1 = sv[3 * 128];
+      tc.af = sv[4 * 128]; tc.bf = sv[5 * 128]; tc.ab = sv[6 * 128]; tc.bb = sv[7 * 128];
+      tc.aB = sv[8 * 128]; tc.bB = sv[9 * 128];
     }
     if (robust) cost += half_b * log(prod);
     if (L > 1) {
@@ -385,27 +456,37 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
 template <int NC, int L>
 constexpr int rows_smem_bytes() {
   return (L == 1 ? 0 : ((NC * (NC + 1) / 2 + NC + 1) + L - 1) / L) * 128 * (int)sizeof(double) + 4 * 2 * 8 * kLensRow * (int)sizeof(double2) +
-         4 * 3 * 32 * ((int)sizeof(double2) + (int)sizeof(int32_t));
+         4 * 3 * 32 * ((int)sizeof(double2) + (int)sizeof(int32_t)) + 10 * 128 * (int)sizeof(double);
 }
 
 template <int NC, int NRAD>
 static void launch_rows_nc(const Dev& d, int L, int grid, cudaStream_t s) {
   switch (L) {
-    case 1: k_eval_rows<NC, NRAD, 1><<<grid, 128, rows_smem_bytes<NC, 1>(), s>>>(d); break;
-    case 2: k_eval_rows<NC, NRAD, 2><<<grid, 128, rows_smem_bytes<NC, 2>(), s>>>(d); break;
-    case 4: k_eval_rows<NC, NRAD, 4><<<grid, 128, rows_smem_bytes<NC, 4>(), s>>>(d); break;
-    case 8: k_eval_rows<NC, NRAD, 8><<<grid, 128, rows_smem_bytes<NC, 8>(), s>>>(d); break;
-    default: k_eval_rows<NC, NRAD, 16><<<grid, 128, rows_smem_bytes<NC, 16>(), s>>>(d); break;
+    case 1:
+      switch (((d.config & 0x800u) ? 1 : 0) | ((d.config & 0x200u) ? 2 : 0)) {
+        case 0: k_eval_rows<NC, NRAD, 1, 0><<<grid, 128, rows_smem_bytes<NC, 1>(), s>>>(d); break;
+        case 1: k_eval_rows<NC, NRAD, 1, 1><<<grid, 128, rows_smem_bytes<NC, 1>(), s>>>(d); break;
+        case 2: k_eval_rows<NC, NRAD, 1, 2><<<grid, 128, rows_smem_bytes<NC, 1>(), s>>>(d); break;
+        default: k_eval_rows<NC, NRAD, 1, 3><<<grid, 128, rows_smem_bytes<NC, 1>(), s>>>(d); break;
+      }
+      break;
+    case 2: k_eval_rows<NC, NRAD, 2, -1><<<grid, 128, rows_smem_bytes<NC, 2>(), s>>>(d); break;
+    case 4: k_eval_rows<NC, NRAD, 4, -1><<<grid, 128, rows_smem_bytes<NC, 4>(), s>>>(d); break;
+    case 8: k_eval_rows<NC, NRAD, 8, -1><<<grid, 128, rows_smem_bytes<NC, 8>(), s>>>(d); break;
+    default: k_eval_rows<NC, NRAD, 16, -1><<<grid, 128, rows_smem_bytes<NC, 16>(), s>>>(d); break;
   }
 }
 
 template <int NC, int NRAD>
 static void prepare_rows_nc() {
-  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 1>());
-  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 2>());
-  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 4>());
-  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 8>());
-  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 16>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 1>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 1>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 1>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 1>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 2, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 2>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 4, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 4>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 8, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 8>());
+  cudaFuncSetAttribute(k_eval_rows<NC, NRAD, 16, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes<NC, 16>());
 }
 
 void prepare_rows_kernels() {

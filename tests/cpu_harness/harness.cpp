@@ -62,7 +62,7 @@ static void eval_all(const lfba_problem* pb, const CamModel& m, const double* vi
       {  // what the fused kernel does: NC features (f2 dropped), Gram weighted as (w f_a).f_b, rebuilt by gram9_expand
         constexpr int NF9 = Feat9Dims<NC>::NF, NQ9 = Feat9Dims<NC>::NQ;
         double r9[2], F9[2 * NF9], g9[NQ9 + NF9], go[NQ + NF];
-        obs_features9<NC, NRAD>(m, t, le, pb->obs_x[i], pb->obs_y[i], r9, F9);
+        obs_features9<NC, NRAD>(m, t, le, pb->obs_x[i], pb->obs_y[i], r9, F9, m.ml_adjust != 0, m.any_dist != 0);
         const double s9 = r9[0] * r9[0] + r9[1] * r9[1];
         const double w = 1.0 / (1.0 + s9 * m.loss_c);  // rho' of the Cauchy loss
         int q9 = 0;
