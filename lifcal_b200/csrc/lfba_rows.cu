@@ -47,6 +47,7 @@ __device__ __forceinline__ void cp_async_ca16(void* smem_dst, const void* gsrc) 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
+constexpr int kRing = 4;     // rows of the packed stream in flight per warp (slot = row % kRing)
 constexpr int kLensRow = 33;  // double2 per chunk row of the shared lens tile: 32 lanes + 1 pad (bank spread)
 
 template <int NV>
@@ -111,20 +112,20 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   extern __shared__ double dyn[];
   double* pers = dyn;                                              // [NVL][128]
   double2* tiles = reinterpret_cast<double2*>(dyn + NVL * 128);    // [4 warps][2][8][kLensRow]
-  double2* ring_o = tiles + 4 * 2 * 8 * kLensRow;                  // [4 warps][3][32] observations of rows s, s+1, s+2
-  int32_t* ring_l = reinterpret_cast<int32_t*>(ring_o + 4 * 3 * 32);  // [4 warps][3][32] their lens ids
-  double* tc_save = reinterpret_cast<double*>(ring_l + 4 * 3 * 32);    // [10][128] per-thread track coefficients
+  double2* ring_o = tiles + 4 * 2 * 8 * kLensRow;                  // [4 warps][kRing][32] observations of rows s .. s+3
+  int32_t* ring_l = reinterpret_cast<int32_t*>(ring_o + 4 * kRing * 32);  // [4 warps][kRing][32] their lens ids
+  double* tc_save = reinterpret_cast<double*>(ring_l + 4 * kRing * 32);    // [10][128] per-thread track coefficients
 #pragma unroll
   for (int v = 0; v < NVL; ++v) pers[v * 128 + threadIdx.x] = 0.0;
   for (int i = threadIdx.x; i < 4 * 2 * 8 * kLensRow; i += 128) tiles[i] = make_double2(0.0, 0.0);  // padding lanes read it
-  for (int i = threadIdx.x; i < 4 * 3 * 32; i += 128) ring_l[i] = -1;  // no row yet
+  for (int i = threadIdx.x; i < 4 * kRing * 32; i += 128) ring_l[i] = -1;  // no row yet
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lig = lane % L, grp = lane / L;
   double2* tile = tiles + warp * (2 * 8 * kLensRow);
-  double2* my_o = ring_o + warp * (3 * 32) + lane;
-  int32_t* my_l = ring_l + warp * (3 * 32) + lane;
+  double2* my_o = ring_o + warp * (kRing * 32) + lane;
+  int32_t* my_l = ring_l + warp * (kRing * 32) + lane;
   const double* __restrict__ frames = d.frames[cand];
   const double* __restrict__ points = d.points[cand];
   const double2* __restrict__ lens2 = reinterpret_cast<const double2*>(d.lens);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
     for (int k = 0; k < 8; ++k)
       if (ids[k] >= 0) cp_async_ca16(buf + chunk * kLensRow + lane8 + k, lens2 + (size_t)ids[k] * 8 + chunk);
   };
-  int32_t* warp_l = ring_l + warp * (3 * 32);
+  int32_t* warp_l = ring_l + warp * (kRing * 32);
 
   // Software pipeline, all through cp.async (no register rotation: the compiler turns rotated load targets into moves
   // right behind the loads, which puts the full memory latency back on the critical path):
@@ -165,29 +166,49 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   //   tile half row % 2 : the lens entries of the row's 32 lanes     (gathered one row ahead, needs that row's lens ids)
   auto fetch_row = [&](int rw) {  // coalesced: 512 B + 128 B per warp
     if (rw < row_end) {
-      __pipeline_memcpy_async(my_o + (rw % 3) * 32, s_obs + (size_t)rw * 32 + lane, 16);
-      __pipeline_memcpy_async(my_l + (rw % 3) * 32, s_lid + (size_t)rw * 32 + lane, 4);
+      __pipeline_memcpy_async(my_o + (rw % kRing) * 32, s_obs + (size_t)rw * 32 + lane, 16);
+      __pipeline_memcpy_async(my_l + (rw % kRing) * 32, s_lid + (size_t)rw * 32 + lane, 4);
     }
   };
   // inside the row loop (row_end >= 1): no branch, the rows behind the warp's last one re-fetch that one
   auto fetch_row_clamped = [&](int rw) {
     const int src = min(rw, row_end - 1);
-    __pipeline_memcpy_async(my_o + (rw % 3) * 32, s_obs + (size_t)src * 32 + lane, 16);
-    __pipeline_memcpy_async(my_l + (rw % 3) * 32, s_lid + (size_t)src * 32 + lane, 4);
+    __pipeline_memcpy_async(my_o + (rw % kRing) * 32, s_obs + (size_t)src * 32 + lane, 16);
+    __pipeline_memcpy_async(my_l + (rw % kRing) * 32, s_lid + (size_t)src * 32 + lane, 4);
   };
+  // Copy groups alternate [gather of row x + 1] [stream rows x + 3] per step; "all but the newest group" at the top of
+  // step x + 1 is then: the lens entries of row x + 1 (one step old, L1 / L2) and the stream up to row x + 2 (two steps
+  // old: DRAM latency has two rows of arithmetic to hide behind).
   fetch_row(row);
   fetch_row(row + 1);
+  fetch_row(row + 2);
   __pipeline_commit();
   __pipeline_wait_prior(0);
   __syncwarp();
-  gather_row(warp_l + (row % 3) * 32, tile + (row & 1) * (8 * kLensRow));
+  gather_row(warp_l + (row % kRing) * 32, tile + (row & 1) * (8 * kLensRow));
   __pipeline_commit();
+  __pipeline_commit();  // (empty: keeps the alternation)
 
+  // (track, point, frame) of this lane's track in the next round: two coalesced loads, one round ahead of their use
+  int t_n = 0;
+  int2 pf_n = make_int2(0, 0);
+  if (r_begin < r_end && r_begin * G + grp < d.T) {
+    t_n = d.eval_order[r_begin * G + grp];
+    pf_n = d.eval_pf[r_begin * G + grp];
+  }
   for (int r = r_begin; r < r_end; ++r) {
     const int nsteps = step_base[r + 1] - step_base[r];
     const int pos = r * G + grp;
     const bool valid = pos < d.T;
-    const int t = valid ? d.eval_order[pos] : 0;
+    const int t = t_n;
+    const int2 pf = pf_n;
+    {
+      const int pos_n = min(pos + G, d.T - 1);  // (the last round's look-ahead re-reads a valid position)
+      if (d.T > 0) {
+        t_n = d.eval_order[pos_n];
+        pf_n = d.eval_pf[pos_n];
+      }
+    }
     double g[NG9];
 #pragma unroll
     for (int v = 0; v < NG9; ++v) g[v] = 0.0;
@@ -197,9 +218,8 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
     double t_wpx, t_wpy, t_kl;
     {
       TrackCtx tc0;
-      const int p = d.trk_point[t], f = d.trk_frame[t];
       double Pc[3];
-      track_point(frames + (size_t)f * kFrameStride, points + 3 * (size_t)p, Pc);
+      track_point(frames + (size_t)pf.y * kFrameStride, points + 3 * (size_t)pf.x, Pc);
       track_setup(cm, Pc, tc0);
       t_wpx = tc0.wpx;
       t_wpy = tc0.wpy;
@@ -213,13 +233,13 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
     // (features, residual, weight). Straight-line: a padding lane (lens id -1) reads a stale but finite tile entry (the
     // tile starts zeroed) and gets weight 0.
     auto row_features = [&](double* F, double* rr, double& w) {
-      __pipeline_wait_prior(0);  // this lane's copies for rows row (lens) and row + 1 (observation) have landed ...
+      __pipeline_wait_prior(1);  // this lane's copies for rows row (lens) and row + 1 (observation) have landed ...
       __syncwarp();              // ... and so have everybody else's; nobody still reads what is refilled next
       // Read everything this step needs from shared memory BEFORE queueing the next copies: the load/store unit is in
       // order, an LDS issued behind the ten LDGSTS below would wait for all of them (measured: 10% of the kernel on
       // the first use of lid_c).
-      const int lid_c = my_l[(row % 3) * 32];
-      const double2 o_c = my_o[(row % 3) * 32];
+      const int lid_c = my_l[(row % kRing) * 32];
+      const double2 o_c = my_o[(row % kRing) * 32];
       double e[kLensStride];
       {
         const double2* lp = tile + (row & 1) * (8 * kLensRow) + lane;
@@ -230,8 +250,9 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
           e[2 * k + 1] = v2.y;
         }
       }
-      gather_row(warp_l + ((row + 1) % 3) * 32, tile + ((row + 1) & 1) * (8 * kLensRow));
-      fetch_row_clamped(row + 2);
+      gather_row(warp_l + ((row + 1) % kRing) * 32, tile + ((row + 1) & 1) * (8 * kLensRow));
+      __pipeline_commit();
+      fetch_row_clamped(row + 3);
       __pipeline_commit();
       // The copies must be ISSUED here, a whole row of arithmetic ahead of their wait. Nothing below depends on them, so
       // inside one basic block the assembler's scheduler is free to sink them to the end of the step (measured: 42% of all
@@ -456,7 +477,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
 template <int NC, int L>
 constexpr int rows_smem_bytes() {
   return (L == 1 ? 0 : ((NC * (NC + 1) / 2 + NC + 1) + L - 1) / L) * 128 * (int)sizeof(double) + 4 * 2 * 8 * kLensRow * (int)sizeof(double2) +
-         4 * 3 * 32 * ((int)sizeof(double2) + (int)sizeof(int32_t)) + 10 * 128 * (int)sizeof(double);
+         4 * kRing * 32 * ((int)sizeof(double2) + (int)sizeof(int32_t)) + 10 * 128 * (int)sizeof(double);
 }
 
 template <int NC, int NRAD>

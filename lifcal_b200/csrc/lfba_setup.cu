@@ -137,6 +137,13 @@ __global__ void k_iota(int32_t* a, int n) {
 // Sort key of the evaluation order: track length (so that the tracks of a warp round have the same number of steps),
 // then the image cell of the track's first micro lens (64 x 64 px cells, row-major): tracks that are neighbours in the
 // order gather largely the SAME lens-table entries, which the L1-allocating cp.async of k_eval_rows turns into hits.
+__global__ void k_eval_pf(const int32_t* __restrict__ eval_order, const int32_t* __restrict__ trk_point,
+                          const int32_t* __restrict__ trk_frame, int2* __restrict__ out, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const int t = eval_order[i];
+  out[i] = make_int2(trk_point[t], trk_frame[t]);
+}
 __global__ void k_track_len(const int32_t* trk_begin, const int32_t* __restrict__ lens_id, const double* __restrict__ lens_xy,
                             int32_t* len, int T) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,13 +463,15 @@ void build_index(const lfba_problem& pb, ProblemIndex& ix, cudaStream_t s, int64
   fr_count.download(ix.h_frame_count.data(), (size_t)F + 1, s);
   ix.frm_trk.alloc(T);
   ix.eval_order.alloc(T);
+  ix.eval_pf.alloc(T);
   if (T > 0) {
     DevBuf<int32_t> iota(T), keys_out(T), len(T);
     k_iota<<<grid_for(T), 256, 0, s>>>(iota.p, T);
     sort_pairs(tmp, ix.trk_frame.p, keys_out.p, iota.p, ix.frm_trk.p, (size_t)T, s, bits_for((uint64_t)(F > 0 ? F - 1 : 0)));
     k_track_len<<<grid_for(T), 256, 0, s>>>(ix.trk_begin.p, ix.lens_id_sorted, ix.lens_xy.p, len.p, T);
     sort_pairs(tmp, len.p, keys_out.p, iota.p, ix.eval_order.p, (size_t)T, s, 32, true);
-    nl += 6;
+    k_eval_pf<<<grid_for(T), 256, 0, s>>>(ix.eval_order.p, ix.trk_point.p, ix.trk_frame.p, ix.eval_pf.p, T);
+    nl += 7;
   }
   phase("csr+orders");
   // ---- co-visible frame pairs

@@ -204,6 +204,7 @@ struct ProblemIndex {
   DevBuf<int32_t> trk_point, trk_frame, trk_begin, pt_trk_begin, frm_begin, frm_trk;
   DevBuf<int32_t> pair_begin, pair_f1, pair_f2, pair_t1, pair_t2;
   DevBuf<int32_t> eval_order;
+  DevBuf<int2> eval_pf;       // (point, frame) of track eval_order[pos]
   // packed evaluation stream (build_stream): observations re-laid out in the order the fused evaluation kernel consumes
   // them. A ROUND is 32 / L length-adjacent tracks (one per L-lane group of a warp); its rows are 32 entries each:
   // entry (row, lane) = observation  lane % L + L * step  of the track of group lane / L, or padding (lens id -1).
