@@ -82,6 +82,23 @@ __device__ __forceinline__ double rcp_ge1(double x) {
   return fma(y, e, y);
 }
 
+// Where entry v of the camera block [Hcc lower triangle row-major | gc] waits at the end of k_eval_rows (one lane per
+// track): entries that involve fL, bL0, B (a per-track coefficient) in compact order (c1, c2 <= min(c1, 2)) row by row,
+// then gc(0..2), at slots 0 ..; the lens-column block (c1, c2 >= 3), then gc(3 ..), at slots 32 ...
+template <int NC>
+__device__ __forceinline__ int cam_entry_slot(int v) {
+  constexpr int NH = NC * (NC + 1) / 2, NLC = NC - 3;
+  if (v >= NH) {
+    const int c = v - NH;
+    return c < 3 ? 6 + 3 * NLC + c : 32 + NLC * (NLC + 1) / 2 + (c - 3);
+  }
+  int c1 = 0;
+  while ((c1 + 1) * (c1 + 2) / 2 <= v) ++c1;
+  const int c2 = v - c1 * (c1 + 1) / 2;
+  if (c2 >= 3) return 32 + (c1 - 3) * (c1 - 2) / 2 + (c2 - 3);
+  return c1 < 3 ? c1 * (c1 + 1) / 2 + c2 : 6 + 3 * (c1 - 3) + c2;
+}
+
 // first round whose first row is >= row
 __device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ step_base, int R, int64_t row) {
   int lo = 0, hi = R;  // answer in [0, R]
@@ -138,7 +155,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   constexpr bool any_dist = NC > 5;
   const double loss_c = cm.loss_c, half_b = 0.5 * cm.loss_b;
   double cost = 0.0;
-  double camacc[2] = {0.0, 0.0};  // L == 1: this lane's two entries of the camera block (see the end of a round)
+  double camacc = 0.0;  // L == 1: this lane's compact entry of the camera block (see the end of a round)
 
   // this warp's rounds: an even split of the rows, aligned to round boundaries
   const int R = d.n_rounds;
@@ -189,6 +206,18 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   __pipeline_commit();
   __pipeline_commit();  // (empty: keeps the alternation)
 
+  // Running sums of the round's track: Gram of the NC features + their products with r. With one lane per track the
+  // block of the lens columns (features 3 ..: cx, cy, distortion) enters the camera block Hcc / gc as it is — no
+  // per-track coefficient — so those (NC-3)(NC-2)/2 + (NC-3) sums simply keep running over ALL tracks of the lane and
+  // are reduced once at the end of the kernel; only the other half is reset, expanded and reduced per round.
+  constexpr bool kPersist = L == 1;
+  constexpr int NLC = NC - 3;                         // lens columns
+  constexpr int NPER = NLC * (NLC + 1) / 2 + NLC;     // persistent sums
+  constexpr int NCMP = NV - 1 - NPER;                 // camera-block entries reduced per round (<= 27)
+  static_assert(NCMP <= 32, "one butterfly chunk");
+  double g[NG9];
+#pragma unroll
+  for (int v = 0; v < NG9; ++v) g[v] = 0.0;
   // (track, point, frame) of this lane's track in the next round: two coalesced loads, one round ahead of their use
   int t_n = 0;
   int2 pf_n = make_int2(0, 0);
@@ -209,9 +238,18 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
         pf_n = d.eval_pf[pos_n];
       }
     }
-    double g[NG9];
+    {
+      int q = 0;
 #pragma unroll
-    for (int v = 0; v < NG9; ++v) g[v] = 0.0;
+      for (int a = 0; a < NF9; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          if (!(kPersist && b >= 3)) g[q] = 0.0;
+          ++q;
+        }
+        if (!(kPersist && a >= 3)) g[NQ9 + a] = 0.0;
+      }
+    }
     double prod = 1.0;
     // Only (wp, kl) of the track context are read per observation; the ten coefficients of the expansion wait in shared
     // memory until the end of the track instead of occupying twenty registers through the row loop.
@@ -323,10 +361,10 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
 #pragma unroll
         for (int o = L / 2; o > 0; o >>= 1) g[v] += __shfl_xor_sync(0xffffffffu, g[v], o);
     }
-    double cv[L == 1 ? NV - 1 : 1];  // L == 1: camera-block contribution of this lane's track (zero for an idle lane)
+    double cv[L == 1 ? NCMP : 1];  // L == 1: camera-block contribution of this lane's track (zero for an idle lane)
     if constexpr (L == 1) {
 #pragma unroll
-      for (int v = 0; v < NV - 1; ++v) cv[v] = 0.0;
+      for (int v = 0; v < NCMP; ++v) cv[v] = 0.0;
     }
     if (valid) {
       // rebuild the sums that involve f2, then expand into the track record and the camera block; the entries are
@@ -406,63 +444,72 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
           }
         }
       } else {
-        int hh = 0;
+        // compact order (cam_entry_slot below): (c1, c2 <= min(c1, 2)) row by row, then gc of fL, bL0, B
+        int j = 0;
 #pragma unroll
         for (int c1 = 0; c1 < NC; ++c1)
 #pragma unroll
-          for (int c2 = 0; c2 <= c1; ++c2) cv[hh++] = GM::cc(tc, go, c1, c2);
+          for (int c2 = 0; c2 <= (c1 < 2 ? c1 : 2); ++c2) cv[j++] = GM::cc(tc, go, c1, c2);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          if (c < 3) {
-            double a, b;
-            GM::geo(tc, c, a, b);
-            cv[NH + c] = a * h[3] + b * h[2];
-          } else {
-            cv[NH + c] = h[c + 1];
-          }
+        for (int c = 0; c < 3; ++c) {
+          double a, b;
+          GM::geo(tc, c, a, b);
+          cv[j++] = a * h[3] + b * h[2];
         }
       }
     }
     if constexpr (L == 1) {
-      // Camera block (Hcc, gc): the 32 tracks of the round are summed by a reduce-scatter butterfly over the warp, in two
-      // chunks of 32 values; lane l ends up with entries brev5(l) and 32 + brev5(l), which it keeps in two registers for
-      // the whole kernel. (This replaced a 66 KB per-thread shared-memory accumulator: the freed space is L1 for the
+      // Camera block (Hcc, gc), the entries with a per-track coefficient: the 32 tracks of the round are summed by a
+      // reduce-scatter butterfly over the warp; lane l ends up with compact entry brev5(l), which it keeps in a register
+      // for the whole kernel. (This replaced a 66 KB per-thread shared-memory accumulator: the freed space is L1 for the
       // lens gather.) Fixed order: deterministic.
+      double v[32];
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        double v[32];
+      for (int i = 0; i < 32; ++i) v[i] = i < NCMP ? cv[i] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (32 * ch + i < NV - 1) ? cv[32 * ch + i] : 0.0;
+      for (int k = 0; k < 5; ++k) {
+        const int half = 16 >> k;
+        const bool up = (lane >> k) & 1;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const int half = 16 >> k;
-          const bool up = (lane >> k) & 1;
-#pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const double send = up ? v[i] : v[i + half];
-            const double keep = up ? v[i + half] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << k);
-          }
+        for (int i = 0; i < half; ++i) {
+          const double send = up ? v[i] : v[i + half];
+          const double keep = up ? v[i + half] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << k);
         }
-        camacc[ch] += v[0];
       }
+      camacc += v[0];
     }
   }
   __pipeline_wait_prior(0);
   if constexpr (L == 1) {
+    // wsum[warp][slot]: slots 0 .. NCMP-1 the compact entries, 32 .. 32+NPER-1 the persistent ones, 63 the cost
     __shared__ double wsum[4][64];
-    __shared__ double wcost[4];
     const int br = ((lane & 1) << 4) | ((lane & 2) << 2) | (lane & 4) | ((lane & 8) >> 2) | ((lane & 16) >> 4);
-    wsum[warp][br] = camacc[0];
-    wsum[warp][32 + br] = camacc[1];
+    wsum[warp][br] = camacc;
+    {
+      int k = 0;
+#pragma unroll
+      for (int part = 0; part < 2; ++part)
+#pragma unroll
+        for (int a = 3; a < NF9; ++a)
+#pragma unroll
+          for (int b = 3; b <= (part == 0 ? a : 3); ++b) {  // part 0: Gram (a, b >= 3) row by row; part 1: h(a)
+            double x = part == 0 ? g[a * (a + 1) / 2 + b] : g[NQ9 + a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) wsum[warp][32 + k] = x;
+            ++k;
+          }
+    }
     double c = cost;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) wcost[warp] = c;
+    if (lane == 0) wsum[warp][63] = c;
     __syncthreads();
     for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+      const int slot = v == NV - 1 ? 63 : cam_entry_slot<NC>(v);
       double s_ = 0.0;
-      for (int w = 0; w < 4; ++w) s_ += v < NV - 1 ? wsum[w][v] : wcost[w];
+      for (int w = 0; w < 4; ++w) s_ += wsum[w][slot];
       d.part_eval[(size_t)blockIdx.x * 64 + v] = s_;
     }
   } else {
