@@ -741,13 +741,17 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
   LmState* st = d.st;
   if (linear_phase_idle(st)) return;
   const int cur = st->cur;
-  const int f = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  // split index fastest: the CTAs in flight at any time cover FEW frames, whose points' records (each point is seen by a
+  // handful of neighbouring frames) are then still in L2 when the next frame asks for them
+  const int split = blockIdx.x, nsplit = gridDim.x;
   constexpr int RS = rec_stride(NC);
   constexpr int NP = 21 + 6 + 6 + 6;  // S_ff (lower 21), reduced gradient, full gradient, diag(F^T F)
   constexpr int NV = NP + 6 * NC;     // + camera-pose block
   __shared__ double fe[kFrameStride];
   __shared__ double red[4 * NV];
   __shared__ double out[NV];
+  for (int f = blockIdx.y; f < d.F; f += gridDim.y) {  // (one frame per CTA unless F exceeds the grid limit)
+  __syncthreads();
   if (threadIdx.x < kFrameStride) fe[threadIdx.x] = d.frames[cur][(size_t)f * kFrameStride + threadIdx.x];
   __syncthreads();
   double acc[NV];
@@ -888,6 +892,7 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
   if (threadIdx.x < NV) {
     if (nsplit == 1) frame_all_scatter<NC>(d, f, threadIdx.x, out[threadIdx.x]);
     else d.frame_part[((size_t)f * nsplit + split) * NV + threadIdx.x] = out[threadIdx.x];  // summed by k_frame_finish
+  }
   }
 }
 
@@ -1440,7 +1445,7 @@ int launch_assembly(const Dev& d, int frame_splits, cudaStream_t s) {
     ++launches;
   }
   if (d.refine_poses) {
-    dim3 grid(d.F, frame_splits);
+    dim3 grid(frame_splits, std::min(d.F, 65535));
     LFBA_DISPATCH_NC(d.NC, (k_frame_all<NC><<<grid, 128, 0, s>>>(d)));
     launches += 1;
     if (frame_splits > 1) {

@@ -22,7 +22,8 @@
 //     of 32) straight into a padded, double-buffered shared-memory tile, from which each lane reads its own entry with
 //     conflict-free LDS.128. About 100 instead of 280 L1TEX wavefronts per warp step, and the dependent chain
 //     lens id -> lens entry is one row ahead of its use.
-// Rounds (32 / L length-adjacent tracks, one per L-lane group) are split evenly by ROW count over the warps of the grid.
+// Rounds (32 / L length-adjacent tracks, one per L-lane group) are split evenly by cost (rows + a fixed part per round)
+// over the warps of the grid.
 #include <cuda_pipeline.h>
 
 #include <mutex>
@@ -99,12 +100,17 @@ __device__ __forceinline__ int cam_entry_slot(int v) {
   return c1 < 3 ? c1 * (c1 + 1) / 2 + c2 : 6 + 3 * (c1 - 3) + c2;
 }
 
-// first round whose first row is >= row
-__device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ step_base, int R, int64_t row) {
+// The rounds are split over the warps of the grid by COST, not by row count: a round costs its rows plus a fixed part
+// (track set-up, expansion of the Gram sums, record store, butterfly) worth about kRoundCost rows (ncu: 18% of the stall
+// samples on 125k rounds against 82% on 3.38M rows at cfg4). Tracks are sorted by length, so an even split by rows
+// gave the warps at the short end of the order several times the rounds of those at the long end, and the kernel
+// waited for them (14% of the warp slots idle). First round r whose cost prefix step_base[r] + kRoundCost r >= target:
+constexpr int kRoundCost = 6;
+__device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ step_base, int R, int64_t target) {
   int lo = 0, hi = R;  // answer in [0, R]
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (step_base[mid] < row) lo = mid + 1; else hi = mid;
+    if ((int64_t)step_base[mid] + (int64_t)kRoundCost * mid < target) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
@@ -157,11 +163,12 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   double cost = 0.0;
   double camacc = 0.0;  // L == 1: this lane's compact entry of the camera block (see the end of a round)
 
-  // this warp's rounds: an even split of the rows, aligned to round boundaries
+  // this warp's rounds: an even split of the cost, aligned to round boundaries
   const int R = d.n_rounds;
   const int64_t W = (int64_t)gridDim.x * 4, wg = (int64_t)blockIdx.x * 4 + warp;
-  const int r_begin = round_lower_bound(step_base, R, (int64_t)d.n_rows * wg / W);
-  const int r_end = round_lower_bound(step_base, R, (int64_t)d.n_rows * (wg + 1) / W);
+  const int64_t total_cost = (int64_t)d.n_rows + (int64_t)kRoundCost * R;
+  const int r_begin = round_lower_bound(step_base, R, total_cost * wg / W);
+  const int r_end = round_lower_bound(step_base, R, total_cost * (wg + 1) / W);
   int row = R > 0 ? step_base[r_begin] : 0;
   const int row_end = R > 0 ? step_base[r_end] : 0;
 
