@@ -170,6 +170,7 @@ struct Dev {
   const int32_t* pair_t2;
   int npairs;
   const int32_t* eval_order;  // track processing order of the evaluation kernel (length-sorted)
+  int round_cost;             // fixed part of a round's cost in rows (split of the rounds over the warps)
   const int2* eval_pf;        // [T] (point, frame) of track eval_order[pos]: one coalesced load per round and lane
   // packed evaluation stream (lfba_setup.cuh, build_stream): rows of 32 entries in the order k_eval_rows consumes them
   const double2* s_obs;       // [n_rows * 32]

@@ -104,9 +104,9 @@ __device__ __forceinline__ int cam_entry_slot(int v) {
 // (track set-up, expansion of the Gram sums, record store, butterfly) worth about kRoundCost rows (ncu: 18% of the stall
 // samples on 125k rounds against 82% on 3.38M rows at cfg4). Tracks are sorted by length, so an even split by rows
 // gave the warps at the short end of the order several times the rounds of those at the long end, and the kernel
-// waited for them (14% of the warp slots idle). First round r whose cost prefix step_base[r] + kRoundCost r >= target:
-constexpr int kRoundCost = 6;
-__device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ step_base, int R, int64_t target) {
+// waited for them (14% of the warp slots idle). The weight is Dev::round_cost. First round r whose cost prefix
+// step_base[r] + kRoundCost r >= target:
+__device__ __forceinline__ int round_lower_bound(const int32_t* __restrict__ step_base, int R, int64_t target, int kRoundCost) {
   int lo = 0, hi = R;  // answer in [0, R]
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   // this warp's rounds: an even split of the cost, aligned to round boundaries
   const int R = d.n_rounds;
   const int64_t W = (int64_t)gridDim.x * 4, wg = (int64_t)blockIdx.x * 4 + warp;
-  const int64_t total_cost = (int64_t)d.n_rows + (int64_t)kRoundCost * R;
-  const int r_begin = round_lower_bound(step_base, R, total_cost * wg / W);
-  const int r_end = round_lower_bound(step_base, R, total_cost * (wg + 1) / W);
+  const int64_t total_cost = (int64_t)d.n_rows + (int64_t)d.round_cost * R;
+  const int r_begin = round_lower_bound(step_base, R, total_cost * wg / W, d.round_cost);
+  const int r_end = round_lower_bound(step_base, R, total_cost * (wg + 1) / W, d.round_cost);
   int row = R > 0 ? step_base[r_begin] : 0;
   const int row_end = R > 0 ? step_base[r_end] : 0;
 

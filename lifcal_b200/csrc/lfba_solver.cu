@@ -420,6 +420,8 @@ struct Solver {
     d.trk_begin = ix.trk_begin.p; d.pt_trk_begin = ix.pt_trk_begin.p; d.frm_begin = ix.frm_begin.p;
     d.frm_trk = ix.frm_trk.p; d.pair_begin = ix.pair_begin.p; d.pair_f1 = ix.pair_f1.p; d.pair_f2 = ix.pair_f2.p;
     d.pair_t1 = ix.pair_t1.p; d.pair_t2 = ix.pair_t2.p; d.npairs = ix.npairs; d.eval_order = ix.eval_order.p; d.eval_pf = ix.eval_pf.p;
+    d.round_cost = 6;
+    if (const char* e = std::getenv("LFBA_ROUND_COST")) d.round_cost = std::max(0, std::min(64, std::atoi(e)));  // experiment
     d.s_obs = ix.s_obs.p; d.s_lid = ix.s_lid.p; d.step_base = ix.step_base.p;
     d.n_rounds = ix.n_rounds; d.n_rows = ix.n_rows; d.stream_L = ix.stream_L;
     d.pt_coupled = pt_coupled.p; d.coupled_pts = coupled_pts.p; d.pt_active = pt_active.p; d.frm_active = frm_active.p;
