@@ -669,15 +669,20 @@ __global__ void __launch_bounds__(128) k_points(Dev d) {
       acc[NH + NC + 1] += 1.0;
       for (int k = 0; k < 6; ++k) Hi[k] = 0.0;
     }
+    {  // 320-byte record, 32-byte aligned: ten 256-bit stores (forty 8-byte stores cost forty times 32 L1 wavefronts per warp)
+      double pv[kPointStride];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) pd[k] = Hi[k];
+      for (int k = 0; k < 6; ++k) pv[k] = Hi[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      pd[6 + k] = gp[k];
-      pd[9 + k] = dmp[k];
+      for (int k = 0; k < 3; ++k) {
+        pv[6 + k] = gp[k];
+        pv[9 + k] = dmp[k];
+      }
+#pragma unroll
+      for (int k = 0; k < kPointStride - 12; ++k) pv[12 + k] = k < 3 * NC ? Hcp[k] : 0.0;
+#pragma unroll
+      for (int k = 0; k < kPointStride / 4; ++k) stg256(pd + 4 * k, pv[4 * k], pv[4 * k + 1], pv[4 * k + 2], pv[4 * k + 3]);
     }
-#pragma unroll
-    for (int k = 0; k < 3 * NC; ++k) pd[12 + k] = Hcp[k];
     // camera-camera Schur term: -(Hcp Hi) Hcp^T, -(Hcp Hi) g_p
     double Tm[3 * NC];
 #pragma unroll
