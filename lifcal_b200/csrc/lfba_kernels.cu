@@ -850,46 +850,41 @@ __global__ void __launch_bounds__(128) k_frame_all(Dev d) {
         acc[27 + a] += gva;
       }
     }
-    // camera-pose block: C_t^T M_t - Hcp W_t^T
+    // camera-pose block: C_t^T M_t - Hcp W_t^T, streamed in memory order in 256-bit pieces — no register copy of the two
+    // 3 x NC blocks (they were 104 registers beside the 93 accumulators, most of the spill traffic). C is 3 x NC row-major
+    // at doubles 9 .. of the track record: value (i, c) adds C_ic m[3a + i] to entry (c, a < 3) and itself to entry
+    // (c, 3 + i). Hcp is NC x 3 at doubles 12 .. of the point record: value (c, j) subtracts Hcp_cj W[3a + j] from (c, a).
     {
-      double cc[3 * NC + 1], hc[3 * NC + 1 + ((3 * NC + 1) & 1)];  // cc[0] = rc[9]; hc = pd[12 ..]
-      cc[0] = rc[9];
-      if (RS % 4 == 0) {
-        cc[1] = rc[10];
-        cc[2] = rc[11];
-        double tmp[RS - 12 + 4];
+      static_assert(RS % 4 == 0, "records are whole 32-byte sectors");
+      auto add_c = [&](int k, double v) {  // k: index into C, compile-time after unrolling
+        const int i = k / NC, c = k - i * NC;
 #pragma unroll
-        for (int k = 3; k < RS / 4; ++k) ldg256(rcp + 4 * k, tmp + 4 * (k - 3));
+        for (int a = 0; a < 3; ++a) acc[NP + 6 * c + a] = fma(v, m[3 * a + i], acc[NP + 6 * c + a]);
+        acc[NP + 6 * c + 3 + i] += v;
+      };
+      auto sub_h = [&](int k, double v) {  // k: index into Hcp
+        const int c = k / 3, jj = k - 3 * c;
 #pragma unroll
-        for (int k = 12; k < 9 + 3 * NC; ++k) cc[k - 9] = tmp[k - 12];
-      } else if (RS % 2 == 0) {
+        for (int a = 0; a < 6; ++a) acc[NP + 6 * c + a] = fma(-v, W[3 * a + jj], acc[NP + 6 * c + a]);
+      };
+      add_c(0, rc[9]);
+      add_c(1, rc[10]);
+      add_c(2, rc[11]);
 #pragma unroll
-        for (int k = 5; k < RS / 2; ++k) {
-          const double2 v2 = __ldg(reinterpret_cast<const double2*>(rcp) + k);
-          cc[2 * k - 9] = v2.x;
-          cc[2 * k - 8] = v2.y;
-        }
-      } else {
+      for (int q = 3; q < RS / 4; ++q) {
+        double t4[4];
+        ldg256(rcp + 4 * q, t4);
 #pragma unroll
-        for (int k = 10; k < RS; ++k) cc[k - 9] = __ldg(rcp + k);
-      }
-      {  // Hcp = pd[12 ..]: 7 x 256 bit
-        double tmp[28];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) ldg256(d.pdata + (size_t)p * kPointStride + 12 + 4 * k, tmp + 4 * k);
-#pragma unroll
-        for (int k = 0; k < 3 * NC + 1; ++k) hc[k] = tmp[k];
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e - 9 < 3 * NC) add_c(4 * q + e - 9, t4[e]);
       }
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const double c0 = cc[c], c1 = cc[NC + c], c2 = cc[2 * NC + c];
-        const double h0 = hc[3 * c], h1 = hc[3 * c + 1], h2 = hc[3 * c + 2];
+      for (int q = 3; q < kPointStride / 4; ++q) {
+        double t4[4];
+        ldg256(d.pdata + (size_t)p * kPointStride + 4 * q, t4);
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          const double cm = a < 3 ? (c0 * m[3 * a] + c1 * m[3 * a + 1] + c2 * m[3 * a + 2])
-                                  : (a == 3 ? c0 : (a == 4 ? c1 : c2));
-          acc[NP + 6 * c + a] += cm - (h0 * W[3 * a] + h1 * W[3 * a + 1] + h2 * W[3 * a + 2]);
-        }
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e - 12 < 3 * NC) sub_h(4 * q + e - 12, t4[e]);
       }
     }
   }
@@ -1244,14 +1239,13 @@ __global__ void __launch_bounds__(128) k_point_step(Dev d) {
     if (d.refine_poses) {
       for (int t = d.pt_trk_begin[p]; t < d.pt_trk_begin[p + 1]; ++t) {
         double V[18];
-        {
-          const double2* V2 = reinterpret_cast<const double2*>(d.vw + (size_t)t * kVWStride);
+        {  // 144 bytes at a 32-byte aligned address: four 256-bit loads + one 128-bit
+          const double* Vp = d.vw + (size_t)t * kVWStride;
 #pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            const double2 v2 = __ldg(V2 + k);
-            V[2 * k] = v2.x;
-            V[2 * k + 1] = v2.y;
-          }
+          for (int k = 0; k < 4; ++k) ldg256(Vp + 4 * k, V + 4 * k);
+          const double2 v2 = __ldg(reinterpret_cast<const double2*>(Vp) + 8);
+          V[16] = v2.x;
+          V[17] = v2.y;
         }
         const double* yf = y + 6 * d.trk_frame[t];
 #pragma unroll
