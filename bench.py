@@ -35,9 +35,9 @@ if ROOT not in sys.path:
 # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the ncu --set full
 # capture of the same build (profiles/README.md); None where no capture exists for that workload
 # per-launch DRAM traffic and FP64 instruction counts from `ncu --set full` of this build (profiles/r02_ncu_eval_kernels_cfg4.txt)
-NCU_TRAFFIC = {"cfg4": 4.399e9}             # k_eval_rows: 3.267 GB read + 1.132 GB written
+NCU_TRAFFIC = {"cfg4": 3.788e9}             # k_eval_rows: 2.658 GB read + 1.129 GB written (profiles/r02_ncu_eval_kernels_cfg4_final.txt)
 NCU_TRAFFIC_EVAL_ONLY = {"cfg4": 3.7229e10}  # k_eval_only, live camera columns: 3.195 GB read + 34.034 GB written
-FP64_INST_PER_OBS = 262.6  # (dfma + dmul + dadd thread instructions of k_eval_rows<9,2,1>) / observations = 2.9446e10 / 112137616
+FP64_INST_PER_OBS = 227.3  # (dfma + dmul + dadd thread instructions of k_eval_rows<9,2,1,3>) / observations = 2.5492e10 / 112137616
 REC_STRIDE_NC9 = 36        # doubles per track record at NC = 9 (lfba_device.cuh rec_stride)
 METRIC = "lm_residual_jacobian_evals_per_s"
 UNIT = "M evals/s"
