@@ -225,6 +225,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
+    # The contract is ONE JSON line on stdout. Libraries write banners there (NCCL prints its version at communicator
+    # creation): everything but the final line goes to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -249,7 +259,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_scene", "oracle_mode")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "final_cost": cb["final_cost"], "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -424,7 +434,7 @@ def main():
                               warmup=1 if small else 0)
         line["cpu_baseline"] = {k: v for k, v in cb.items()
                                 if k in ("value", "unit", "cores", "kind", "sample", "lm_iters_per_s", "same_scene", "oracle_mode")}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
