@@ -100,12 +100,20 @@ def default_options(**kw) -> capi.Options:
 
 
 def solve(pa: capi.ProblemArrays, camera, views, points, options: capi.Options | None = None,
-          raise_on_failure: bool = True):
-    """lfba_solve: returns (camera17, views6F, points3P, summary dict); inputs are left untouched."""
+          raise_on_failure: bool = True, inplace: bool = False):
+    """lfba_solve: returns (camera17, views6F, points3P, summary dict). By default the inputs are left untouched (the
+    library gets copies); inplace=True hands the caller's own contiguous float64 arrays to the C ABI, which updates them
+    in place exactly like the reference's Ceres call does (src/CameraCalibration.cpp:965)."""
     L = load()
-    cam = np.array(camera, np.float64, copy=True)
-    vw = np.array(views, np.float64, copy=True)
-    pt = np.array(points, np.float64, copy=True)
+    if inplace:
+        cam, vw, pt = camera, views, points
+        for a_ in (cam, vw, pt):
+            if not (isinstance(a_, np.ndarray) and a_.dtype == np.float64 and a_.flags.c_contiguous and a_.flags.writeable):
+                raise ValueError("inplace=True needs writable C-contiguous float64 arrays")
+    else:
+        cam = np.array(camera, np.float64, copy=True)
+        vw = np.array(views, np.float64, copy=True)
+        pt = np.array(points, np.float64, copy=True)
     o = options if options is not None else default_options()
     s, rows = capi.new_summary(max(8, o.max_num_iterations + 8))
     p = pa.as_struct()

@@ -246,6 +246,17 @@ def test_max_iterations_and_idempotent_session(gpu):
     for a, b in zip(p1, p2):
         assert np.array_equal(a, b)
     ds.close()
+    # the C ABI updates the caller's arrays in place (like Ceres does through the raw pointers, :965): same bits as the
+    # copying wrapper, and the copies' sources are untouched
+    cam0, vw0, pt0 = (np.array(x, np.float64, copy=True) for x in (sc.camera_init, sc.views_init, sc.points_init))
+    cam_c, vw_c, pt_c, s_c = api.solve(sc.problem, cam0, vw0, pt0)
+    assert np.array_equal(cam0, np.asarray(sc.camera_init, np.float64)) and np.array_equal(pt0, np.asarray(sc.points_init, np.float64).ravel().reshape(pt0.shape))
+    cam_i, vw_i, pt_i, s_i = api.solve(sc.problem, cam0, vw0, pt0, inplace=True)
+    assert cam_i is cam0 and pt_i is pt0
+    assert np.array_equal(cam_i, cam_c) and np.array_equal(vw_i, vw_c) and np.array_equal(pt_i, pt_c)
+    assert s_i["final_cost"] == s_c["final_cost"]
+    with pytest.raises(ValueError):
+        api.solve(sc.problem, cam0.astype(np.float32), vw0, pt0, inplace=True)
 
 
 def test_full_size_properties_cfg3(gpu):
