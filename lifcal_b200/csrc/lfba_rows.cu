@@ -48,7 +48,8 @@ __device__ __forceinline__ void cp_async_ca16(void* smem_dst, const void* gsrc) 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
-constexpr int kRing = 4;     // rows of the packed stream in flight per warp (slot = row % kRing)
+constexpr int kRing = 4;     // rows of the packed stream in flight per warp (slot = row % kRing; a power of two)
+__device__ __forceinline__ int ring_slot(int row) { return (int)((unsigned)row & (unsigned)(kRing - 1)); }  // row >= 0
 constexpr int kLensRow = 33;  // double2 per chunk row of the shared lens tile: 32 lanes + 1 pad (bank spread)
 
 template <int NV>
@@ -190,15 +191,15 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   //   tile half row % 2 : the lens entries of the row's 32 lanes     (gathered one row ahead, needs that row's lens ids)
   auto fetch_row = [&](int rw) {  // coalesced: 512 B + 128 B per warp
     if (rw < row_end) {
-      __pipeline_memcpy_async(my_o + (rw % kRing) * 32, s_obs + (size_t)rw * 32 + lane, 16);
-      __pipeline_memcpy_async(my_l + (rw % kRing) * 32, s_lid + (size_t)rw * 32 + lane, 4);
+      __pipeline_memcpy_async(my_o + ring_slot(rw) * 32, s_obs + (size_t)rw * 32 + lane, 16);
+      __pipeline_memcpy_async(my_l + ring_slot(rw) * 32, s_lid + (size_t)rw * 32 + lane, 4);
     }
   };
   // inside the row loop (row_end >= 1): no branch, the rows behind the warp's last one re-fetch that one
   auto fetch_row_clamped = [&](int rw) {
     const int src = min(rw, row_end - 1);
-    __pipeline_memcpy_async(my_o + (rw % kRing) * 32, s_obs + (size_t)src * 32 + lane, 16);
-    __pipeline_memcpy_async(my_l + (rw % kRing) * 32, s_lid + (size_t)src * 32 + lane, 4);
+    __pipeline_memcpy_async(my_o + ring_slot(rw) * 32, s_obs + (size_t)src * 32 + lane, 16);
+    __pipeline_memcpy_async(my_l + ring_slot(rw) * 32, s_lid + (size_t)src * 32 + lane, 4);
   };
   // Copy groups alternate [gather of row x + 1] [stream rows x + 3] per step; "all but the newest group" at the top of
   // step x + 1 is then: the lens entries of row x + 1 (one step old, L1 / L2) and the stream up to row x + 2 (two steps
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
   __pipeline_commit();
   __pipeline_wait_prior(0);
   __syncwarp();
-  gather_row(warp_l + (row % kRing) * 32, tile + (row & 1) * (8 * kLensRow));
+  gather_row(warp_l + ring_slot(row) * 32, tile + (row & 1) * (8 * kLensRow));
   __pipeline_commit();
   __pipeline_commit();  // (empty: keeps the alternation)
 
@@ -283,8 +284,8 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
       // Read everything this step needs from shared memory BEFORE queueing the next copies: the load/store unit is in
       // order, an LDS issued behind the ten LDGSTS below would wait for all of them (measured: 10% of the kernel on
       // the first use of lid_c).
-      const int lid_c = my_l[(row % kRing) * 32];
-      const double2 o_c = my_o[(row % kRing) * 32];
+      const int lid_c = my_l[ring_slot(row) * 32];
+      const double2 o_c = my_o[ring_slot(row) * 32];
       double e[kLensStride];
       {
         const double2* lp = tile + (row & 1) * (8 * kLensRow) + lane;
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(128, 2) k_eval_rows(Dev d) {
           e[2 * k + 1] = v2.y;
         }
       }
-      gather_row(warp_l + ((row + 1) % kRing) * 32, tile + ((row + 1) & 1) * (8 * kLensRow));
+      gather_row(warp_l + ring_slot(row + 1) * 32, tile + ((row + 1) & 1) * (8 * kLensRow));
       __pipeline_commit();
       fetch_row_clamped(row + 3);
       __pipeline_commit();
