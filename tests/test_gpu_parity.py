@@ -180,6 +180,21 @@ def test_model_variants_match_oracle(gpu):
                 _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread, name=f"variant:{cfg:#06x}")
 
 
+def test_model_variants_one_lane_per_track(gpu, monkeypatch):
+    """Large problems run the fused evaluation kernel with ONE lane per track and the model flags compiled in (24
+    instantiations: 6 distortion variants x mlAdj x robust); small scenes would pick several lanes per track, so the
+    lane count is forced here (LFBA_LANES, read when the solver is created). Same bar as everywhere: the oracle's rows."""
+    monkeypatch.setenv("LFBA_LANES", "1")
+    for nrad in (0, 1, 2):
+        for tan in (0, capi.CFG_TANGENTIAL):
+            for extra in (0, capi.CFG_MLADJ, capi.CFG_ROBUST, capi.CFG_ROBUST | capi.CFG_MLADJ):
+                cfg = nrad | tan | extra | capi.CFG_REFINE_POSES | capi.CFG_REFINE_POINTS
+                sc = capi.make_scene(None, n_points=160, n_frames=5, seed=300 + nrad + tan + extra, config=cfg)
+                cam, vw, pt, s = api.solve(sc.problem, sc.camera_init, sc.views_init, sc.points_init)
+                spread, (ocam, ovw, opt_, os_) = _oracle_spread(sc.problem, (sc.camera_init, sc.views_init, sc.points_init))
+                _assert_solution_parity(s, (cam, vw, pt), os_, (ocam, ovw, opt_), sc, spread, name=f"one_lane:{cfg:#06x}")
+
+
 def test_windowed_scene_partitioned_reduced_solve(gpu):
     # 64 frames, window 4: the reduced system is banded (3 frames) + border, long enough for the partitioned
     # factorisation (lfba_chol_part.cu: 4 partitions, 3 separators). Same answer as the oracle's dense LLT.
