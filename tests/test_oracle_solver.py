@@ -145,6 +145,66 @@ def test_oracle_minimum_agrees_with_an_independent_solver(built):
     assert ref.cost * (1 - 1e-9) <= s2["final_cost"] <= ref.cost * (1 + 1e-3)
 
 
+def test_oracle_robust_minimum_agrees_with_an_independent_solver(built):
+    """The same independent check for the ROBUST cost 0.5 sum rho(|r_i|^2), rho = CauchyLoss(0.5) per 2-vector block
+    (src/CameraCalibration.cpp:905): scipy minimises 0.5 sum |g(s_i) r_i|^2 with g = sqrt(rho(s) / s), which is the very
+    same function, on residuals and Jacobians of the REFERENCE's own functor (oracle/_ref). Ceres' Corrector (incl. its
+    second-order term) only shapes the path; the minimum it must reach is this one."""
+    from scipy.optimize import least_squares
+    cfg = 2 | capi.CFG_TANGENTIAL | capi.CFG_MLADJ | capi.CFG_ROBUST | capi.CFG_REFINE_POSES | capi.CFG_REFINE_POINTS
+    sc = capi.make_scene(None, n_points=40, n_frames=4, seed=321, config=cfg)
+    pa = sc.problem
+    F, P, n = pa.n_frames, pa.n_points, pa.n_obs
+    live, b = 9, 0.25  # a = 0.5: rho(s) = b log(1 + s / b)
+
+    def unpack(x):
+        cam = sc.camera_init.copy()
+        cam[:live] = x[:live]
+        return cam, x[live:live + 6 * F].copy(), x[live + 6 * F:].copy()
+
+    def g_and_dg(sq):
+        sq = np.maximum(sq, 1e-300)
+        h = b * np.log1p(sq / b) / sq
+        dh = (1.0 / (1.0 + sq / b) * sq - b * np.log1p(sq / b)) / (sq * sq)
+        small = sq < 1e-8  # series: h = 1 - s / (2 b) + ...
+        h = np.where(small, 1.0 - sq / (2 * b), h)
+        dh = np.where(small, -1.0 / (2 * b), dh)
+        g = np.sqrt(h)
+        return g, dh / (2.0 * g)
+
+    def fun(x):
+        cam, vw, pt = unpack(x)
+        r = ob.evaluate(pa, cam, vw, pt, jacobians=False, use_ref=True)["residuals"]
+        g, _ = g_and_dg(np.sum(r * r, axis=1))
+        return (g[:, None] * r).ravel()
+
+    def jac(x):
+        cam, vw, pt = unpack(x)
+        e = ob.evaluate(pa, cam, vw, pt, use_ref=True)
+        r = e["residuals"]
+        g, dg = g_and_dg(np.sum(r * r, axis=1))
+        J = np.zeros((2 * n, live + 6 * F + 3 * P))
+        rows = np.arange(2 * n).reshape(n, 2)
+        for i in range(n):
+            f, p = pa.frame_idx[i], pa.point_idx[i]
+            Ji = np.zeros((2, J.shape[1]))
+            Ji[:, :live] = e["jac_camera"][i][:, :live]
+            Ji[:, live + 6 * f:live + 6 * f + 6] = e["jac_view"][i]
+            Ji[:, live + 6 * F + 3 * p:live + 6 * F + 3 * p + 3] = e["jac_point"][i]
+            J[rows[i]] = (g[i] * np.eye(2) + 2.0 * dg[i] * np.outer(r[i], r[i])) @ Ji  # d (g(s) r) = (g I + 2 g' r r^T) dr
+        return J
+
+    x0 = np.concatenate([sc.camera_init[:live], sc.views_init, sc.points_init])
+    ref = least_squares(fun, x0, jac=jac, method="trf", x_scale="jac", ftol=1e-14, xtol=1e-14, gtol=1e-14, max_nfev=300)
+    # the transformed problem IS the robust cost: check against the oracle's own cost function at the start point
+    e0 = ob.evaluate(pa, sc.camera_init, sc.views_init, sc.points_init, jacobians=False)
+    assert abs(0.5 * np.sum(fun(x0) ** 2) - e0["cost"]) <= 1e-12 * e0["cost"]
+    o = ob.default_options(function_tolerance=1e-13, parameter_tolerance=1e-13, max_num_iterations=300)
+    _, _, _, s = ob.solve(pa, sc.camera_init, sc.views_init, sc.points_init, options=o, threads=2)
+    assert ref.cost > 0 and ref.cost < 0.9 * e0["cost"]
+    assert abs(s["final_cost"] - ref.cost) <= 1e-6 * ref.cost, (s["final_cost"], ref.cost)
+
+
 @pytest.mark.parametrize("scene", [
     dict(n_points=200, n_frames=6, n_constraints=2, seed=7),                       # constraints + coupled points
     dict(n_points=300, n_frames=24, window=4, seed=5, order=1),                    # windowed (cfg4 family)
